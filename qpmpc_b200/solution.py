@@ -1,0 +1,31 @@
+"""Duck-typed stand-in for ``qpsolvers.Solution``.
+
+The reference's ``Plan`` reads only ``.found`` and ``.x`` of the solver's
+return value (``qpmpc/plan.py:36-37``).  ``qpsolvers`` is not a dependency of
+this engine, so the CUDA path returns this small record instead; it carries the
+same two fields plus what the kernel reports per instance.
+"""
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+
+@dataclass
+class Solution:
+    """Result of one condensed-QP solve.
+
+    Attributes:
+        found: True if the solver converged (kernel status 0).
+        x: Stacked input vector U (N * nu), or None when not found.
+        z: Multipliers of ``G u <= h`` (m), when requested.
+        obj: Optimal cost ``0.5 u'Pu + q'u``, when available.
+        extras: ``{"status", "iters"}`` from the kernel.
+    """
+
+    found: bool
+    x: Optional[np.ndarray] = None
+    z: Optional[np.ndarray] = None
+    obj: Optional[float] = None
+    extras: Dict[str, Any] = field(default_factory=dict)
