@@ -1,0 +1,162 @@
+/*
+ * qpmpc_b200.h -- C ABI of the B200 batched linear-MPC engine.
+ *
+ * This is the drop-in boundary for ONE path of stephane-caron/qpmpc: condense
+ * an MPC problem into a dense QP and solve it.  Citations are relative to the
+ * reference tree (/root/reference):
+ *
+ *   qpmpc_b200_solve / _solve_host   replace   qpmpc/solve_mpc.py:42-43
+ *       MPCQP(problem)                      (qpmpc/mpc_qp.py:39-122)
+ *       qpsolvers.solve_problem(P,q,G,h)    (qpmpc/solve_mpc.py:43)
+ *     and hand back what Plan reads (qpmpc/plan.py:36-39): found + x.
+ *   qpmpc_b200_condense              replaces  qpmpc/mpc_qp.py:53-122,139-163
+ *     (fields P, q, G, h, Phi, Psi, phi_last, psi_last of MPCQP).
+ *   qpmpc_b200_integrate             replaces  qpmpc/mpc_problem.py:316-335
+ *     (MPCProblem.integrate, what Plan.states calls, qpmpc/plan.py:100-109).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Device entry
+ * points take DEVICE pointers owned by the caller (row-major, batch-major,
+ * contiguous), run asynchronously on the given cudaStream_t (passed as void*)
+ * and allocate nothing.  Nothing throws; every function returns
+ *   0   success,
+ *  <0   bad argument / unsupported shape (QPMPC_B200_E*),
+ *  >0   a cudaError_t.
+ * Per-instance outcome is written to status[batch]:
+ *   0 solved, 1 iteration limit, 2 infeasible, 3 Hessian not positive definite;
+ * Plan.is_empty  <=>  status != 0  (qpmpc/plan.py:36,45-48).  U of an
+ * unsolved instance is filled with NaN.
+ *
+ * Operand modes say how each of A, B, C, D, e is laid out:
+ *   ABSENT            pointer ignored (C or D "None": the null matrix,
+ *                     qpmpc/mpc_problem.py:55-60)
+ *   SHARED_LTI        [r, c]          one matrix for all instances and steps
+ *   SHARED_LTV        [N, r, c]       per step, shared by all instances
+ *   BATCH_LTI         [batch, r, c]   per instance, time-invariant
+ *   BATCH_LTV         [batch, N, r, c]
+ * with (r, c) = (nx,nx) A, (nx,nu) B, (nc,nx) C, (nc,nu) D, (nc,1) e.
+ * x0 is [batch, nx] (BATCH) or [nx] (SHARED); goal likewise; targets is
+ * [batch, N*nx] or [N*nx]; goal / targets may be ABSENT.
+ */
+#ifndef QPMPC_B200_H
+#define QPMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPMPC_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    QPMPC_B200_ABSENT = 0,
+    QPMPC_B200_SHARED_LTI = 1,
+    QPMPC_B200_SHARED_LTV = 2,
+    QPMPC_B200_BATCH_LTI = 3,
+    QPMPC_B200_BATCH_LTV = 4
+};
+enum { QPMPC_B200_VEC_ABSENT = 0, QPMPC_B200_VEC_SHARED = 1, QPMPC_B200_VEC_BATCH = 2 };
+enum { QPMPC_B200_F64 = 0, QPMPC_B200_F32 = 1 };
+enum { QPMPC_B200_ACTIVE_SET = 0, QPMPC_B200_PDIP = 1 };
+
+enum {
+    QPMPC_B200_STATUS_SOLVED = 0,
+    QPMPC_B200_STATUS_MAX_ITER = 1,
+    QPMPC_B200_STATUS_INFEASIBLE = 2,
+    QPMPC_B200_STATUS_NOT_SPD = 3
+};
+
+enum {
+    QPMPC_B200_EINVAL = -1,      /* null/contradictory argument */
+    QPMPC_B200_ESHAPE = -2,      /* N*nu or N*nc beyond the compiled kernels */
+    QPMPC_B200_EWEIGHT = -3,     /* w_u <= 0, or neither w_t nor w_x set */
+    QPMPC_B200_ENODEVICE = -4,   /* no CUDA device / not sm_100 */
+    QPMPC_B200_EUNSUPPORTED = -5 /* combination not implemented */
+};
+
+/* Problem descriptor.  Mirrors the constructor of MPCProblem
+ * (qpmpc/mpc_problem.py:88-102) plus solver settings. */
+typedef struct qpmpc_b200_desc {
+    int32_t batch;      /* number of independent MPC instances */
+    int32_t N;          /* nb_timesteps */
+    int32_t nx, nu, nc; /* state, input, per-step inequality dimensions */
+    int32_t dtype;      /* QPMPC_B200_F64 / _F32: type of every operand and of U */
+    int32_t mode_A, mode_B, mode_C, mode_D, mode_e;
+    int32_t mode_x0, mode_goal, mode_targets;
+    int32_t has_wt;     /* terminal_cost_weight is not None */
+    int32_t has_wx;     /* stage_state_cost_weight is not None */
+    double w_t, w_x, w_u;
+    int32_t method;     /* QPMPC_B200_ACTIVE_SET (default, exact) or _PDIP */
+    int32_t max_iter;   /* <= 0: library default */
+    double tol;         /* PDIP stopping tolerance; <= 0: library default */
+    int32_t paired;     /* 1: every C_k, D_k, has rows [M; -M] (two-sided
+                           bounds); lets the kernel keep one row per pair.
+                           0 is always valid. */
+    int32_t reserved;
+} qpmpc_b200_desc;
+
+/* Inputs of the path (device pointers for the device entry points, host
+ * pointers for qpmpc_b200_solve_host).  Element type is desc->dtype. */
+typedef struct qpmpc_b200_operands {
+    const void *A, *B, *C, *D, *e;
+    const void *x0, *goal, *targets;
+} qpmpc_b200_operands;
+
+/* Outputs.  U [batch, N*nu] and status [batch] are required; iters [batch]
+ * (solver iterations) and Z [batch, N*nc] (multipliers of G u <= h, >= 0) are
+ * optional (NULL to skip). */
+typedef struct qpmpc_b200_outputs {
+    void *U;
+    int32_t *status;
+    int32_t *iters;
+    void *Z;
+} qpmpc_b200_outputs;
+
+/* Condense + solve on the device.  Replaces qpmpc/solve_mpc.py:42-43 for a
+ * whole batch.  Asynchronous on `stream`. */
+int qpmpc_b200_solve(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                     const qpmpc_b200_outputs *out, void *stream);
+
+/* Same with HOST buffers: copies operands to the device (pinned staging,
+ * buffers cached inside the library per calling thread), solves, copies the
+ * outputs back and synchronises.  This is the call a host program that has no
+ * device memory of its own binds. */
+int qpmpc_b200_solve_host(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                          const qpmpc_b200_outputs *out, int device);
+
+/* Condensed QP fields of MPCQP (qpmpc/mpc_qp.py:28-37,93-117), per instance.
+ * Any output may be NULL.  P [batch,n,n], q [batch,n], G [batch,m,n],
+ * h [batch,m], Phi [batch,N*nx,nx], Psi [batch,N*nx,n], phi_last [batch,nx,nx],
+ * psi_last [batch,nx,n]; n = N*nu, m = N*nc. */
+typedef struct qpmpc_b200_qp_fields {
+    void *P, *q, *G, *h, *Phi, *Psi, *phi_last, *psi_last;
+} qpmpc_b200_qp_fields;
+
+int qpmpc_b200_condense(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                        const qpmpc_b200_qp_fields *out, void *stream);
+
+/* X[b, k+1] = A_k X[b, k] + B_k U[b, k], X[b, 0] = x0[b]; X is [batch, N+1, nx].
+ * Replaces MPCProblem.integrate (qpmpc/mpc_problem.py:316-335).  Uses
+ * desc->mode_A/B/x0, in->A/B/x0; U is [batch, N*nu]. */
+int qpmpc_b200_integrate(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                         const void *U, void *X, void *stream);
+
+/* Scratch the device entry points need from the caller: none (0) today; kept
+ * in the ABI so a future kernel can ask for it without a signature change. */
+size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *desc);
+
+/* Largest n = N*nu and m = N*nc the compiled kernels accept for this dtype. */
+int qpmpc_b200_max_vars(int dtype);
+int qpmpc_b200_max_rows(int dtype, int n);
+
+/* Number of kernels this library has launched in this process. */
+long long qpmpc_b200_launch_count(void);
+
+const char *qpmpc_b200_strerror(int code);
+int qpmpc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPMPC_B200_H */

@@ -1,0 +1,125 @@
+"""NumPy model of the iteration the CUDA kernel runs.  TEST INFRASTRUCTURE ONLY.
+
+Batched (vectorised over instances) Mehrotra predictor-corrector interior
+point for   min 1/2 u'Pu + q'u  s.t.  G u <= h   followed by an active-set
+polish, written to mirror ``qpmpc_b200/csrc/mpc_kernels.cuh`` step for step so
+that an algorithmic disagreement between the kernel and the exact active-set
+oracle (``mpc_oracle.c``) can be told apart from an indexing bug.  It replaces
+the third-party solve at ``qpmpc/solve_mpc.py:43`` (reference tree) in tests
+that cross-check the Goldfarb-Idnani oracle with an independent method.
+
+Newton step (slack form  G u + s = h, s, z >= 0,  W = z / s):
+    (P + G'WG) du = -r_d - G'(W r_p - r_c / s)
+    ds = -r_p - G du ;  dz = -(r_c + z ds) / s
+with r_d = P u + q + G'z, r_p = G u + s - h, r_c = s z (predictor) or
+s z + ds_a dz_a - sigma mu (corrector).  One step length for primal and dual,
+so r_d and r_p shrink by exactly (1 - alpha).
+
+Polish: rows with z > s are taken as the active set A; the equality QP on A is
+solved by a few proximal multiplier steps that reuse the same factorisation
+code,  (P + G_A' G_A / delta) u+ = -q - G_A'(lam - h_A / delta),
+lam+ = lam + (G_A u+ - h_A) / delta.  The polished point is kept only if it is
+primal feasible and its multipliers are non-negative to tolerance.
+"""
+
+import numpy as np
+
+
+def _solve(L, b):
+    y = np.linalg.solve(L, b[..., None])
+    return np.linalg.solve(np.swapaxes(L, -1, -2), y)[..., 0]
+
+
+def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
+               delta=1e-7):
+    """Solve a batch of QPs.  P [B,n,n], q [B,n], G [B,m,n], h [B,m].
+
+    Returns dict(U, z, status, iters): status 0 solved, 1 max_iter, 2 numerical.
+    """
+    P, q, G, h = (np.asarray(a, dtype=np.float64) for a in (P, q, G, h))
+    B, m, n = G.shape
+    u = np.zeros((B, n))
+    # start: u = 0, s = max(h, 1), z = 1
+    s = np.maximum(h - np.einsum("bmn,bn->bm", G, u), 1.0)
+    z = np.ones((B, m))
+    status = np.full(B, 1, dtype=np.int32)
+    iters = np.zeros(B, dtype=np.int32)
+    active = np.ones(B, dtype=bool)
+    hscale = np.maximum(1.0, np.abs(h).max(axis=1))
+    qscale = np.maximum(1.0, np.abs(q).max(axis=1))
+    for it in range(max_iter):
+        r_d = np.einsum("bij,bj->bi", P, u) + q + np.einsum("bmn,bm->bn", G, z)
+        r_p = np.einsum("bmn,bn->bm", G, u) + s - h
+        mu = (s * z).sum(axis=1) / m
+        done = (
+            (np.abs(r_d).max(axis=1) <= tol * qscale)
+            & (np.abs(r_p).max(axis=1) <= tol * hscale)
+            & (mu <= tol)
+        )
+        newly = active & done
+        status[newly] = 0
+        active &= ~done
+        if not active.any():
+            break
+        iters[active] += 1
+        W = z / s
+        H = P + np.einsum("bmi,bm,bmj->bij", G, W, G)
+        try:
+            L = np.linalg.cholesky(H)
+        except np.linalg.LinAlgError:
+            status[active] = 2
+            break
+        # predictor
+        rhs = -r_d - np.einsum("bmn,bm->bn", G, W * r_p - z)
+        du = _solve(L, rhs)
+        ds = -r_p - np.einsum("bmn,bn->bm", G, du)
+        dz = -(s * z + z * ds) / s
+        a_aff = _step(s, z, ds, dz, 1.0)
+        mu_aff = ((s + a_aff[:, None] * ds) * (z + a_aff[:, None] * dz)).sum(axis=1) / m
+        sigma = (mu_aff / mu) ** 3
+        # corrector
+        r_c = s * z + ds * dz - (sigma * mu)[:, None]
+        rhs = -r_d - np.einsum("bmn,bm->bn", G, W * r_p - r_c / s)
+        du = _solve(L, rhs)
+        ds = -r_p - np.einsum("bmn,bn->bm", G, du)
+        dz = -(r_c + z * ds) / s
+        alpha = _step(s, z, ds, dz, 0.99)
+        alpha = np.where(active, alpha, 0.0)[:, None]
+        u = u + alpha * du
+        s = s + alpha * ds
+        z = z + alpha * dz
+    if polish:
+        up, zp, ok = _polish(P, q, G, h, u, s, z, polish_steps, delta)
+        ok &= status == 0
+        u = np.where(ok[:, None], up, u)
+        z = np.where(ok[:, None], zp, z)
+    return dict(U=u, z=z, status=status, iters=iters)
+
+
+def _step(s, z, ds, dz, frac):
+    """Largest alpha in (0, 1] keeping s + alpha ds, z + alpha dz positive."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a_s = np.where(ds < 0, -s / ds, np.inf).min(axis=1)
+        a_z = np.where(dz < 0, -z / dz, np.inf).min(axis=1)
+    return np.minimum(1.0, frac * np.minimum(a_s, a_z))
+
+
+def _polish(P, q, G, h, u, s, z, steps, delta):
+    act = z > s
+    Wa = act / delta
+    H = P + np.einsum("bmi,bm,bmj->bij", G, Wa, G)
+    L = np.linalg.cholesky(H)
+    lam = np.where(act, z, 0.0)
+    up = u
+    for _ in range(steps):
+        rhs = -q - np.einsum("bmn,bm->bn", G, np.where(act, lam - h / delta, 0.0))
+        up = _solve(L, rhs)
+        viol = np.einsum("bmn,bn->bm", G, up) - h
+        lam = np.where(act, lam + viol / delta, 0.0)
+    viol = np.einsum("bmn,bn->bm", G, up) - h
+    hscale = np.maximum(1.0, np.abs(h).max(axis=1))[:, None]
+    zscale = np.maximum(1.0, np.abs(lam).max(axis=1))[:, None]
+    ok = (viol <= 1e-9 * hscale).all(axis=1) & (lam >= -1e-9 * zscale).all(axis=1)
+    r_d = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
+    ok &= np.abs(r_d).max(axis=1) <= 1e-9 * np.maximum(1.0, np.abs(q).max(axis=1))
+    return up, lam, ok

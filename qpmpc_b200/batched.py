@@ -1,0 +1,443 @@
+"""Tensor-native batched surface: many independent MPC problems in one call.
+
+The reference solves one problem per ``solve_mpc`` call (``qpmpc/solve_mpc.py:
+42-44``, reference tree).  Here a :class:`BatchedMPCProblem` holds B problems
+of one shape as CUDA tensors and :func:`solve_mpc_batch` runs the fused
+condense + QP kernel on all of them; :class:`BatchedPlan` is the batched
+counterpart of ``Plan`` (``qpmpc/plan.py:18-109``).
+
+Operand layouts (see ``include/qpmpc_b200.h``): every matrix operand is either
+shared by the batch or per instance, and either time-invariant or per step:
+
+    ndim 2  [r, c]          shared,       time-invariant
+    ndim 3  [B, r, c]       per instance, time-invariant   (default for ndim 3)
+    ndim 3  [N, r, c]       shared,       per step         (name listed in ``ltv``)
+    ndim 4  [B, N, r, c]    per instance, per step
+
+``ineq_vector`` follows the same rule with r = nc and no trailing axis.
+"""
+
+import ctypes
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from .exceptions import BackendError, ProblemDefinitionError, StateError
+from .mpc_problem import MPCProblem
+
+_TORCH_DTYPE = {_capi.F64: torch.float64, _capi.F32: torch.float32}
+_DTYPE_CODE = {torch.float64: _capi.F64, torch.float32: _capi.F32}
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise BackendError(
+            "the qpmpc_b200 engine needs a CUDA device (sm_100a); there is no CPU path"
+        )
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedMPCProblem:
+    """B linear MPC problems sharing (N, nx, nu, nc), stored as tensors.
+
+    Argument names follow ``MPCProblem`` (``qpmpc/mpc_problem.py:88-102``).
+    Tensors are moved to ``device`` / ``dtype`` and made contiguous once, here.
+
+    Args:
+        ltv: Names among ``"A", "B", "C", "D", "e"`` whose 3-D (2-D for e)
+            tensor is a per-step stack shared by the batch rather than a
+            per-instance stack.
+        batch_size: Needed only when no operand carries the batch axis.
+    """
+
+    def __init__(
+        self,
+        transition_state_matrix,
+        transition_input_matrix,
+        ineq_state_matrix,
+        ineq_input_matrix,
+        ineq_vector,
+        nb_timesteps: int,
+        terminal_cost_weight: Optional[float],
+        stage_state_cost_weight: Optional[float],
+        stage_input_cost_weight: float,
+        initial_state=None,
+        goal_state=None,
+        target_states=None,
+        ltv: Iterable[str] = (),
+        batch_size: Optional[int] = None,
+        dtype: torch.dtype = torch.float64,
+        device=None,
+    ) -> None:
+        if stage_input_cost_weight <= 0.0:
+            raise ProblemDefinitionError("the input weight must be positive")
+        if terminal_cost_weight is None and stage_state_cost_weight is None:
+            raise ProblemDefinitionError(
+                "set a terminal cost weight, a stage state cost weight, or both"
+            )
+        if dtype not in _DTYPE_CODE:
+            raise ProblemDefinitionError("dtype must be torch.float64 or torch.float32")
+        self.device = _require_cuda(device)
+        self.dtype = dtype
+        self.nb_timesteps = int(nb_timesteps)
+        self.terminal_cost_weight = terminal_cost_weight
+        self.stage_state_cost_weight = stage_state_cost_weight
+        self.stage_input_cost_weight = float(stage_input_cost_weight)
+        self._ltv = set(ltv)
+        N = self.nb_timesteps
+
+        A = self._tensor(transition_state_matrix)
+        B = self._tensor(transition_input_matrix)
+        self.state_dim = int(A.shape[-1])
+        self.input_dim = int(B.shape[-1])
+        nx, nu = self.state_dim, self.input_dim
+        e = self._tensor(ineq_vector)
+        self.ineq_dim = int(e.shape[-1]) if e is not None else 0
+        nc = self.ineq_dim
+        C = self._tensor(ineq_state_matrix)
+        D = self._tensor(ineq_input_matrix)
+
+        self._batch = batch_size
+        self.A, self.mode_A = self._matrix("A", A, (nx, nx), False)
+        self.B, self.mode_B = self._matrix("B", B, (nx, nu), False)
+        self.C, self.mode_C = self._matrix("C", C, (nc, nx), True)
+        self.D, self.mode_D = self._matrix("D", D, (nc, nu), True)
+        self.e, self.mode_e = self._matrix("e", e, (nc,), nc == 0)
+        self.x0 = self.goal = self.targets = None
+        self.mode_x0 = self.mode_goal = self.mode_targets = _capi.VEC_ABSENT
+        if initial_state is not None:
+            self.update_initial_state(initial_state)
+        if goal_state is not None:
+            self.update_goal_state(goal_state)
+        if target_states is not None:
+            self.update_target_states(target_states)
+        if self._batch is None:
+            raise ProblemDefinitionError(
+                "no operand carries a batch axis: pass batch_size explicitly"
+            )
+
+    # -- packing -----------------------------------------------------------
+
+    def _tensor(self, value) -> Optional[torch.Tensor]:
+        if value is None:
+            return None
+        if not isinstance(value, torch.Tensor):
+            value = torch.as_tensor(np.asarray(value))
+        return value.to(device=self.device, dtype=self.dtype).contiguous()
+
+    def _set_batch(self, b: int, what: str) -> None:
+        if self._batch is None:
+            self._batch = int(b)
+        elif self._batch != int(b):
+            raise ProblemDefinitionError(
+                f"{what} has batch {b}, other operands have {self._batch}"
+            )
+
+    def _matrix(self, name, t, item, optional):
+        if t is None:
+            if not optional:
+                raise ProblemDefinitionError(f"operand {name} is required")
+            return None, _capi.ABSENT
+        k = len(item)
+        N = self.nb_timesteps
+        if tuple(t.shape[-k:]) != tuple(item):
+            raise ProblemDefinitionError(
+                f"operand {name} has trailing shape {tuple(t.shape[-k:])}, expected {item}"
+            )
+        lead = t.shape[:-k]
+        if len(lead) == 0:
+            return t, _capi.SHARED_LTI
+        if len(lead) == 1 and name in self._ltv:
+            if lead[0] != N:
+                raise ProblemDefinitionError(f"operand {name}: per-step stack needs {N} steps")
+            return t, _capi.SHARED_LTV
+        if len(lead) == 1:
+            self._set_batch(lead[0], f"operand {name}")
+            return t, _capi.BATCH_LTI
+        if len(lead) == 2:
+            if lead[1] != N:
+                raise ProblemDefinitionError(f"operand {name}: per-step stack needs {N} steps")
+            self._set_batch(lead[0], f"operand {name}")
+            return t, _capi.BATCH_LTV
+        raise ProblemDefinitionError(f"operand {name} has too many axes: {tuple(t.shape)}")
+
+    def _vector(self, value, size, what):
+        t = self._tensor(value)
+        if t.ndim <= 1:
+            if t.numel() != size:
+                raise StateError(f"{what} has {t.numel()} entries, expected {size}")
+            return t.reshape(size), _capi.VEC_SHARED
+        t = t.reshape(t.shape[0], -1)
+        if t.shape[1] != size:
+            raise StateError(f"{what} has {t.shape[1]} entries per instance, expected {size}")
+        self._set_batch(t.shape[0], what)
+        return t.contiguous(), _capi.VEC_BATCH
+
+    # -- state setters (mpc_problem.py:247-295) ------------------------------
+
+    def update_initial_state(self, initial_state) -> None:
+        """Set x_0: [B, nx] per instance or [nx] shared."""
+        self.x0, self.mode_x0 = self._vector(initial_state, self.state_dim, "initial state")
+
+    def update_goal_state(self, goal_state) -> None:
+        """Set the terminal goal: [B, nx] or [nx]."""
+        self.goal, self.mode_goal = self._vector(goal_state, self.state_dim, "goal state")
+
+    def update_target_states(self, target_states) -> None:
+        """Set the stage targets for x_0..x_{N-1}: [B, N*nx] (or [B, N, nx]) or [N*nx]."""
+        t = self._tensor(target_states)
+        size = self.state_dim * self.nb_timesteps
+        if t.ndim == 3:
+            t = t.reshape(t.shape[0], -1)
+        elif t.ndim == 2 and t.numel() == size:
+            t = t.reshape(size)
+        self.targets, self.mode_targets = self._vector(t, size, "target states")
+
+    @property
+    def batch_size(self) -> int:
+        return int(self._batch)
+
+    @property
+    def nb_vars(self) -> int:
+        return self.nb_timesteps * self.input_dim
+
+    @property
+    def nb_rows(self) -> int:
+        return self.nb_timesteps * self.ineq_dim
+
+    # -- C ABI views ----------------------------------------------------------
+
+    def desc(self, method: int = _capi.ACTIVE_SET, max_iter: int = 0, tol: float = 0.0) -> _capi.Desc:
+        if self.x0 is None:
+            raise ProblemDefinitionError("initial state is undefined")  # mpc_qp.py:49-51
+        d = _capi.Desc()
+        d.batch, d.N = self.batch_size, self.nb_timesteps
+        d.nx, d.nu, d.nc = self.state_dim, self.input_dim, self.ineq_dim
+        d.dtype = _DTYPE_CODE[self.dtype]
+        d.mode_A, d.mode_B, d.mode_C = self.mode_A, self.mode_B, self.mode_C
+        d.mode_D, d.mode_e = self.mode_D, self.mode_e
+        d.mode_x0, d.mode_goal, d.mode_targets = self.mode_x0, self.mode_goal, self.mode_targets
+        d.has_wt = self.terminal_cost_weight is not None
+        d.has_wx = self.stage_state_cost_weight is not None
+        d.w_t = float(self.terminal_cost_weight or 0.0)
+        d.w_x = float(self.stage_state_cost_weight or 0.0)
+        d.w_u = self.stage_input_cost_weight
+        d.method, d.max_iter, d.tol = method, int(max_iter), float(tol)
+        return d
+
+    def operands(self) -> _capi.Operands:
+        return _capi.Operands(
+            _ptr(self.A), _ptr(self.B), _ptr(self.C), _ptr(self.D), _ptr(self.e),
+            _ptr(self.x0), _ptr(self.goal), _ptr(self.targets),
+        )
+
+    # -- construction from host-side problems ---------------------------------
+
+    @classmethod
+    def from_problems(cls, problems: Sequence[MPCProblem], dtype=torch.float64, device=None):
+        """Stack host-side ``MPCProblem`` objects of one shape (convenience;
+        for throughput build the tensors directly)."""
+        first = problems[0]
+        N = first.nb_timesteps
+        packed = [pack_problem(p) for p in problems]
+
+        def stack(key):
+            vals = [pk[key] for pk in packed]
+            if vals[0] is None:
+                return None
+            return np.stack(vals)
+
+        obj = cls(
+            stack("A"), stack("B"), stack("C"), stack("D"), stack("e"), N,
+            first.terminal_cost_weight, first.stage_state_cost_weight,
+            first.stage_input_cost_weight,
+            initial_state=stack("x0"), goal_state=stack("goal"),
+            target_states=stack("targets"), dtype=dtype, device=device,
+        )
+        obj.row_map = packed[0]["row_map"]
+        return obj
+
+
+def pack_problem(problem: MPCProblem) -> dict:
+    """Canonical arrays of one ``MPCProblem``: A, B [N?, ...] etc.
+
+    LTV operands (Python lists, ``mpc_problem.py:178-180``) become [N, r, c]
+    stacks.  Ragged per-step row counts are padded to the largest ``nc`` with
+    all-zero rows whose bound is huge, and ``row_map`` lists the real rows.
+    """
+    N = problem.nb_timesteps
+    if problem.initial_state is None:
+        raise ProblemDefinitionError("initial state is undefined")  # mpc_qp.py:49-51
+    e_steps = [np.asarray(problem.get_ineq_vector(k), dtype=float).reshape(-1) for k in range(N)]
+    ncs = [ek.shape[0] for ek in e_steps]
+    nc = max(ncs)
+    ragged = len(set(ncs)) > 1
+    BIG = 1e30
+
+    def mat(op, cols):
+        if op is None:
+            return None
+        ltv = isinstance(op, list)
+        if not ltv and not ragged:
+            return np.asarray(op, dtype=float).reshape(-1, cols) if cols else np.asarray(op, dtype=float)
+        out = np.zeros((N, nc, cols))
+        for k in range(N):
+            blk = op[k] if ltv else op
+            if blk is not None:
+                blk = np.asarray(blk, dtype=float).reshape(-1, cols)
+                out[k, : blk.shape[0]] = blk
+        return out
+
+    def dyn(op):
+        return np.stack([np.asarray(a, dtype=float) for a in op]) if isinstance(op, list) else np.asarray(op, dtype=float)
+
+    nx, nu = problem.state_dim, problem.input_dim
+    A = dyn(problem.transition_state_matrix)
+    B = dyn(problem.transition_input_matrix)
+    B = B.reshape((N, nx, nu)) if isinstance(problem.transition_input_matrix, list) else B.reshape((nx, nu))
+    C, D = problem.ineq_state_matrix, problem.ineq_input_matrix
+    if isinstance(C, list) and any(c is None for c in C):
+        C = [np.zeros((ncs[k], nx)) if c is None else c for k, c in enumerate(C)]
+    if isinstance(D, list) and any(d is None for d in D):
+        D = [np.zeros((ncs[k], nu)) if d is None else d for k, d in enumerate(D)]
+    Cm, Dm = mat(C, nx), mat(D, nu)
+    if isinstance(problem.ineq_vector, list) or ragged:
+        e = np.full((N, nc), BIG)
+        for k in range(N):
+            e[k, : ncs[k]] = e_steps[k]
+    else:
+        e = e_steps[0]
+    row_map = [k * nc + r for k in range(N) for r in range(ncs[k])]
+    return dict(A=A, B=B, C=Cm, D=Dm, e=e, x0=problem.initial_state,
+                goal=problem.goal_state, targets=problem.target_states,
+                nc=nc, row_map=row_map)
+
+
+def problem_to_batch(problem: MPCProblem, dtype=torch.float64, device=None) -> BatchedMPCProblem:
+    """One host-side ``MPCProblem`` as a batch of one (what ``solve_mpc`` does)."""
+    pk = pack_problem(problem)
+    names = [k for k in ("A", "B", "C", "D", "e")
+             if pk[k] is not None and pk[k].ndim == (2 if k == "e" else 3)]
+    obj = BatchedMPCProblem(
+        pk["A"], pk["B"], pk["C"], pk["D"], pk["e"], problem.nb_timesteps,
+        problem.terminal_cost_weight, problem.stage_state_cost_weight,
+        problem.stage_input_cost_weight, initial_state=pk["x0"],
+        goal_state=pk["goal"], target_states=pk["targets"], ltv=names,
+        batch_size=1, dtype=dtype, device=device,
+    )
+    obj.row_map = pk["row_map"]
+    return obj
+
+
+class BatchedPlan:
+    """Result of :func:`solve_mpc_batch` -- batched ``Plan`` (``qpmpc/plan.py``).
+
+    Attributes:
+        problem: The batched problem that was solved.
+        inputs: U, tensor [B, N, nu]; rows of unsolved instances are NaN.
+        status: int32 [B]: 0 solved, 1 iteration limit, 2 infeasible, 3 not SPD.
+        iters: int32 [B] solver iterations.
+        multipliers: [B, N*nc] or None.
+    """
+
+    def __init__(self, problem, U, status, iters, Z=None):
+        self.problem = problem
+        self.inputs = U.view(problem.batch_size, problem.nb_timesteps, problem.input_dim)
+        self.status = status
+        self.iters = iters
+        self.multipliers = Z
+        self._states = None
+
+    @property
+    def found(self) -> torch.Tensor:
+        """bool [B]: ``qpsol.found`` per instance."""
+        return self.status == 0
+
+    @property
+    def is_empty(self) -> torch.Tensor:
+        """bool [B]: batched ``Plan.is_empty`` (``plan.py:45-48``)."""
+        return self.status != 0
+
+    @property
+    def first_input(self) -> torch.Tensor:
+        """u_0 of every instance, [B, nu] (``plan.py:50-62``)."""
+        return self.inputs[:, 0, :]
+
+    @property
+    def states(self) -> torch.Tensor:
+        """X [B, N+1, nx], integrated on the device on first access
+        (``plan.py:81-109`` -> ``mpc_problem.py:316-335``)."""
+        if self._states is None:
+            self._states = integrate_batch(self.problem, self.inputs)
+        return self._states
+
+
+def solve_mpc_batch(
+    problem: BatchedMPCProblem,
+    method: str = "active_set",
+    max_iter: int = 0,
+    tol: float = 0.0,
+    return_multipliers: bool = False,
+    out: Optional[torch.Tensor] = None,
+) -> BatchedPlan:
+    """Condense and solve every instance of ``problem`` on its CUDA device.
+
+    Asynchronous on the current CUDA stream, like any torch op.
+    """
+    lib = _capi.load()
+    meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}.get(method)
+    if meth is None:
+        raise ProblemDefinitionError(f"unknown method {method!r}")
+    desc = problem.desc(meth, max_iter, tol)
+    B, n, m = problem.batch_size, problem.nb_vars, problem.nb_rows
+    with torch.cuda.device(problem.device):
+        U = out if out is not None else torch.empty((B, n), dtype=problem.dtype, device=problem.device)
+        status = torch.empty(B, dtype=torch.int32, device=problem.device)
+        iters = torch.empty(B, dtype=torch.int32, device=problem.device)
+        Z = torch.empty((B, m), dtype=problem.dtype, device=problem.device) if return_multipliers else None
+        outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), _ptr(Z))
+        ops = problem.operands()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        rc = lib.qpmpc_b200_solve(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), stream)
+    _capi.check(rc, "qpmpc_b200_solve")
+    return BatchedPlan(problem, U, status, iters, Z)
+
+
+def condense_batch(problem: BatchedMPCProblem, fields: Sequence[str] = ("P", "q", "G", "h")) -> dict:
+    """Materialise condensed-QP fields of every instance (MPCQP, batched)."""
+    lib = _capi.load()
+    desc = problem.desc()
+    B, N = problem.batch_size, problem.nb_timesteps
+    n, m, nx = problem.nb_vars, problem.nb_rows, problem.state_dim
+    shapes = dict(P=(B, n, n), q=(B, n), G=(B, m, n), h=(B, m), Phi=(B, N * nx, nx),
+                  Psi=(B, N * nx, n), phi_last=(B, nx, nx), psi_last=(B, nx, n))
+    with torch.cuda.device(problem.device):
+        out = {k: torch.zeros(shapes[k], dtype=problem.dtype, device=problem.device) for k in fields}
+        qf = _capi.QPFields(*[_ptr(out.get(k)) for k in
+                              ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")])
+        ops = problem.operands()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        rc = lib.qpmpc_b200_condense(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(qf), stream)
+    _capi.check(rc, "qpmpc_b200_condense")
+    return out
+
+
+def integrate_batch(problem: BatchedMPCProblem, inputs: torch.Tensor) -> torch.Tensor:
+    """X [B, N+1, nx] from x0 and U on the device (batched ``integrate``)."""
+    lib = _capi.load()
+    desc = problem.desc()
+    B, N, nx = problem.batch_size, problem.nb_timesteps, problem.state_dim
+    U = inputs.reshape(B, -1).to(problem.dtype).contiguous()
+    with torch.cuda.device(problem.device):
+        X = torch.empty((B, N + 1, nx), dtype=problem.dtype, device=problem.device)
+        ops = problem.operands()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        rc = lib.qpmpc_b200_integrate(ctypes.byref(desc), ctypes.byref(ops), _ptr(U), _ptr(X), stream)
+    _capi.check(rc, "qpmpc_b200_integrate")
+    return X

@@ -1,0 +1,111 @@
+// mpc_common.cuh -- parameter blocks, shared-memory layout and small device
+// helpers shared by the kernels of the batched MPC engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qpmpc {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// Operand slots in the staged-input table.
+enum { OP_A = 0, OP_B, OP_C, OP_D, OP_E, OP_X0, OP_GOAL, OP_TGT, OP_COUNT };
+
+// One staged operand: where it lives in HBM and where a CTA puts it in shared
+// memory.  `sz` elements per instance (item * N for per-step operands).
+struct OperandView {
+    const void *ptr;   // nullptr: absent
+    int sz;            // elements staged per instance (or once if shared)
+    int step;          // element stride between steps in the staged copy (0: LTI)
+    int per_instance;  // 1: [batch, sz] in HBM; 0: one copy shared by the batch
+    int smem_off;      // element offset inside the CTA's input region
+};
+
+struct SolveParams {
+    int batch, N, nx, nu, nc, n, m;
+    OperandView op[OP_COUNT];
+    int has_wt, has_wx;  // weight "is not None": term enters P (mpc_qp.py:102,104)
+    int q_wt, q_wx;      // term enters q (weight > 1e-10 and reference present)
+    double w_t, w_x, w_u;
+    int max_iter;
+    double tol;
+    // shared-memory geometry (elements of T), computed by the host
+    int inst_stride;     // per-instance work region
+    int psi_elems;       // size of the runtime-sized psi/J region
+    int input_elems;     // CTA-level input region
+    // outputs
+    void *U;
+    int *status;
+    int *iters;
+    void *Z;
+    // condensed-field dump (condense kernel only)
+    void *P, *q, *G, *h, *Phi, *Psi, *phi_last, *psi_last;
+};
+
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
+__device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
+__device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
+__device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
+__device__ __forceinline__ float sqrt_(float v) { return sqrtf(v); }
+__device__ __forceinline__ double abs_(double v) { return fabs(v); }
+__device__ __forceinline__ float abs_(float v) { return fabsf(v); }
+
+template <typename T> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+    static constexpr double viol_eps = 1e-13;  // "is this row violated" (oracle/mpc_oracle.c)
+    static constexpr double dep_eps = 1e-24;   // |d2|^2 <= dep_eps |d|^2: dependent normal
+};
+template <> struct Num<float> {
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+    static constexpr float viol_eps = 2e-6f;
+    static constexpr float dep_eps = 1e-10f;
+};
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy, completion reported to an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace qpmpc

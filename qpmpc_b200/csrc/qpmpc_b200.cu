@@ -1,0 +1,391 @@
+// qpmpc_b200.cu -- C ABI of the batched MPC engine (see include/qpmpc_b200.h):
+// argument checking, kernel-variant dispatch, shared-memory geometry, and the
+// host-buffer convenience entry.  No torch, no C++ types across the boundary.
+
+#include "../../include/qpmpc_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "mpc_kernels.cuh"
+
+using namespace qpmpc;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+struct Variant {
+    int np, mr;
+    bool mreg;
+};
+
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Smallest compiled (NP, MR) that holds n variables and m constraint rows.
+bool pick_variant(int n, int m, Variant *out) {
+    static const Variant table[] = {{8, 2, true},  {8, 4, true},   {16, 2, true},
+                                    {16, 4, false}, {32, 2, false}, {32, 4, false}};
+    for (const Variant &v : table)
+        if (n <= v.np && m <= v.np * v.mr) {
+            *out = v;
+            return true;
+        }
+    return false;
+}
+
+int check_desc(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in) {
+    if (!d || !in) return QPMPC_B200_EINVAL;
+    if (d->batch < 0 || d->N <= 0 || d->nx <= 0 || d->nu <= 0 || d->nc < 0) return QPMPC_B200_EINVAL;
+    if (d->dtype != QPMPC_B200_F64 && d->dtype != QPMPC_B200_F32) return QPMPC_B200_EINVAL;
+    if (!(d->w_u > 0.0)) return QPMPC_B200_EWEIGHT;           // mpc_problem.py:104-107
+    if (!d->has_wt && !d->has_wx) return QPMPC_B200_EWEIGHT;  // mpc_problem.py:108-111
+    auto mat_ok = [](int mode, const void *p, bool optional) {
+        if (mode == QPMPC_B200_ABSENT) return optional;
+        return mode >= QPMPC_B200_SHARED_LTI && mode <= QPMPC_B200_BATCH_LTV && p != nullptr;
+    };
+    if (!mat_ok(d->mode_A, in->A, false) || !mat_ok(d->mode_B, in->B, false)) return QPMPC_B200_EINVAL;
+    if (!mat_ok(d->mode_C, in->C, true) || !mat_ok(d->mode_D, in->D, true)) return QPMPC_B200_EINVAL;
+    if (d->nc > 0 && !mat_ok(d->mode_e, in->e, false)) return QPMPC_B200_EINVAL;
+    if (d->mode_x0 == QPMPC_B200_VEC_ABSENT || !in->x0) return QPMPC_B200_EINVAL;  // mpc_qp.py:49-51
+    if (d->mode_goal != QPMPC_B200_VEC_ABSENT && !in->goal) return QPMPC_B200_EINVAL;
+    if (d->mode_targets != QPMPC_B200_VEC_ABSENT && !in->targets) return QPMPC_B200_EINVAL;
+    return 0;
+}
+
+void set_matrix(OperandView *v, int mode, const void *ptr, int item, int N) {
+    v->ptr = nullptr;
+    v->sz = v->step = v->per_instance = v->smem_off = 0;
+    if (mode == QPMPC_B200_ABSENT || item == 0) return;
+    const bool ltv = (mode == QPMPC_B200_SHARED_LTV || mode == QPMPC_B200_BATCH_LTV);
+    v->ptr = ptr;
+    v->sz = item * (ltv ? N : 1);
+    v->step = ltv ? item : 0;
+    v->per_instance = (mode == QPMPC_B200_BATCH_LTI || mode == QPMPC_B200_BATCH_LTV);
+}
+
+void set_vector(OperandView *v, int mode, const void *ptr, int size) {
+    v->ptr = nullptr;
+    v->sz = v->step = v->per_instance = v->smem_off = 0;
+    if (mode == QPMPC_B200_VEC_ABSENT) return;
+    v->ptr = ptr;
+    v->sz = size;
+    v->per_instance = (mode == QPMPC_B200_VEC_BATCH);
+}
+
+// Fill everything of SolveParams that does not depend on the kernel variant.
+void fill_params(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, SolveParams *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->batch = d->batch;
+    p->N = d->N;
+    p->nx = d->nx;
+    p->nu = d->nu;
+    p->nc = d->nc;
+    p->n = d->N * d->nu;
+    p->m = d->N * d->nc;
+    set_matrix(&p->op[OP_A], d->mode_A, in->A, d->nx * d->nx, d->N);
+    set_matrix(&p->op[OP_B], d->mode_B, in->B, d->nx * d->nu, d->N);
+    set_matrix(&p->op[OP_C], d->mode_C, in->C, d->nc * d->nx, d->N);
+    set_matrix(&p->op[OP_D], d->mode_D, in->D, d->nc * d->nu, d->N);
+    set_matrix(&p->op[OP_E], d->mode_e, in->e, d->nc, d->N);
+    set_vector(&p->op[OP_X0], d->mode_x0, in->x0, d->nx);
+    set_vector(&p->op[OP_GOAL], d->mode_goal, in->goal, d->nx);
+    set_vector(&p->op[OP_TGT], d->mode_targets, in->targets, d->N * d->nx);
+    p->has_wt = d->has_wt != 0;
+    p->has_wx = d->has_wx != 0;
+    p->w_t = d->has_wt ? d->w_t : 0.0;
+    p->w_x = d->has_wx ? d->w_x : 0.0;
+    p->w_u = d->w_u;
+    // q follows update_cost_vector (mpc_qp.py:139-149): a term needs weight >
+    // 1e-10 (mpc_problem.py:146,159); a missing goal aborts before the stage
+    // term is reached, a missing target trajectory drops only the stage term.
+    const bool t_on = d->has_wt && d->w_t > 1e-10;
+    const bool x_on = d->has_wx && d->w_x > 1e-10;
+    const bool have_goal = d->mode_goal != QPMPC_B200_VEC_ABSENT;
+    const bool have_tgt = d->mode_targets != QPMPC_B200_VEC_ABSENT;
+    p->q_wt = t_on && have_goal;
+    p->q_wx = x_on && have_tgt && !(t_on && !have_goal);
+    p->max_iter = d->max_iter > 0 ? d->max_iter : 10 * (p->n + p->m) + 50;
+    p->tol = d->tol > 0.0 ? d->tol : 1e-9;
+}
+
+// Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
+template <typename T>
+size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc) {
+    p->psi_elems = psi_region_elems(np, p->nx);
+    p->inst_stride = fixed_elems + p->psi_elems;
+    int off = 0;
+    for (int o = 0; o < OP_COUNT; ++o) {
+        OperandView &v = p->op[o];
+        if (!v.ptr) continue;
+        v.smem_off = off;
+        int elems = v.sz * (v.per_instance ? ipc : 1);
+        off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
+    }
+    p->input_elems = off;
+    return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
+}
+
+template <typename T, int NP, int MR, bool MREG>
+int launch_solve(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 2 : 1);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_solve_kernel<T, NP, MR, MREG>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int NP, int MR>
+int launch_condense(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    int wpc = 2;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_condense_kernel<T, NP, MR>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int dispatch_solve(const SolveParams &p, const Variant &v, cudaStream_t s) {
+    if (v.np == 8 && v.mr == 2) return launch_solve<T, 8, 2, true>(p, s);
+    if (v.np == 8 && v.mr == 4) return launch_solve<T, 8, 4, true>(p, s);
+    if (v.np == 16 && v.mr == 2) return launch_solve<T, 16, 2, true>(p, s);
+    if (v.np == 16 && v.mr == 4) return launch_solve<T, 16, 4, false>(p, s);
+    if (v.np == 32 && v.mr == 2) return launch_solve<T, 32, 2, false>(p, s);
+    if (v.np == 32 && v.mr == 4) return launch_solve<T, 32, 4, false>(p, s);
+    return QPMPC_B200_ESHAPE;
+}
+
+template <typename T>
+int dispatch_condense(const SolveParams &p, const Variant &v, cudaStream_t s) {
+    if (v.np == 8 && v.mr == 2) return launch_condense<T, 8, 2>(p, s);
+    if (v.np == 8 && v.mr == 4) return launch_condense<T, 8, 4>(p, s);
+    if (v.np == 16 && v.mr == 2) return launch_condense<T, 16, 2>(p, s);
+    if (v.np == 16 && v.mr == 4) return launch_condense<T, 16, 4>(p, s);
+    if (v.np == 32 && v.mr == 2) return launch_condense<T, 32, 2>(p, s);
+    if (v.np == 32 && v.mr == 4) return launch_condense<T, 32, 4>(p, s);
+    return QPMPC_B200_ESHAPE;
+}
+
+// ---- host-buffer entry: cached device buffers, one set per calling thread ----
+struct HostCache {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void *buf[OP_COUNT] = {nullptr};
+    size_t cap[OP_COUNT] = {0};
+    void *U = nullptr, *Z = nullptr;
+    int32_t *status = nullptr, *iters = nullptr;
+    size_t capU = 0, capZ = 0, capS = 0, capI = 0;
+};
+thread_local HostCache g_cache;
+
+cudaError_t ensure(void **ptr, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return cudaSuccess;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qpmpc_b200_version(void) { return QPMPC_B200_VERSION; }
+
+long long qpmpc_b200_launch_count(void) { return g_launches.load(); }
+
+size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *) { return 0; }
+
+int qpmpc_b200_max_vars(int) { return 32; }
+
+int qpmpc_b200_max_rows(int, int n) {
+    Variant v;
+    int best = -1;
+    for (int m = 128; m >= 0; m -= 8)
+        if (pick_variant(n, m, &v)) {
+            best = m;
+            break;
+        }
+    return best;
+}
+
+const char *qpmpc_b200_strerror(int code) {
+    switch (code) {
+        case 0: return "success";
+        case QPMPC_B200_EINVAL: return "invalid argument (null pointer, bad mode or dimension)";
+        case QPMPC_B200_ESHAPE: return "N*nu or N*nc exceeds the compiled kernel variants";
+        case QPMPC_B200_EWEIGHT: return "weights: need w_u > 0 and at least one of w_t, w_x";
+        case QPMPC_B200_ENODEVICE: return "no usable CUDA device";
+        case QPMPC_B200_EUNSUPPORTED: return "combination not implemented";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+int qpmpc_b200_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                     void *stream) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!out || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    if (d->method != QPMPC_B200_ACTIVE_SET) return QPMPC_B200_EUNSUPPORTED;
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.U = out->U;
+    p.status = out->status;
+    p.iters = out->iters;
+    p.Z = out->Z;
+    Variant v;
+    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);
+}
+
+int qpmpc_b200_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_qp_fields *out,
+                        void *stream) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!out) return QPMPC_B200_EINVAL;
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.P = out->P;
+    p.q = out->q;
+    p.G = out->G;
+    p.h = out->h;
+    p.Phi = out->Phi;
+    p.Psi = out->Psi;
+    p.phi_last = out->phi_last;
+    p.psi_last = out->psi_last;
+    Variant v;
+    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return d->dtype == QPMPC_B200_F64 ? dispatch_condense<double>(p, v, s) : dispatch_condense<float>(p, v, s);
+}
+
+int qpmpc_b200_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *U, void *X,
+                         void *stream) {
+    if (!d || !in || !U || !X || !in->A || !in->B || !in->x0) return QPMPC_B200_EINVAL;
+    if (d->batch < 0 || d->N <= 0 || d->nx <= 0 || d->nu <= 0) return QPMPC_B200_EINVAL;
+    if (d->mode_A == QPMPC_B200_ABSENT || d->mode_B == QPMPC_B200_ABSENT || d->mode_x0 == QPMPC_B200_VEC_ABSENT)
+        return QPMPC_B200_EINVAL;
+    if (d->batch == 0) return 0;
+    IntegrateParams p;
+    p.batch = d->batch;
+    p.N = d->N;
+    p.nx = d->nx;
+    p.nu = d->nu;
+    p.A = in->A;
+    p.B = in->B;
+    p.x0 = in->x0;
+    p.U = U;
+    p.X = X;
+    auto ltv = [](int mode) { return mode == QPMPC_B200_SHARED_LTV || mode == QPMPC_B200_BATCH_LTV; };
+    auto per = [](int mode) { return mode == QPMPC_B200_BATCH_LTI || mode == QPMPC_B200_BATCH_LTV; };
+    p.sA = ltv(d->mode_A) ? d->nx * d->nx : 0;
+    p.sB = ltv(d->mode_B) ? d->nx * d->nu : 0;
+    p.bA = per(d->mode_A) ? (long long)d->nx * d->nx * (ltv(d->mode_A) ? d->N : 1) : 0;
+    p.bB = per(d->mode_B) ? (long long)d->nx * d->nu * (ltv(d->mode_B) ? d->N : 1) : 0;
+    p.bx0 = d->mode_x0 == QPMPC_B200_VEC_BATCH ? d->nx : 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    if (d->dtype == QPMPC_B200_F64)
+        mpc_integrate_kernel<double><<<grid, threads, 0, s>>>(p);
+    else
+        mpc_integrate_kernel<float><<<grid, threads, 0, s>>>(p);
+    g_launches.fetch_add(1);
+    return (int)cudaGetLastError();
+}
+
+int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                          int device) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!out || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    if (d->batch == 0) return 0;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    HostCache &c = g_cache;
+    if (c.device != device) {
+        c = HostCache();
+        c.device = device;
+        e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
+    }
+    SolveParams p;
+    fill_params(d, in, &p);
+    const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
+    const void *host[OP_COUNT] = {in->A, in->B, in->C, in->D, in->e, in->x0, in->goal, in->targets};
+    qpmpc_b200_operands dev;
+    const void **devp[OP_COUNT] = {&dev.A, &dev.B, &dev.C, &dev.D, &dev.e, &dev.x0, &dev.goal, &dev.targets};
+    for (int o = 0; o < OP_COUNT; ++o) {
+        *devp[o] = nullptr;
+        const OperandView &v = p.op[o];
+        if (!v.ptr) continue;
+        const size_t bytes = (size_t)v.sz * (v.per_instance ? d->batch : 1) * es;
+        e = ensure(&c.buf[o], &c.cap[o], bytes);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(c.buf[o], host[o], bytes, cudaMemcpyHostToDevice, c.stream);
+        if (e != cudaSuccess) return (int)e;
+        *devp[o] = c.buf[o];
+    }
+    const size_t bU = (size_t)d->batch * p.n * es, bZ = (size_t)d->batch * p.m * es, bS = (size_t)d->batch * 4;
+    if ((e = ensure(&c.U, &c.capU, bU)) != cudaSuccess) return (int)e;
+    if ((e = ensure((void **)&c.status, &c.capS, bS)) != cudaSuccess) return (int)e;
+    qpmpc_b200_outputs dout = {c.U, c.status, nullptr, nullptr};
+    if (out->iters) {
+        if ((e = ensure((void **)&c.iters, &c.capI, bS)) != cudaSuccess) return (int)e;
+        dout.iters = c.iters;
+    }
+    if (out->Z && bZ) {
+        if ((e = ensure(&c.Z, &c.capZ, bZ)) != cudaSuccess) return (int)e;
+        dout.Z = c.Z;
+    }
+    rc = qpmpc_b200_solve(d, &dev, &dout, c.stream);
+    if (rc) return rc;
+    cudaMemcpyAsync(out->U, c.U, bU, cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(out->status, c.status, bS, cudaMemcpyDeviceToHost, c.stream);
+    if (dout.iters) cudaMemcpyAsync(out->iters, c.iters, bS, cudaMemcpyDeviceToHost, c.stream);
+    if (dout.Z) cudaMemcpyAsync(out->Z, c.Z, bZ, cudaMemcpyDeviceToHost, c.stream);
+    e = cudaStreamSynchronize(c.stream);
+    return (int)e;
+}
+
+}  // extern "C"

@@ -29,3 +29,19 @@ class Solution:
     z: Optional[np.ndarray] = None
     obj: Optional[float] = None
     extras: Dict[str, Any] = field(default_factory=dict)
+
+
+@dataclass
+class QPProblem:
+    """(P, q, G, h) record returned by ``MPCQP.problem``; stands in for
+    ``qpsolvers.Problem`` (``qpmpc/mpc_qp.py:124-127``): no equalities, no
+    bounds."""
+
+    P: Any
+    q: np.ndarray
+    G: Optional[Any] = None
+    h: Optional[np.ndarray] = None
+    A: Optional[np.ndarray] = None
+    b: Optional[np.ndarray] = None
+    lb: Optional[np.ndarray] = None
+    ub: Optional[np.ndarray] = None

@@ -1,0 +1,250 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the
+golden fixtures generated from the reference's own condensing.
+
+Bars: condensing within 1e-12 relative of the reference fields (summation
+order differs from ndarray.dot); U within 1e-6 absolute of the exact
+active-set oracle in fp64 (BASELINE north_star), plus KKT certificates.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, golden_problem, load_golden
+
+pytestmark = pytest.mark.gpu
+
+U_TOL = 1e-6  # |du|_inf, fp64 (BASELINE.json north_star)
+
+
+def _solve(w, **kw):
+    import torch
+
+    from qpmpc_b200 import solve_mpc_batch
+    from qpmpc_b200.workloads import to_batched
+
+    prob = to_batched(w)
+    plan = solve_mpc_batch(prob, return_multipliers=True, **kw)
+    torch.cuda.synchronize()
+    return prob, plan
+
+
+def _oracle(w):
+    import oracle
+    from qpmpc_b200.workloads import oracle_ops
+
+    return oracle.solve_batch(w["batch"], w["N"], w["nx"], w["nu"], w["nc"], oracle_ops(w),
+                              w["w_t"], w["w_x"], w["w_u"], want_kkt=True)
+
+
+def _check_against_oracle(w, tol=U_TOL):
+    prob, plan = _solve(w)
+    ref = _oracle(w)
+    U = plan.inputs.reshape(w["batch"], -1).cpu().numpy()
+    st = plan.status.cpu().numpy()
+    assert np.array_equal(st == 0, ref["status"] == 0), (st[:16], ref["status"][:16])
+    ok = st == 0
+    assert ok.any()
+    err = np.abs(U[ok] - ref["U"][ok]).max()
+    assert err <= tol, f"|dU|_inf = {err:.3e}"
+    assert np.isnan(U[~ok]).all()
+    return prob, plan, ref
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_condense_matches_reference_fields(name):
+    """mpc_condense_kernel reproduces the reference MPCQP fields (golden)."""
+    g = load_golden(name)
+    n = g["ref_q"].size
+    if n > 32:
+        pytest.skip("n = 64 variant not compiled yet")
+    from qpmpc_b200 import MPCQP
+
+    qp = MPCQP(golden_problem(g))
+    for field in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last", "e"):
+        ref = g[f"ref_{field}"]
+        got = getattr(qp, field)
+        assert got.shape == ref.shape, field
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(got - ref).max() <= 1e-12 * scale, field
+
+
+@pytest.mark.parametrize("name", ["triple_integrator", "humanoid", "pendulum",
+                                  "random_ltv_cd", "random_ltv_c", "random_ltv_d",
+                                  "triple_integrator_N8", "triple_integrator_N32"])
+def test_solve_mpc_single_matches_oracle(name):
+    """solve_mpc(problem, "b200") on the golden problems vs the exact QP oracle
+    applied to the REFERENCE's condensed matrices."""
+    import oracle
+    from qpmpc_b200 import solve_mpc
+
+    g = load_golden(name)
+    st, x, z, _ = oracle.qp_gi(g["ref_P"], g["ref_q"], g["ref_G"], g["ref_h"])
+    plan = solve_mpc(golden_problem(g), solver="b200")
+    if st != 0:
+        assert plan.is_empty
+        return
+    assert not plan.is_empty
+    assert np.abs(plan.inputs.reshape(-1) - x).max() <= U_TOL
+    kkt = oracle.kkt(g["ref_P"], g["ref_q"], g["ref_G"], g["ref_h"],
+                     plan.inputs.reshape(-1), plan.qpsol.z)
+    scale = max(1.0, np.abs(g["ref_q"]).max())
+    assert kkt[0] <= 1e-9 * scale and kkt[1] <= 1e-9 and kkt[2] == 0.0 and kkt[3] <= 1e-9
+
+
+def test_triple_integrator_known_answer():
+    """The one non-trivial QP answer recorded in SURVEY.md 8(c) (KKT-certified)."""
+    from qpmpc_b200 import solve_mpc
+
+    g = load_golden("triple_integrator")
+    plan = solve_mpc(golden_problem(g), solver="b200")
+    U = plan.inputs.reshape(-1)
+    expect = {0: 48.0, 7: -27.51976087031062, 8: -54.819558402499155,
+              9: -13.660680727190227, 15: 47.92404503861714}
+    for i in range(16):
+        assert abs(U[i] - expect.get(i, 0.0)) <= U_TOL
+
+
+@pytest.mark.parametrize("N,batch", [(16, 4096), (8, 2048), (32, 1024)])
+def test_triple_integrator_batch(N, batch):
+    """BASELINE config 2 / 5 shapes against the oracle."""
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    _check_against_oracle(triple_integrator_batch(batch, N=N, seed=N))
+
+
+def test_triple_integrator_shared_model_and_jitter():
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    _check_against_oracle(triple_integrator_batch(1024, per_instance_model=False))
+    _check_against_oracle(triple_integrator_batch(1024, jitter=0.1, seed=5))
+
+
+@pytest.mark.parametrize("ltv_model", [False, True])
+def test_pendulum_batch(ltv_model):
+    """BASELINE config 3, one cycle: box bounds on u through D only."""
+    from qpmpc_b200.workloads import pendulum_batch
+
+    _check_against_oracle(pendulum_batch(2048, ltv_model=ltv_model))
+
+
+def test_humanoid_batch():
+    """BASELINE config 4 data in fp64: per-instance per-step e_k."""
+    from qpmpc_b200.workloads import humanoid_batch
+
+    _check_against_oracle(humanoid_batch(2048))
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 2, 3), (5, 4, 1, 2), (7, 2, 2, 4), (4, 5, 3, 6),
+                                   (10, 2, 1, 1), (3, 6, 2, 0)])
+@pytest.mark.parametrize("ltv", [False, True])
+def test_random_shapes(shape, ltv):
+    """Random per-instance problems over (N, nx, nu, nc), C and D both present."""
+    from qpmpc_b200.workloads import random_batch
+
+    N, nx, nu, nc = shape
+    _check_against_oracle(random_batch(257, N, nx, nu, nc, seed=sum(shape), ltv=ltv))
+
+
+@pytest.mark.parametrize("with_C,with_D,w_t,w_x", [(True, False, 0.7, None), (False, True, None, 0.3),
+                                                   (True, True, 1e-12, 0.5)])
+def test_random_operand_patterns(with_C, with_D, w_t, w_x):
+    from qpmpc_b200.workloads import random_batch
+
+    _check_against_oracle(random_batch(130, 6, 3, 2, 2, seed=7, with_C=with_C, with_D=with_D,
+                                       w_t=w_t, w_x=w_x))
+
+
+def test_ragged_tail_and_tiny_batches():
+    """Batches that do not fill a CTA / warp (bulk-copy fallback path)."""
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    for batch in (1, 2, 3, 5, 7, 31):
+        _check_against_oracle(triple_integrator_batch(batch, seed=batch))
+
+
+def test_infeasible_instances_are_flagged():
+    """Q3 / H4: an infeasible instance gets status 2 and NaN inputs; its warp
+    neighbour is unaffected."""
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    w = triple_integrator_batch(64, seed=11)
+    w["x0"][::4, 2] = 5.0  # |accel_0| > 3: row k=0 violated, inputs cannot repair it
+    prob, plan, ref = _check_against_oracle(w)
+    st = plan.status.cpu().numpy()
+    assert (st[::4] == 2).all() and (st[1::4] == 0).all()
+
+
+def test_multipliers_certify_kkt():
+    """Z >= 0 and KKT residuals of (U, Z) on the oracle's condensed matrices."""
+    import oracle
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    w = triple_integrator_batch(64, seed=3)
+    prob, plan = _solve(w)
+    U = plan.inputs.reshape(64, -1).cpu().numpy()
+    Z = plan.multipliers.cpu().numpy()
+    assert (Z >= 0).all()
+    for b in range(64):
+        c = oracle.condense(16, 3, 1, 2, w["A"][b], w["B"][b], w["C"][b], None, w["e"][b],
+                            w["x0"][b], w["goal"][b], None, 1.0, None, 1e-6)
+        k = oracle.kkt(c["P"], c["q"], c["G"], c["h"], U[b], Z[b])
+        assert k[0] <= 1e-10 and k[1] <= 1e-9 and k[3] <= 1e-9, k
+
+
+def test_states_match_host_integrate():
+    from qpmpc_b200.workloads import pendulum_batch
+
+    w = pendulum_batch(33)
+    prob, plan = _solve(w)
+    X = plan.states.cpu().numpy()
+    U = plan.inputs.cpu().numpy()
+    for b in (0, 17, 32):
+        x = w["x0"][b].copy()
+        for k in range(w["N"]):
+            assert np.abs(X[b, k] - x).max() <= 1e-12
+            x = w["A"] @ x + w["B"] @ U[b, k]
+        assert np.abs(X[b, -1] - x).max() <= 1e-12
+
+
+def test_solve_host_entry_matches_device_entry():
+    """qpmpc_b200_solve_host (host buffers, the e2e call) == device entry."""
+    import ctypes
+
+    from qpmpc_b200 import _capi
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    w = triple_integrator_batch(1000, seed=9)
+    prob, plan = _solve(w)
+    lib = _capi.load()
+    desc = prob.desc()
+    arrs = {k: np.ascontiguousarray(w[k]) for k in ("A", "B", "C", "e", "x0", "goal")}
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    ops = _capi.Operands(ptr(arrs["A"]), ptr(arrs["B"]), ptr(arrs["C"]), None, ptr(arrs["e"]),
+                         ptr(arrs["x0"]), ptr(arrs["goal"]), None)
+    U = np.zeros((1000, 16))
+    st = np.zeros(1000, dtype=np.int32)
+    outs = _capi.Outputs(ptr(U), ptr(st), None, None)
+    rc = lib.qpmpc_b200_solve_host(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), 0)
+    assert rc == 0
+    assert np.array_equal(U, plan.inputs.reshape(1000, 16).cpu().numpy())
+    assert (st == 0).all()
+
+
+def test_fp32_humanoid_within_stated_tolerance():
+    """BASELINE config 4 runs in fp32: |du|_inf <= 2e-3 * max(1, |u|_inf) vs the
+    fp64 oracle (the reference itself is float64 only, mpc_qp.py:93-98)."""
+    import torch
+
+    from qpmpc_b200 import solve_mpc_batch
+    from qpmpc_b200.workloads import humanoid_batch, to_batched
+
+    w = humanoid_batch(1024)
+    ref = _oracle(w)
+    plan = solve_mpc_batch(to_batched(w, dtype=torch.float32))
+    U = plan.inputs.reshape(1024, -1).double().cpu().numpy()
+    st = plan.status.cpu().numpy()
+    ok = (st == 0) & (ref["status"] == 0)
+    assert ok.mean() > 0.99
+    scale = np.maximum(1.0, np.abs(ref["U"][ok]).max(axis=1))
+    err = np.abs(U[ok] - ref["U"][ok]).max(axis=1) / scale
+    assert err.max() <= 2e-3, err.max()
