@@ -150,6 +150,10 @@ size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *desc);
 int qpmpc_b200_max_vars(int dtype);
 int qpmpc_b200_max_rows(int dtype, int n);
 
+/* Measures the FP64 FMA peak of `device` (TFLOP/s) with a register-only
+ * kernel: the denominator of the FP64 roofline bench.py reports. */
+int qpmpc_b200_fp64_peak(int device, double *tflops);
+
 /* Number of kernels this library has launched in this process. */
 long long qpmpc_b200_launch_count(void);
 

@@ -22,7 +22,7 @@ EXPORTS = (
     "qpmpc_b200_solve", "qpmpc_b200_solve_host", "qpmpc_b200_condense",
     "qpmpc_b200_integrate", "qpmpc_b200_workspace_bytes", "qpmpc_b200_max_vars",
     "qpmpc_b200_max_rows", "qpmpc_b200_launch_count", "qpmpc_b200_strerror",
-    "qpmpc_b200_version",
+    "qpmpc_b200_version", "qpmpc_b200_fp64_peak",
 )
 
 
@@ -94,6 +94,8 @@ def load():
     lib.qpmpc_b200_workspace_bytes.argtypes = [P(Desc)]
     lib.qpmpc_b200_workspace_bytes.restype = ctypes.c_size_t
     lib.qpmpc_b200_launch_count.restype = ctypes.c_longlong
+    lib.qpmpc_b200_fp64_peak.argtypes = [ctypes.c_int, P(ctypes.c_double)]
+    lib.qpmpc_b200_fp64_peak.restype = ctypes.c_int
     lib.qpmpc_b200_strerror.argtypes = [ctypes.c_int]
     lib.qpmpc_b200_strerror.restype = ctypes.c_char_p
     _lib = lib

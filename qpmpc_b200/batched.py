@@ -140,8 +140,8 @@ class BatchedMPCProblem:
             )
 
     def _matrix(self, name, t, item, optional):
-        if t is None:
-            if not optional:
+        if t is None or 0 in item:
+            if not optional and 0 not in item:
                 raise ProblemDefinitionError(f"operand {name} is required")
             return None, _capi.ABSENT
         k = len(item)

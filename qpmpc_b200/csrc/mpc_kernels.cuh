@@ -400,17 +400,12 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
             Gc[c * L::LDG + l + s * NP] = v;
     };
 
-    // Tolerances of the violation test (same rule as oracle/mpc_oracle.c).
-    T hmax = T(1);
-#pragma unroll
-    for (int s = 0; s < MR; ++s)
-        if (rowvalid[s]) hmax = fmax(hmax, abs_(hs[l + s * NP]));
-#pragma unroll
-    for (int off = NP / 2; off > 0; off >>= 1) hmax = fmax(hmax, __shfl_xor_sync(FULL_MASK, hmax, off, NP));
+    // Tolerance of the violation test, per row: eps * (max(1, |h_i|) + |G_i|).
     T vtol[MR], ginv[MR];
 #pragma unroll
     for (int s = 0; s < MR; ++s) {
-        vtol[s] = Num<T>::viol_eps * (hmax + sqrt_(gn2[s]));
+        const T hi = rowvalid[s] ? abs_(hs[l + s * NP]) : T(1);
+        vtol[s] = Num<T>::viol_eps * (fmax(T(1), hi) + sqrt_(gn2[s]));
         ginv[s] = gn2[s] > T(0) ? rsqrt_(gn2[s]) : T(1e30);
     }
     __syncwarp();  // Lc (aliased by Rc) and Jf are dead from here on

@@ -222,9 +222,55 @@ cudaError_t ensure(void **ptr, size_t *cap, size_t bytes) {
     return e;
 }
 
+// FP64 FMA peak probe: 16 independent dependent chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fma(v[i], a, b);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc += v[i];
+    if (acc == 123.456) out[0] = acc;  // never true; keeps the chains alive
+}
+
 }  // namespace
 
 extern "C" {
+
+int qpmpc_b200_fp64_peak(int device, double *tflops) {
+    if (!tflops) return QPMPC_B200_EINVAL;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    double *out = nullptr;
+    if ((e = cudaMalloc(&out, 8)) != cudaSuccess) return (int)e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int iters = 4096, grid = sms * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0);
+        dfma_peak_kernel<<<grid, threads>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        const double flops = 2.0 * 16.0 * iters * (double)grid * threads;
+        if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+        g_launches.fetch_add(1);
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(out);
+    *tflops = best;
+    return (int)cudaGetLastError();
+}
 
 int qpmpc_b200_version(void) { return QPMPC_B200_VERSION; }
 
