@@ -55,7 +55,7 @@ __host__ __device__ inline int psi_region_elems(int NP, int nx) {
 // ---------------------------------------------------------------------------
 // Phase 0: stage the operands of instances [inst0, inst0 + cnt) into `inbase`.
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T>  // @phase 0 stage inputs
 __device__ __forceinline__ void stage_inputs(const SolveParams &p, T *inbase, int inst0, int cnt,
                                              uint64_t *bar) {
     if (threadIdx.x == 0) {
@@ -105,7 +105,7 @@ __device__ __forceinline__ void stage_inputs(const SolveParams &p, T *inbase, in
 // Prow is row l of P, qj is q_l, and psi (buffer returned) holds psi_N,
 // xbar the free response phi_N x0.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR, bool DUMP>
+template <typename T, int NP, int MR, bool DUMP>  // @phase A condense
 __device__ __forceinline__ int condense_instance(const SolveParams &p, const T *const (&in)[OP_COUNT],
                                                  T *Gc, T *hs, T *psi, int l, T (&Prow)[NP], T &qj,
                                                  long long inst, bool valid) {
@@ -231,7 +231,7 @@ __device__ __forceinline__ int condense_instance(const SolveParams &p, const T *
 // The fused kernel.  MREG: rows of M = G J live in registers (NP <= 16);
 // otherwise M overwrites G in shared memory.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR, bool MREG>
+template <typename T, int NP, int MR, bool MREG>  // @phase kernel prologue
 __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR>;
     using T2 = typename Pair<T>::type;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
     condense_instance<T, NP, MR, false>(p, in, Gc, hs, psi, l, Prow, qj, inst, valid);
     __syncwarp();
 
-    // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----
+    // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----  // @phase B cholesky
     T dinv = T(0);
     bool spd = true;
 #pragma unroll
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
             Prow[i + 1] -= lc * v.y;
         }
     }
-    // J = L^-T, row l per lane: back-substitution over rows from the bottom.
+    // J = L^-T, row l per lane: back-substitution over rows from the bottom.  // @phase B J=L^-T
     T Jrow[NP];
 #pragma unroll
     for (int c = 0; c < NP; ++c) Jrow[c] = (c == l) ? T(1) : T(0);
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
             }
         }
     }
-    // x = -J J' q
+    // x = -J J' q  // @phase B x=-P^-1 q
     {
         T tl = T(0);
 #pragma unroll
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
     xs[l] = x;
     __syncwarp();
 
-    // M = G J (rows l + s*NP), violations, row norms.
+    // M = G J (rows l + s*NP), violations, row norms.  // @phase B M=GJ, violations
     T Mrow[MREG ? MR : 1][NP];
     T viol[MR], gn2[MR], mn2[MR];
     bool rowvalid[MR];
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
     }
     __syncwarp();  // Lc (aliased by Rc) and Jf are dead from here on
 
-    // ---- phase C: dual active-set iteration ---------------------------------
+    // ---- phase C: dual active-set iteration ---------------------------------  // @phase C select row (step 1)
     const int max_iter = p.max_iter;
     int na = 0, it = 0;
     int st = spd ? 0 : 3;
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
                 act = false;
             }
         }
-        // d = J' n_p = -(row p of M); published by the lane that owns row p.
+        // d = J' n_p = -(row p of M); published by the lane that owns row p.  // @phase C publish d
         const int owner = pidx % NP, pslot = pidx / NP;
         if (act && l == owner) {
             T vp = T(0), m2p = T(0);
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
             sc[1] = m2p;
         }
         __syncwarp();
-        // z = J2 d2 (this lane's component), G z (owned rows), |d2|^2
+        // z = J2 d2 (this lane's component), G z (owned rows), |d2|^2  // @phase C z, Gz
         T z = T(0), a2 = T(0);
         T gz[MR];
 #pragma unroll
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
                 gz[s] += mget(s, c + 1) * v.y;
             }
         }
-        // r = R^-1 d1 (component l on lane l < na)
+        // r = R^-1 d1 (component l on lane l < na)  // @phase C r=R^-1 d
         T rv = (l < na) ? dfull[l] : T(0);
         {
             const int namax = __reduce_max_sync(FULL_MASK, act ? na : 0);
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
                 }
             }
         }
-        // step lengths
+        // step lengths  // @phase C step length, move
         const T cand = (act && l < na && rv > T(0)) ? lam / rv : INF;
         T t1 = cand;
 #pragma unroll
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
         const bool full = act && !zzero && t2 <= t1;
         const bool part = act && !full;
 
-        if (__any_sync(FULL_MASK, full)) {
+        if (__any_sync(FULL_MASK, full)) {  // @phase C add constraint (Householder)
             // Constraint p enters: reflect d2 onto its first entry.  H = I - tau v v',
             // v = d2 - beta e_na, applied to columns >= na of J and M.
             const T dna = d2[na < NP ? na : NP - 1];
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
                 cont = false;
             }
         }
-        if (__any_sync(FULL_MASK, part)) {
+        if (__any_sync(FULL_MASK, part)) {  // @phase C drop constraint (Givens)
             // Constraint at active position lidx leaves; p stays the candidate.
             const int cidx = __shfl_sync(FULL_MASK, aidx, lidx, NP);
             if (part && l == cidx % NP) actbits &= ~(1u << (cidx / NP));
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
         __syncwarp();
     }
 
-    // ---- phase D: outputs ---------------------------------------------------
+    // ---- phase D: outputs ---------------------------------------------------  // @phase D outputs
     if (valid) {
         if (l < n) static_cast<T *>(p.U)[(size_t)inst * n + l] = (st == 0) ? x : Num<T>::nan();
         if (l == 0) {
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const SolveParams p) {
 // Condense-only kernel: materialises the MPCQP fields for parity checks and
 // for the MPCQP host class (qpmpc/mpc_qp.py:28-37).
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR>
+template <typename T, int NP, int MR>  // @phase condense-only kernel
 __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR>;
     constexpr int IPW = 32 / NP;
