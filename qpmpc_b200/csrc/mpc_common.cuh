@@ -32,7 +32,7 @@ struct SolveParams {
     double tol;
     // shared-memory geometry (elements of T), computed by the host
     int inst_stride;     // per-instance work region
-    int psi_elems;       // size of the runtime-sized psi/J region
+    int tail_elems;      // runtime-sized tail of the work region (see tail_elems())
     int input_elems;     // CTA-level input region
     // outputs
     void *U;
@@ -51,6 +51,9 @@ __device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
 __device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
 __device__ __forceinline__ float sqrt_(float v) { return sqrtf(v); }
+// Reciprocal (correctly rounded): a * rcp_(b) replaces a / b where one ulp is irrelevant.
+__device__ __forceinline__ double rcp_(double v) { return __drcp_rn(v); }
+__device__ __forceinline__ float rcp_(float v) { return __frcp_rn(v); }
 __device__ __forceinline__ double abs_(double v) { return fabs(v); }
 __device__ __forceinline__ float abs_(float v) { return fabsf(v); }
 

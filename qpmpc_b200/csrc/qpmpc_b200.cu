@@ -117,9 +117,9 @@ void fill_params(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, SolveP
 
 // Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
 template <typename T>
-size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc) {
-    p->psi_elems = psi_region_elems(np, p->nx);
-    p->inst_stride = fixed_elems + p->psi_elems;
+size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc, bool mreg) {
+    p->tail_elems = tail_elems(np, p->nx, mreg);
+    p->inst_stride = fixed_elems + p->tail_elems;
     int off = 0;
     for (int o = 0; o < OP_COUNT; ++o) {
         OperandView &v = p->op[o];
@@ -136,12 +136,12 @@ template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream) {
     using L = Lay<T, NP, MR>;
     constexpr int IPW = 32 / NP;
-    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 2 : 1);
+    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 4 : 1);
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
     size_t smem = 0;
     for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc);
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, MREG);
         if (smem <= 227 * 1024 || wpc == 1) break;
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
@@ -163,7 +163,7 @@ int launch_condense(SolveParams p, cudaStream_t stream) {
     int wpc = 2;
     size_t smem = 0;
     for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc);
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, true);
         if (smem <= 227 * 1024 || wpc == 1) break;
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
