@@ -1,0 +1,8 @@
+// Explicit instantiations of the warp kernels: float, NP = 8.
+#define QPMPC_INSTANTIATE
+#include "mpc_launch.cuh"
+
+namespace qpmpc {
+QPMPC_INSTANTIATE_VARIANT(float, 8, 2, true)
+QPMPC_INSTANTIATE_VARIANT(float, 8, 4, true)
+}  // namespace qpmpc

@@ -1,0 +1,8 @@
+// Explicit instantiations of the warp kernels: double, NP = 32.
+#define QPMPC_INSTANTIATE
+#include "mpc_launch.cuh"
+
+namespace qpmpc {
+QPMPC_INSTANTIATE_VARIANT(double, 32, 2, false)
+QPMPC_INSTANTIATE_VARIANT(double, 32, 4, false)
+}  // namespace qpmpc

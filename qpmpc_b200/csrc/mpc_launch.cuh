@@ -1,0 +1,101 @@
+// mpc_launch.cuh -- launch wrappers of the warp kernels (mpc_kernels.cuh).
+//
+// The kernels are instantiated in one small translation unit per (dtype, NP)
+// (inst_*.cu) so that the library builds in parallel; the host API
+// (qpmpc_b200.cu) only sees the declarations below.  A translation unit that
+// defines QPMPC_INSTANTIATE gets the definitions.
+#pragma once
+
+#include "../../include/qpmpc_b200.h"
+#include "mpc_common.cuh"
+
+namespace qpmpc {
+
+void count_launch();                        // qpmpc_b200.cu
+int env_int(const char *name, int dflt);    // qpmpc_b200.cu
+
+template <typename T, int NP, int MR, bool MREG>
+int launch_solve(SolveParams p, cudaStream_t stream);
+template <typename T, int NP, int MR>
+int launch_condense(SolveParams p, cudaStream_t stream);
+
+}  // namespace qpmpc
+
+#ifdef QPMPC_INSTANTIATE
+#include "mpc_kernels.cuh"
+
+namespace qpmpc {
+
+// Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
+template <typename T>
+size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc, bool mreg) {
+    p->tail_elems = tail_elems(np, p->nx, mreg);
+    p->inst_stride = fixed_elems + p->tail_elems;
+    int off = 0;
+    for (int o = 0; o < OP_COUNT; ++o) {
+        OperandView &v = p->op[o];
+        if (!v.ptr) continue;
+        v.smem_off = off;
+        int elems = v.sz * (v.per_instance ? ipc : 1);
+        off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
+    }
+    p->input_elems = off;
+    return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
+}
+
+template <typename T, int NP, int MR, bool MREG>
+int launch_solve(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 4 : 1);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 4) wpc = 4;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, MREG);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    // Occupancy experiments only: pad the dynamic shared memory request.
+    const size_t pad = (size_t)env_int("QPMPC_B200_SMEM_PAD_KB", 0) * 1024;
+    if (pad && smem + pad <= 227 * 1024) smem += pad;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_solve_kernel<T, NP, MR, MREG>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int NP, int MR>
+int launch_condense(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    int wpc = 2;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, true);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_condense_kernel<T, NP, MR>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+
+#define QPMPC_INSTANTIATE_VARIANT(T, NP, MR, MREG)                               \
+    template int launch_solve<T, NP, MR, MREG>(SolveParams, cudaStream_t);      \
+    template int launch_condense<T, NP, MR>(SolveParams, cudaStream_t);
+
+}  // namespace qpmpc
+#endif  // QPMPC_INSTANTIATE

@@ -10,23 +10,28 @@
 #include <cstring>
 #include <mutex>
 
-#include "mpc_kernels.cuh"
+#include "mpc_cta_kernel.cuh"
+#include "mpc_integrate.cuh"
+#include "mpc_launch.cuh"
 
 using namespace qpmpc;
 
+namespace qpmpc {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1); }
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+}  // namespace qpmpc
+
 namespace {
 
-std::atomic<long long> g_launches{0};
 
 struct Variant {
     int np, mr;
     bool mreg;
 };
-
-int env_int(const char *name, int dflt) {
-    const char *v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : dflt;
-}
 
 // Smallest compiled (NP, MR) that holds n variables and m constraint rows.
 bool pick_variant(int n, int m, Variant *out) {
@@ -115,68 +120,40 @@ void fill_params(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, SolveP
     p->tol = d->tol > 0.0 ? d->tol : 1e-9;
 }
 
-// Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
+// One CTA per instance (mpc_cta_kernel.cuh): any shape whose matrices fit in
+// 227 KB of shared memory.
 template <typename T>
-size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc, bool mreg) {
-    p->tail_elems = tail_elems(np, p->nx, mreg);
-    p->inst_stride = fixed_elems + p->tail_elems;
-    int off = 0;
-    for (int o = 0; o < OP_COUNT; ++o) {
-        OperandView &v = p->op[o];
-        if (!v.ptr) continue;
-        v.smem_off = off;
-        int elems = v.sz * (v.per_instance ? ipc : 1);
-        off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
-    }
-    p->input_elems = off;
-    return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
+size_t cta_smem_bytes(int n, int m, int nx) {
+    return (size_t)cta_layout(n, m, nx, (int)sizeof(T)).total * sizeof(T);
 }
 
-template <typename T, int NP, int MR, bool MREG>
-int launch_solve(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR>;
-    constexpr int IPW = 32 / NP;
-    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 4 : 1);
-    if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
-    size_t smem = 0;
-    for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, MREG);
-        if (smem <= 227 * 1024 || wpc == 1) break;
-    }
+template <typename T>
+int launch_solve_cta(const SolveParams &p, cudaStream_t stream) {
+    const size_t smem = cta_smem_bytes<T>(p.n, p.m, p.nx);
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
-    const int ipc = IPW * wpc;
-    auto kern = mpc_solve_kernel<T, NP, MR, MREG>;
+    auto kern = mpc_solve_cta_kernel<T>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    const int grid = (p.batch + ipc - 1) / ipc;
-    if (grid == 0) return 0;
-    kern<<<grid, wpc * 32, smem, stream>>>(p);
-    g_launches.fetch_add(1);
+    int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
+    threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
+    kern<<<p.batch, threads, smem, stream>>>(p);
+    count_launch();
     return (int)cudaGetLastError();
 }
 
-template <typename T, int NP, int MR>
-int launch_condense(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR>;
-    constexpr int IPW = 32 / NP;
-    int wpc = 2;
-    size_t smem = 0;
-    for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, true);
-        if (smem <= 227 * 1024 || wpc == 1) break;
-    }
+template <typename T>
+int launch_condense_cta(const SolveParams &p, cudaStream_t stream) {
+    const size_t smem = cta_smem_bytes<T>(p.n, p.m, p.nx);
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
-    const int ipc = IPW * wpc;
-    auto kern = mpc_condense_kernel<T, NP, MR>;
+    auto kern = mpc_condense_cta_kernel<T>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    const int grid = (p.batch + ipc - 1) / ipc;
-    if (grid == 0) return 0;
-    kern<<<grid, wpc * 32, smem, stream>>>(p);
-    g_launches.fetch_add(1);
+    kern<<<p.batch, 256, smem, stream>>>(p);
+    count_launch();
     return (int)cudaGetLastError();
 }
+
+bool use_cta(int n, int m, Variant *v) { return env_int("QPMPC_B200_FORCE_CTA", 0) != 0 || !pick_variant(n, m, v); }
 
 template <typename T>
 int dispatch_solve(const SolveParams &p, const Variant &v, cudaStream_t s) {
@@ -263,7 +240,7 @@ int qpmpc_b200_fp64_peak(int device, double *tflops) {
         cudaEventElapsedTime(&ms, t0, t1);
         const double flops = 2.0 * 16.0 * iters * (double)grid * threads;
         if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
-        g_launches.fetch_add(1);
+        count_launch();
     }
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
@@ -278,17 +255,22 @@ long long qpmpc_b200_launch_count(void) { return g_launches.load(); }
 
 size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *) { return 0; }
 
-int qpmpc_b200_max_vars(int) { return 32; }
+// Capacity of the CTA kernel (shared memory bound), assuming nx <= 8.
+static size_t cta_bytes(int dtype, int n, int m) {
+    return dtype == QPMPC_B200_F64 ? cta_smem_bytes<double>(n, m, 8) : cta_smem_bytes<float>(n, m, 8);
+}
 
-int qpmpc_b200_max_rows(int, int n) {
-    Variant v;
-    int best = -1;
-    for (int m = 128; m >= 0; m -= 8)
-        if (pick_variant(n, m, &v)) {
-            best = m;
-            break;
-        }
-    return best;
+int qpmpc_b200_max_vars(int dtype) {
+    int n = 32;
+    while (cta_bytes(dtype, n + 1, 2 * (n + 1)) <= 227 * 1024) ++n;  // with m = 2 n rows
+    return n;
+}
+
+int qpmpc_b200_max_rows(int dtype, int n) {
+    if (n <= 0 || cta_bytes(dtype, n, 0) > 227 * 1024) return -1;
+    int m = 0;
+    while (cta_bytes(dtype, n, m + 8) <= 227 * 1024) m += 8;
+    return m;
 }
 
 const char *qpmpc_b200_strerror(int code) {
@@ -319,8 +301,9 @@ int qpmpc_b200_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, co
     p.iters = out->iters;
     p.Z = out->Z;
     Variant v;
-    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_cta(p.n, p.m, &v))
+        return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);
 }
 
@@ -341,8 +324,9 @@ int qpmpc_b200_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in,
     p.phi_last = out->phi_last;
     p.psi_last = out->psi_last;
     Variant v;
-    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_cta(p.n, p.m, &v))
+        return d->dtype == QPMPC_B200_F64 ? launch_condense_cta<double>(p, s) : launch_condense_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_condense<double>(p, v, s) : dispatch_condense<float>(p, v, s);
 }
 
@@ -376,7 +360,7 @@ int qpmpc_b200_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in
         mpc_integrate_kernel<double><<<grid, threads, 0, s>>>(p);
     else
         mpc_integrate_kernel<float><<<grid, threads, 0, s>>>(p);
-    g_launches.fetch_add(1);
+    count_launch();
     return (int)cudaGetLastError();
 }
 

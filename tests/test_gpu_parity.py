@@ -54,9 +54,6 @@ def _check_against_oracle(w, tol=U_TOL):
 def test_condense_matches_reference_fields(name):
     """mpc_condense_kernel reproduces the reference MPCQP fields (golden)."""
     g = load_golden(name)
-    n = g["ref_q"].size
-    if n > 32:
-        pytest.skip("n = 64 variant not compiled yet")
     from qpmpc_b200 import MPCQP
 
     qp = MPCQP(golden_problem(g))
@@ -70,7 +67,8 @@ def test_condense_matches_reference_fields(name):
 
 @pytest.mark.parametrize("name", ["triple_integrator", "humanoid", "pendulum",
                                   "random_ltv_cd", "random_ltv_c", "random_ltv_d",
-                                  "triple_integrator_N8", "triple_integrator_N32"])
+                                  "triple_integrator_N8", "triple_integrator_N32",
+                                  "triple_integrator_N64"])
 def test_solve_mpc_single_matches_oracle(name):
     """solve_mpc(problem, "b200") on the golden problems vs the exact QP oracle
     applied to the REFERENCE's condensed matrices."""
@@ -104,7 +102,7 @@ def test_triple_integrator_known_answer():
         assert abs(U[i] - expect.get(i, 0.0)) <= U_TOL
 
 
-@pytest.mark.parametrize("N,batch", [(16, 4096), (8, 2048), (32, 1024)])
+@pytest.mark.parametrize("N,batch", [(16, 4096), (8, 2048), (32, 1024), (64, 512)])
 def test_triple_integrator_batch(N, batch):
     """BASELINE config 2 / 5 shapes against the oracle."""
     from qpmpc_b200.workloads import triple_integrator_batch
@@ -152,6 +150,49 @@ def test_random_operand_patterns(with_C, with_D, w_t, w_x):
 
     _check_against_oracle(random_batch(130, 6, 3, 2, 2, seed=7, with_C=with_C, with_D=with_D,
                                        w_t=w_t, w_x=w_x))
+
+
+@pytest.mark.parametrize("kind", ["ti16", "ti8", "pendulum", "pendulum_ltv", "humanoid", "random",
+                                  "random_lti", "infeasible"])
+def test_cta_kernel_matches_oracle(kind, monkeypatch):
+    """The CTA-per-instance kernel (n > 32 path) forced onto small shapes."""
+    from qpmpc_b200.workloads import (humanoid_batch, pendulum_batch, random_batch,
+                                      triple_integrator_batch)
+
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    if kind == "ti16":
+        w = triple_integrator_batch(700, N=16, seed=21)
+    elif kind == "ti8":
+        w = triple_integrator_batch(300, N=8, seed=22)
+    elif kind == "pendulum":
+        w = pendulum_batch(400)
+    elif kind == "pendulum_ltv":
+        w = pendulum_batch(200, ltv_model=True)
+    elif kind == "humanoid":
+        w = humanoid_batch(400)
+    elif kind == "random":
+        w = random_batch(200, 7, 5, 2, 3, seed=23, ltv=True)
+    elif kind == "random_lti":
+        w = random_batch(200, 9, 2, 3, 5, seed=24, ltv=False)
+    else:
+        w = triple_integrator_batch(64, seed=11)
+        w["x0"][::4, 2] = 5.0
+    _check_against_oracle(w)
+
+
+def test_cta_kernel_condense_fields(monkeypatch):
+    """mpc_condense_cta_kernel reproduces the reference MPCQP fields."""
+    from qpmpc_b200 import MPCQP
+
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    for name in ("humanoid", "pendulum", "random_ltv_cd", "triple_integrator_stage"):
+        g = load_golden(name)
+        qp = MPCQP(golden_problem(g))
+        for field in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last"):
+            ref = g[f"ref_{field}"]
+            got = getattr(qp, field)
+            scale = max(1.0, np.abs(ref).max())
+            assert np.abs(got - ref).max() <= 1e-12 * scale, (name, field)
 
 
 def test_ragged_tail_and_tiny_batches():
