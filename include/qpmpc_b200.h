@@ -142,6 +142,34 @@ int qpmpc_b200_condense(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *
 int qpmpc_b200_integrate(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
                          const void *U, void *X, void *stream);
 
+/* Receding-horizon closed loop of examples/wheeled_inverted_pendulum.py:99-118
+ * for a batch, state resident on the device: per cycle { reference trajectory
+ * from the state (get_target_states, examples/...:65-83); condense + solve
+ * (qpmpc/solve_mpc.py:42-43); `substeps` plant steps of
+ * WheeledInvertedPendulum.integrate (qpmpc/systems/wheeled_inverted_pendulum.py:
+ * 127-160) under the first input of the plan }.  The problem must have nx = 4,
+ * nu = 1 and per-instance x0 / goal / targets: in->x0 [batch,4] is the state
+ * (read and overwritten), in->goal [batch,4] and in->targets [batch,N*4] are
+ * work buffers the loop rewrites every cycle; out->U / status / iters hold the
+ * plan of the last cycle.  An instance without a plan in some cycle gets input
+ * 0 for that cycle and is counted in *unsolved.  2 * cycles + 1 launches,
+ * asynchronous on `stream`. */
+typedef struct qpmpc_b200_closed_loop {
+    int32_t cycles;          /* control cycles (200 in BASELINE config 3) */
+    int32_t substeps;        /* plant steps per cycle (NB_SUBSTEPS = 15) */
+    double dt;               /* plant step = sampling_period / substeps */
+    double sampling_period;  /* T of the MPC model */
+    double length;           /* pendulum length (omega^2 = gravity / length) */
+    double gravity;
+    const void *v_target;    /* [batch] target ground velocity, dtype of desc */
+    void *trajectory;        /* optional [cycles + 1, batch, 4] states after each cycle */
+    int32_t *unsolved;       /* optional device counter, incremented per missing plan */
+} qpmpc_b200_closed_loop;
+
+int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                                    const qpmpc_b200_outputs *out, const qpmpc_b200_closed_loop *loop,
+                                    void *stream);
+
 /* Scratch the device entry points need from the caller: none (0) today; kept
  * in the ABI so a future kernel can ask for it without a signature change. */
 size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *desc);

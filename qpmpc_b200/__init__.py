@@ -25,6 +25,7 @@ from .batched import (  # noqa: E402
     BatchedPlan,
     condense_batch,
     integrate_batch,
+    pendulum_closed_loop,
     problem_to_batch,
     solve_mpc_batch,
 )
@@ -34,5 +35,6 @@ from .solve_mpc import solve_mpc  # noqa: E402  (rebinds the name from module to
 __all__ = [
     "BackendError", "BatchedMPCProblem", "BatchedPlan", "MPCProblem", "MPCQP",
     "Plan", "PlanError", "ProblemDefinitionError", "QPMPCException", "QPProblem",
-    "Solution", "StateError", "solve_mpc", "solve_mpc_batch",
+    "Solution", "StateError", "condense_batch", "integrate_batch", "pendulum_closed_loop",
+    "solve_mpc", "solve_mpc_batch",
 ]

@@ -22,7 +22,7 @@ EXPORTS = (
     "qpmpc_b200_solve", "qpmpc_b200_solve_host", "qpmpc_b200_condense",
     "qpmpc_b200_integrate", "qpmpc_b200_workspace_bytes", "qpmpc_b200_max_vars",
     "qpmpc_b200_max_rows", "qpmpc_b200_launch_count", "qpmpc_b200_strerror",
-    "qpmpc_b200_version", "qpmpc_b200_fp64_peak",
+    "qpmpc_b200_version", "qpmpc_b200_fp64_peak", "qpmpc_b200_pendulum_closed_loop",
 )
 
 
@@ -66,6 +66,18 @@ class QPFields(ctypes.Structure):
                 ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")]
 
 
+class ClosedLoop(ctypes.Structure):
+    """``qpmpc_b200_closed_loop``."""
+
+    _fields_ = [
+        ("cycles", ctypes.c_int32), ("substeps", ctypes.c_int32),
+        ("dt", ctypes.c_double), ("sampling_period", ctypes.c_double),
+        ("length", ctypes.c_double), ("gravity", ctypes.c_double),
+        ("v_target", ctypes.c_void_p), ("trajectory", ctypes.c_void_p),
+        ("unsolved", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -86,8 +98,10 @@ def load():
     lib.qpmpc_b200_condense.argtypes = [P(Desc), P(Operands), P(QPFields), ctypes.c_void_p]
     lib.qpmpc_b200_integrate.argtypes = [
         P(Desc), P(Operands), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.qpmpc_b200_pendulum_closed_loop.argtypes = [
+        P(Desc), P(Operands), P(Outputs), P(ClosedLoop), ctypes.c_void_p]
     for name in ("solve", "solve_host", "condense", "integrate", "version",
-                 "max_vars", "max_rows"):
+                 "max_vars", "max_rows", "pendulum_closed_loop"):
         getattr(lib, f"qpmpc_b200_{name}").restype = ctypes.c_int
     lib.qpmpc_b200_max_vars.argtypes = [ctypes.c_int]
     lib.qpmpc_b200_max_rows.argtypes = [ctypes.c_int, ctypes.c_int]

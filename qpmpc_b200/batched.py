@@ -441,3 +441,60 @@ def integrate_batch(problem: BatchedMPCProblem, inputs: torch.Tensor) -> torch.T
         rc = lib.qpmpc_b200_integrate(ctypes.byref(desc), ctypes.byref(ops), _ptr(U), _ptr(X), stream)
     _capi.check(rc, "qpmpc_b200_integrate")
     return X
+
+
+def pendulum_closed_loop(
+    problem: BatchedMPCProblem,
+    v_target,
+    cycles: int,
+    substeps: int = 15,
+    length: float = 0.6,
+    gravity: float = 9.81,
+    sampling_period: float = 0.1,
+    record: bool = False,
+):
+    """Receding-horizon closed loop of the wheeled inverted pendulum on the
+    device (``examples/wheeled_inverted_pendulum.py:99-118``, batched): per
+    cycle the reference trajectory is rebuilt from the state, the MPC is
+    condensed and solved, and the nonlinear plant advances ``substeps`` steps
+    under the first input.  ``problem.x0`` is the state and is updated in
+    place; goal / targets are (re)allocated per instance.
+
+    Returns ``(plan_of_last_cycle, trajectory or None, unsolved_count_tensor)``;
+    trajectory is [cycles + 1, B, 4].  Asynchronous on the current stream.
+    """
+    lib = _capi.load()
+    B, N, nx = problem.batch_size, problem.nb_timesteps, problem.state_dim
+    if nx != 4 or problem.input_dim != 1:
+        raise ProblemDefinitionError("the pendulum loop needs state_dim 4 and input_dim 1")
+    dev, dt_ = problem.device, problem.dtype
+    if problem.x0 is None or problem.mode_x0 != _capi.VEC_BATCH:
+        raise ProblemDefinitionError("per-instance initial states [B, 4] are required")
+    with torch.cuda.device(dev):
+        problem.goal = torch.empty((B, nx), dtype=dt_, device=dev)
+        problem.mode_goal = _capi.VEC_BATCH
+        problem.targets = torch.empty((B, N * nx), dtype=dt_, device=dev)
+        problem.mode_targets = _capi.VEC_BATCH
+        v = torch.as_tensor(v_target).to(device=dev, dtype=dt_).reshape(-1)
+        if v.numel() == 1:
+            v = v.expand(B)
+        v = v.contiguous()
+        if v.numel() != B:
+            raise StateError(f"v_target has {v.numel()} entries, expected {B}")
+        n = problem.nb_vars
+        U = torch.empty((B, n), dtype=dt_, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        iters = torch.zeros(B, dtype=torch.int32, device=dev)
+        traj = torch.empty((cycles + 1, B, nx), dtype=dt_, device=dev) if record else None
+        unsolved = torch.zeros(1, dtype=torch.int32, device=dev)
+        desc = problem.desc()
+        ops = problem.operands()
+        outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), None)
+        loop = _capi.ClosedLoop(int(cycles), int(substeps), sampling_period / substeps,
+                                float(sampling_period), float(length), float(gravity),
+                                _ptr(v), _ptr(traj), _ptr(unsolved))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.qpmpc_b200_pendulum_closed_loop(ctypes.byref(desc), ctypes.byref(ops),
+                                                 ctypes.byref(outs), ctypes.byref(loop), stream)
+    _capi.check(rc, "qpmpc_b200_pendulum_closed_loop")
+    return BatchedPlan(problem, U, status, iters), traj, unsolved

@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-OBJ_DIR = os.path.join(LIB_DIR, "obj")
+OBJ_DIR = os.path.join(os.path.dirname(HERE), ".scratch", "obj")  # git- and gpurun-ignored
 LIB_PATH = os.path.join(LIB_DIR, "libqpmpc_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

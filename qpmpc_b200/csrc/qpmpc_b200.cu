@@ -13,6 +13,7 @@
 #include "mpc_cta_kernel.cuh"
 #include "mpc_integrate.cuh"
 #include "mpc_launch.cuh"
+#include "mpc_plant.cuh"
 
 using namespace qpmpc;
 
@@ -361,6 +362,53 @@ int qpmpc_b200_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in
     else
         mpc_integrate_kernel<float><<<grid, threads, 0, s>>>(p);
     count_launch();
+    return (int)cudaGetLastError();
+}
+
+int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in,
+                                    const qpmpc_b200_outputs *out, const qpmpc_b200_closed_loop *loop,
+                                    void *stream) {
+    if (!d || !in || !out || !loop) return QPMPC_B200_EINVAL;
+    if (d->nx != 4 || d->nu != 1) return QPMPC_B200_ESHAPE;
+    if (d->mode_x0 != QPMPC_B200_VEC_BATCH || d->mode_goal != QPMPC_B200_VEC_BATCH ||
+        d->mode_targets != QPMPC_B200_VEC_BATCH)
+        return QPMPC_B200_EINVAL;
+    if (!in->x0 || !in->goal || !in->targets || !loop->v_target || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    if (loop->cycles < 0 || loop->substeps <= 0 || !(loop->dt > 0.0) || !(loop->length > 0.0)) return QPMPC_B200_EINVAL;
+    if (d->batch == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PendulumStepParams pp;
+    pp.batch = d->batch;
+    pp.N = d->N;
+    pp.n = d->N * d->nu;
+    pp.dt = loop->dt;
+    pp.T = loop->sampling_period;
+    pp.g = loop->gravity;
+    pp.omega2 = loop->gravity / loop->length;
+    pp.state = const_cast<void *>(in->x0);
+    pp.U = out->U;
+    pp.status = out->status;
+    pp.v_target = loop->v_target;
+    pp.goal = const_cast<void *>(in->goal);
+    pp.targets = const_cast<void *>(in->targets);
+    pp.unsolved = loop->unsolved;
+    const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    auto step = [&](int substeps, int slot) {
+        pp.substeps = substeps;
+        pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 4 * es : nullptr;
+        if (d->dtype == QPMPC_B200_F64)
+            pendulum_step_kernel<double><<<grid, threads, 0, s>>>(pp);
+        else
+            pendulum_step_kernel<float><<<grid, threads, 0, s>>>(pp);
+        count_launch();
+    };
+    step(0, 0);  // targets of the first cycle from the initial state
+    for (int c = 0; c < loop->cycles; ++c) {
+        int rc = qpmpc_b200_solve(d, in, out, stream);
+        if (rc) return rc;
+        step(loop->substeps, c + 1);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -289,3 +289,72 @@ def test_fp32_humanoid_within_stated_tolerance():
     scale = np.maximum(1.0, np.abs(ref["U"][ok]).max(axis=1))
     err = np.abs(U[ok] - ref["U"][ok]).max(axis=1) / scale
     assert err.max() <= 2e-3, err.max()
+
+
+def _cpu_closed_loop(w, cycles, substeps=15):
+    """The loop of examples/wheeled_inverted_pendulum.py:99-118 on the CPU: the
+    oracle solves, the host mirror of the plant integrates."""
+    import oracle
+    from qpmpc_b200.systems import WheeledInvertedPendulum
+    from qpmpc_b200.workloads import oracle_ops, pendulum_targets
+
+    pend = WheeledInvertedPendulum()
+    B, N, T = w["batch"], w["N"], w["T"]
+    state = w["x0"].copy()
+    traj = [state.copy()]
+    w = dict(w)
+    for _ in range(cycles):
+        w["x0"] = state
+        w["targets"], w["goal"] = pendulum_targets(state, w["v_target"], N, T)
+        ref = oracle.solve_batch(B, N, 4, 1, 2, oracle_ops(w), w["w_t"], w["w_x"], w["w_u"])
+        assert (ref["status"] == 0).all()
+        new = np.empty_like(state)
+        for b in range(B):
+            x = state[b]
+            for _s in range(substeps):
+                x = pend.integrate(x, ref["U"][b, 0], T / substeps)
+            new[b] = x
+        state = new
+        traj.append(state.copy())
+    return np.stack(traj)
+
+
+def test_pendulum_closed_loop_matches_cpu_loop():
+    """BASELINE config 3 (receding horizon): device loop == CPU loop, 40 cycles."""
+    import torch
+
+    from qpmpc_b200 import pendulum_closed_loop
+    from qpmpc_b200.workloads import pendulum_batch, to_batched
+
+    w = pendulum_batch(48, seed=1)
+    ref = _cpu_closed_loop(w, 40)
+    prob = to_batched(w)
+    plan, traj, unsolved = pendulum_closed_loop(prob, w["v_target"], 40, record=True)
+    torch.cuda.synchronize()
+    assert int(unsolved.item()) == 0
+    got = traj.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-6, np.abs(got - ref).max()
+    # the bound |u| <= 10 is active early on for some instances (non-degenerate benchmark)
+    assert np.abs(prob.x0.cpu().numpy() - ref[-1]).max() <= 1e-6
+
+
+def test_pendulum_closed_loop_200_cycles_stays_upright():
+    """Full-length loop: every instance has a plan in every cycle; the instances
+    the bounded input can recover (most of this distribution) stay upright and
+    their ground velocity converges to its target (size-independent property)."""
+    import torch
+
+    from qpmpc_b200 import pendulum_closed_loop
+    from qpmpc_b200.workloads import pendulum_batch, to_batched
+
+    w = pendulum_batch(2048, seed=1)
+    prob = to_batched(w)
+    plan, traj, unsolved = pendulum_closed_loop(prob, w["v_target"], 200, record=True)
+    torch.cuda.synchronize()
+    assert int(unsolved.item()) == 0
+    X = traj.cpu().numpy()
+    assert np.isfinite(X).all()
+    upright = np.abs(X[:, :, 1]).max(axis=0) < 1.2
+    assert upright.mean() > 0.9, upright.mean()
+    assert np.abs(X[-1, upright, 2] - w["v_target"][upright]).max() < 5e-2
