@@ -23,6 +23,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC",
 ]
+# tuning experiments: QPMPC_MINB=<resident CTAs/SM> overrides the kernels' default
+if os.environ.get("QPMPC_MINB"):
+    NVCC_FLAGS.append("-DQPMPC_MINB=" + os.environ["QPMPC_MINB"])
 
 
 def _nvcc() -> str:

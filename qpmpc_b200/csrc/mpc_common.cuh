@@ -32,7 +32,8 @@ struct SolveParams {
     double tol;
     // shared-memory geometry (elements of T), computed by the host
     int inst_stride;     // per-instance work region
-    int tail_elems;      // runtime-sized tail of the work region (see tail_elems())
+    int toeplitz;        // 1: A, B, C time-invariant and nx in registers -> G kept as a table
+    int gt_off, g_off, scr_off;  // tail regions of the work region (TailLay)
     int input_elems;     // CTA-level input region
     // outputs
     void *U;
@@ -51,9 +52,51 @@ __device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
 __device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
 __device__ __forceinline__ float sqrt_(float v) { return sqrtf(v); }
-// Reciprocal (correctly rounded): a * rcp_(b) replaces a / b where one ulp is irrelevant.
-__device__ __forceinline__ double rcp_(double v) { return __drcp_rn(v); }
+// Branch-free reciprocal and reciprocal square root for well-scaled positive
+// (rcp: non-zero) arguments: the SFU seed (about 20 bits) plus two Newton
+// steps, ~1 ulp.  The library versions spend most of their instructions on
+// subnormal / infinity handling the solver never needs; zero, subnormal and
+// negative arguments give inf / NaN, which the callers test for.
+__device__ __forceinline__ double rcp_(double v) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    double e = fma(-v, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-v, r, 1.0);
+    return fma(r, e, r);
+}
 __device__ __forceinline__ float rcp_(float v) { return __frcp_rn(v); }
+__device__ __forceinline__ double frsqrt_(double v) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    const double h = 0.5 * v;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ float frsqrt_(float v) { return rsqrtf(v); }
+
+// Exact minimum / maximum of non-negative values over the lanes in `mask`
+// (every lane of the mask calls with the same mask): one or two REDUX.
+__device__ __forceinline__ double seg_min_pos(double v, unsigned mask) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(mask, hi);
+    const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ float seg_min_pos(float v, unsigned mask) {
+    return __uint_as_float(__reduce_min_sync(mask, __float_as_uint(v)));
+}
+__device__ __forceinline__ double seg_max_pos(double v, unsigned mask) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(mask, hi);
+    const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ float seg_max_pos(float v, unsigned mask) {
+    return __uint_as_float(__reduce_max_sync(mask, __float_as_uint(v)));
+}
 __device__ __forceinline__ double abs_(double v) { return fabs(v); }
 __device__ __forceinline__ float abs_(float v) { return fabsf(v); }
 

@@ -28,24 +28,29 @@
 
 #include "mpc_common.cuh"
 
+// Resident CTAs of 128 threads per SM the register-resident variants are
+// compiled for (caps registers per thread at 65536 / (128 * QPMPC_MINB)).
+#ifndef QPMPC_MINB
+#define QPMPC_MINB 3
+#endif
+
 namespace qpmpc {
 
-template <typename T, int NP, int MR>
+template <typename T, int NP, int MR, bool MREG>
 struct Lay {
     static constexpr int MP = MR * NP;     // padded constraint rows
     static constexpr int LDG = MP + 1;     // G / M by columns: Gc[c*LDG + row]
     static constexpr int LDL = NP + 2;     // L by columns:     Lc[c*LDL + row]
-    static constexpr int LDR = NP + 1;     // R by columns:     Rc[k*LDR + row]
-    static constexpr int oG = 0;
     static constexpr int szG = ((NP * LDG + 3) / 4) * 4;
-    static constexpr int oH = oG + szG;    // hs[MP]
-    static constexpr int oRL = oH + MP;    // psi exchange (A), Lc (B), Rc (C)
+    static constexpr int oH = 0;           // hs[MP]
+    static constexpr int oRL = oH + MP;    // psi exchange (A), Lc (B and, if MREG, the final solve)
     static constexpr int szRL = ((NP * LDL + 3) / 4) * 4;
-    static constexpr int oV = oRL + szRL;  // qs, xs, dv, dd, d2 [NP each], sc[8]
+    // R^-1 by columns: its own region when L must survive (MREG), else over L
+    static constexpr int oRi = MREG ? oRL + szRL : oRL;
+    static constexpr int oV = oRL + szRL + (MREG ? NP * NP : 0);  // qs, xs, dv, dd, d2 [NP each], sc[8]
     static constexpr int szV = 5 * NP + 8;
-    static constexpr int fixed = oV + szV;  // runtime-sized tail follows
-    // R^-1 (NP x NP by columns) lives in the G region once M is in registers.
-    static_assert(NP * NP <= szG, "R^-1 must fit in the G region");
+    static constexpr int fixed = oV + szV;  // runtime-sized tail follows (TailLay)
+    static_assert(NP * NP <= szRL, "R^-1 must fit in the L region");
     static_assert(8 * NP <= szRL, "psi exchange buffers must fit in the L region");
 };
 
@@ -56,12 +61,38 @@ __host__ __device__ inline int generic_condense_elems(int NP, int nx) {
 }
 __host__ __device__ inline bool nx_in_registers(int nx) { return nx >= 2 && nx <= 4; }
 
-// Runtime-sized tail of the per-instance region: generic condensing scratch
-// and/or R^-1 when M occupies the G region (MREG = false).
-__host__ __device__ inline int tail_elems(int NP, int nx, bool mreg) {
-    int a = nx_in_registers(nx) ? 0 : generic_condense_elems(NP, nx);
-    int b = mreg ? 0 : NP * NP;
-    return a > b ? a : b;
+// Runtime-sized tail of the per-instance work region, after Lay::fixed:
+//   gt   nc x n   Toeplitz table of G (time-invariant A, B, C only), see g_toeplitz()
+//   G    szG      dense G by columns; absent when the table replaces it and M
+//                 lives in registers
+//   scr           scratch of the generic condensing (nx outside 2..4)
+struct TailLay {
+    int gt_off, g_off, scr_off, total;  // offsets from the start of the instance region
+};
+__host__ __device__ inline TailLay tail_layout(int fixed, int szG, int NP, int nx, int nc, int n, bool toeplitz,
+                                               bool mreg) {
+    TailLay t;
+    int o = fixed;
+    t.gt_off = o;
+    o += toeplitz ? (nc * n + 3) / 4 * 4 : 0;
+    t.g_off = o;
+    o += (toeplitz && mreg) ? 0 : szG;
+    t.scr_off = o;
+    o += nx_in_registers(nx) ? 0 : generic_condense_elems(NP, nx);
+    t.total = o;
+    return t;
+}
+
+// Entry (row, c) of G from the Toeplitz table.  With time-invariant A, B, C
+// the block G[(k, r), c] = C_r A^(k-1-j) B[:, jj] (c = j nu + jj, j < k) depends
+// on k nu - 1 - c only: gt[r*n + e] = C_r psi_N[:, n-1-e] holds all of them.
+// Block column k carries D_k (mpc_qp.py:73-78); everything to its right is 0.
+template <typename T>
+__device__ __forceinline__ T g_toeplitz(const T *gt, const T *Dk, int n, int nu, int k, int r, int c) {
+    const int kb = k * nu;
+    if (c < kb) return gt ? gt[r * n + kb - 1 - c] : T(0);  // no C: only D contributes
+    if (Dk && c - kb < nu) return Dk[r * nu + c - kb];
+    return T(0);
 }
 
 // ---------------------------------------------------------------------------
@@ -133,10 +164,11 @@ __device__ __forceinline__ void prow_axpy(T (&Prow)[NP], T a, const T *v) {
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, int NX, bool DUMP>  // @phase A condense (registers)
 __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *const (&in)[OP_COUNT], T *Gc,
-                                             T *hs, T *xch, int l, T (&Prow)[NP], T &qj, long long inst,
+                                             T *gt, T *hs, T *xch, int l, T (&Prow)[NP], T &qj, long long inst,
                                              bool valid) {
-    using L = Lay<T, NP, MR>;
+    using L = Lay<T, NP, MR, false>;  // only LDG is used here
     const int nu = p.nu, nc = p.nc, N = p.N, n = p.n;
+    const bool toep = p.toeplitz != 0;
     const T w_t = (T)p.w_t, w_x = (T)p.w_x;
     T psi[NX], xb[NX], Ar[NX * NX];
     T phi[DUMP ? NX * NX : 1];
@@ -152,34 +184,38 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
 #pragma unroll
         for (int t = 0; t < NX * NX; ++t) phi[DUMP ? t : 0] = (t / NX == t % NX) ? T(1) : T(0);
     }
-    const int stepA = p.op[OP_A].step;
+    const int stepA = p.op[OP_A].step, stepB = p.op[OP_B].step, stepC = p.op[OP_C].step;
+    const int stepD = p.op[OP_D].step, stepE = p.op[OP_E].step;
+    const T *Ak = in[OP_A], *Bk = in[OP_B], *Ck = in[OP_C], *Dk = in[OP_D], *ek = in[OP_E];
+    const bool hasC = Ck != nullptr, hasD = Dk != nullptr;
+    const bool needG = !toep;  // with the Toeplitz table, G rows are rebuilt from psi_N
+    const int kb = l / nu, jb = l - kb * nu;  // block and position inside it of this lane's variable
+    T *gcol = Gc + l * L::LDG;
+    int row = 0;
 #pragma unroll
-    for (int t = 0; t < NX * NX; ++t) Ar[t] = in[OP_A][t];
+    for (int t = 0; t < NX * NX; ++t) Ar[t] = Ak[t];
     for (int k = 0; k < N; ++k) {
         if (stepA != 0 && k > 0) {
 #pragma unroll
-            for (int t = 0; t < NX * NX; ++t) Ar[t] = in[OP_A][k * stepA + t];
+            for (int t = 0; t < NX * NX; ++t) Ar[t] = Ak[t];
         }
-        const T *Bk = in[OP_B] + k * p.op[OP_B].step;
-        const T *Ck = in[OP_C] ? in[OP_C] + k * p.op[OP_C].step : nullptr;
-        const T *Dk = in[OP_D] ? in[OP_D] + k * p.op[OP_D].step : nullptr;
-        const T *ek = in[OP_E] ? in[OP_E] + k * p.op[OP_E].step : nullptr;
-        const int jj = l - k * nu;  // position of this lane's variable inside block k
-        const bool inblk = (unsigned)jj < (unsigned)nu;
+        const bool inblk = (k == kb);
         // G_k = C_k psi_k + [0 .. D_k .. 0], h_k = e_k - C_k (phi_k x0)   (mpc_qp.py:67-78)
-        for (int r = 0; r < nc; ++r) {
+        for (int r = 0; r < nc; ++r, ++row) {
             T g = T(0), hv = ek[r];
-            if (Ck) {
+            if (hasC) {
 #pragma unroll
                 for (int t = 0; t < NX; ++t) {
                     const T c = Ck[r * NX + t];
-                    g += c * psi[t];
+                    if (needG) g += c * psi[t];
                     hv -= c * xb[t];
                 }
             }
-            if (Dk && inblk) g += Dk[r * nu + jj];
-            Gc[l * L::LDG + k * nc + r] = g;
-            if (l == 0) hs[k * nc + r] = hv;
+            if (needG) {
+                if (hasD && inblk) g += Dk[r * nu + jb];
+                gcol[row] = g;
+            }
+            if (l == 0) hs[row] = hv;
         }
         if (DUMP && valid) {
             if (p.Psi && l < n) {
@@ -217,7 +253,7 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
                 a += Ar[t * NX + s] * psi[s];
                 b += Ar[t * NX + s] * xb[s];
             }
-            if (inblk) a = Bk[t * nu + jj];
+            if (inblk) a = Bk[t * nu + jb];
             pn[t] = a;
             xn[t] = b;
         }
@@ -237,6 +273,20 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
         for (int t = 0; t < NX; ++t) {
             psi[t] = pn[t];
             xb[t] = xn[t];
+        }
+        Ak += stepA;
+        Bk += stepB;
+        Ck += hasC ? stepC : 0;
+        Dk += hasD ? stepD : 0;
+        ek += stepE;
+    }
+    // Toeplitz table of G: gt[r][n-1-l] = C_r psi_N[:, l]
+    if (toep && in[OP_C] && l < n) {
+        for (int r = 0; r < nc; ++r) {
+            T g = T(0);
+#pragma unroll
+            for (int t = 0; t < NX; ++t) g += in[OP_C][r * NX + t] * psi[t];
+            gt[r * n + n - 1 - l] = g;
         }
     }
     // terminal cost: P += w_t psi_N' psi_N, q += w_t psi_N'(phi_N x0 - goal)
@@ -279,7 +329,7 @@ template <typename T, int NP, int MR, bool DUMP>  // @phase A condense (generic 
 __device__ __forceinline__ void condense_generic(const SolveParams &p, const T *const (&in)[OP_COUNT], T *Gc,
                                               T *hs, T *scr, int l, T (&Prow)[NP], T &qj, long long inst,
                                               bool valid) {
-    using L = Lay<T, NP, MR>;
+    using L = Lay<T, NP, MR, false>;  // only LDG is used here
     const int nx = p.nx, nu = p.nu, nc = p.nc, N = p.N, n = p.n;
     T *psi = scr;
     T *xbar = psi + 2 * nx * NP;
@@ -383,63 +433,81 @@ __device__ __forceinline__ void condense_generic(const SolveParams &p, const T *
 
 template <typename T, int NP, int MR, bool DUMP>
 __device__ __forceinline__ void condense_dispatch(const SolveParams &p, const T *const (&in)[OP_COUNT], T *Gc,
-                                                  T *hs, T *xch, T *tail, int l, T (&Prow)[NP], T &qj,
+                                                  T *gt, T *hs, T *xch, T *scr, int l, T (&Prow)[NP], T &qj,
                                                   long long inst, bool valid) {
     switch (p.nx) {
-        case 2: condense_reg<T, NP, MR, 2, DUMP>(p, in, Gc, hs, xch, l, Prow, qj, inst, valid); break;
-        case 3: condense_reg<T, NP, MR, 3, DUMP>(p, in, Gc, hs, xch, l, Prow, qj, inst, valid); break;
-        case 4: condense_reg<T, NP, MR, 4, DUMP>(p, in, Gc, hs, xch, l, Prow, qj, inst, valid); break;
-        default: condense_generic<T, NP, MR, DUMP>(p, in, Gc, hs, tail, l, Prow, qj, inst, valid); break;
+        case 2: condense_reg<T, NP, MR, 2, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
+        case 3: condense_reg<T, NP, MR, 3, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
+        case 4: condense_reg<T, NP, MR, 4, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
+        default: condense_generic<T, NP, MR, DUMP>(p, in, Gc, hs, scr, l, Prow, qj, inst, valid); break;
     }
 }
 
 // ---------------------------------------------------------------------------
-// Forward substitution L y = rhs for two right-hand sides held in registers,
+// Forward substitution L y = rhs for NR right-hand sides held in registers,
 // L by columns in shared memory (Lc), 1/L_kk in dv.  Lane-local: every lane
 // solves its own systems; all lanes read the same L entries (broadcast).
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int LDL>
-__device__ __forceinline__ void fsolve2(const T *Lc, const T *dv, T (&a)[NP], T (&b)[NP]) {
+template <typename T, int NP, int LDL, int NR>
+__device__ __forceinline__ void fsolve(const T *Lc, const T *dv, T (&a)[NR][NP]) {
     using T2 = typename Pair<T>::type;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const T dk = dv[k];
-        const T ak = a[k] * dk, bk = b[k] * dk;
-        a[k] = ak;
-        b[k] = bk;
+        T ak[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            ak[i] = a[i][k] * dk;
+            a[i][k] = ak[i];
+        }
         if (((k + 1) & 1) && k + 1 < NP) {
             const T lv = Lc[k * LDL + k + 1];
-            a[k + 1] -= lv * ak;
-            b[k + 1] -= lv * bk;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) a[i][k + 1] -= lv * ak[i];
         }
 #pragma unroll
         for (int c = (k + 2) & ~1; c < NP; c += 2) {
             const T2 lv = *reinterpret_cast<const T2 *>(Lc + k * LDL + c);
-            a[c] -= lv.x * ak;
-            a[c + 1] -= lv.y * ak;
-            b[c] -= lv.x * bk;
-            b[c + 1] -= lv.y * bk;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                a[i][c] -= lv.x * ak[i];
+                a[i][c + 1] -= lv.y * ak[i];
+            }
         }
     }
 }
 
-// Sortable 64-bit key of a positive score and a row index < 128: larger score
-// wins, ties go to the lower index.  0 means "no candidate".
-__device__ __forceinline__ unsigned long long score_key(double s, int idx) {
-    return ((unsigned long long)__double_as_longlong(s) & ~127ull) | (unsigned)(127 - idx);
+// Minimum / maximum of non-negative values over the NP lanes of an instance.
+template <typename T, int NP>
+__device__ __forceinline__ T group_min_pos(T v, unsigned segmask) {
+    if (NP == 32) return seg_min_pos(v, segmask);
+#pragma unroll
+    for (int off = NP / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
+    return v;
 }
-__device__ __forceinline__ unsigned long long score_key(float s, int idx) {
-    return ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)(127 - idx);
+template <typename T, int NP>
+__device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
+    if (NP == 32) return seg_max_pos(v, segmask);
+#pragma unroll
+    for (int off = NP / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
+    return v;
 }
 
 // ---------------------------------------------------------------------------
-// The fused kernel.  MREG: rows of M = G J live in registers (NP <= 16);
-// otherwise M overwrites G in shared memory.
+// The fused kernel.
+//   MREG = true  (NP <= 16): the owned rows of M = G J live in registers and J
+//     itself is never formed: the iteration only needs rows of M (d = -M_p,
+//     G z = M2 d2), and x is recovered once, at the end, from the multipliers:
+//     x = -P^-1 (q + G_A' lambda) through two triangular solves with L.
+//   MREG = false (NP = 32, or 4 rows per lane at NP = 16): M overwrites G in
+//     shared memory, row l of J is kept in registers and x moves with every
+//     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool MREG>  // @phase kernel prologue
-__global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_kernel(const SolveParams p) {
-    using L = Lay<T, NP, MR>;
+__global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_solve_kernel(const SolveParams p) {
+    using L = Lay<T, NP, MR, MREG>;
     using T2 = typename Pair<T>::type;
+    constexpr bool HASJ = !MREG;
     constexpr int IPW = 32 / NP;  // instances per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -451,6 +519,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
     const int sub = lane / NP;
     const int l = lane % NP;
     const int seg_shift = sub * NP;
+    const unsigned segmask = (NP == 32) ? FULL_MASK : (((1u << (NP & 31)) - 1u) << seg_shift);
     const int iic = warp * IPW + sub;  // instance slot inside the CTA
     const int inst0 = blockIdx.x * ipc;
     const int cnt = min(ipc, p.batch - inst0);
@@ -462,18 +531,18 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
     stage_inputs<T>(p, inbase, inst0, cnt, bar);
 
     T *wk = work + (size_t)iic * p.inst_stride;
-    T *Gc = wk + L::oG;
+    T *Gc = wk + p.g_off;
+    T *gt = p.op[OP_C].ptr ? wk + p.gt_off : nullptr;
     T *hs = wk + L::oH;
     T *Lc = wk + L::oRL;
-    T *Rc = wk + L::oRL;
+    T *Ri = wk + L::oRi;  // R^-1 by columns, Ri[k*NP + row]
     T *qs = wk + L::oV;
     T *xs = qs + NP;
     T *dv = qs + 2 * NP;
     T *dd = qs + 3 * NP;
     T *d2 = qs + 4 * NP;
     T *sc = qs + 5 * NP;
-    T *tail = wk + L::fixed;
-    T *Ri = MREG ? Gc : tail;  // R^-1 by columns: Ri[k*NP + row]
+    const bool toep = p.toeplitz != 0;
 
     const T *in[OP_COUNT];
 #pragma unroll
@@ -486,16 +555,21 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
     // ---- phase A -----------------------------------------------------------
     T Prow[NP];
     T qj;
-    condense_dispatch<T, NP, MR, false>(p, in, Gc, hs, Lc, tail, l, Prow, qj, inst, valid);
+    condense_dispatch<T, NP, MR, false>(p, in, Gc, gt, hs, Lc, wk + p.scr_off, l, Prow, qj, inst, valid);
 
     // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----  // @phase B cholesky
     bool spd = true;
     qs[l] = qj;
+    // Shared vectors start finite: lanes of finished instances keep computing
+    // with them (their results are multiplied by a zero step).
+    dd[l] = T(0);
+    d2[l] = T(0);
+    if (l < 2) sc[l] = T(0);
 #pragma unroll
     for (int c = 0; c < NP; ++c) {
         const T piv = __shfl_sync(FULL_MASK, Prow[c], c, NP);
         spd = spd && (piv > T(0));
-        const T inv = rsqrt_(piv);
+        const T inv = frsqrt_(piv);
         const T lc = Prow[c] * inv;
         Lc[c * L::LDL + l] = lc;
         if (l == c) dv[c] = inv;
@@ -508,82 +582,149 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
             Prow[i + 1] -= lc * v.y;
         }
     }
-    // Row l of J = L^-T is column l of L^-1: solve L y = e_l; t = L^-1 q = J'q
-    // with the same sweep; x = -J t.  // @phase B J=L^-T, x=-P^-1 q
-    T Jrow[NP];
-    T x;
+
+    // Forward substitutions with L, lane-local.  t = L^-1 q always; row l of
+    // J = L^-T (column l of L^-1) when J is kept; the owned rows of M = G J
+    // (solve L m' = g').  // @phase B substitutions: t, J, M; violations
+    T Jrow[HASJ ? NP : 1];
+    T Mrow[MREG ? MR : 1][NP];
+    T x = T(0);
+    T viol[MR], mn2[MR], vtol[MR], ginv[MR];
+    bool rowvalid[MR];
     {
-        T tq[NP];
+        T rhs[3][NP];  // [0] = t, [1..2] = J row / rows of G
 #pragma unroll
         for (int c = 0; c < NP; c += 2) {
             const T2 v = *reinterpret_cast<const T2 *>(qs + c);
-            tq[c] = v.x;
-            tq[c + 1] = v.y;
-            Jrow[c] = (c == l) ? T(1) : T(0);
-            Jrow[c + 1] = (c + 1 == l) ? T(1) : T(0);
+            rhs[0][c] = v.x;
+            rhs[0][c + 1] = v.y;
         }
-        fsolve2<T, NP, L::LDL>(Lc, dv, Jrow, tq);
-        T x0 = T(0), x1 = T(0);
+        // loads the rows s0, s0+1 of G into rhs[1..2]; row norms and tolerances
+        auto load_rows = [&](int s0) {
 #pragma unroll
-        for (int c = 0; c < NP; c += 2) {
-            x0 -= Jrow[c] * tq[c];
-            x1 -= Jrow[c + 1] * tq[c + 1];
-        }
-        x = x0 + x1;
-    }
-    xs[l] = x;
-    __syncwarp();
-
-    // Owned rows of M = G J: solve L m' = g' per row; violations, row norms.  // @phase B M=GJ, violations
-    T Mrow[MREG ? MR : 1][NP];
-    T viol[MR], mn2[MR], vtol[MR], ginv[MR];
-    bool rowvalid[MR];
-#pragma unroll
-    for (int s0 = 0; s0 < MR; s0 += 2) {
-        T acc[2][NP];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int s = s0 + u;
-            const int row = l + s * NP;
-            rowvalid[s] = row < m;
-            T vi0 = T(0), vi1 = T(0), g2 = T(0);
-#pragma unroll
-            for (int k = 0; k < NP; k += 2) {
-                const T ga = rowvalid[s] ? Gc[k * L::LDG + row] : T(0);
-                const T gb = rowvalid[s] ? Gc[(k + 1) * L::LDG + row] : T(0);
-                const T2 xv = *reinterpret_cast<const T2 *>(xs + k);
-                acc[u][k] = ga;
-                acc[u][k + 1] = gb;
-                g2 += ga * ga;
-                g2 += gb * gb;
-                vi0 += ga * xv.x;
-                vi1 += gb * xv.y;
-            }
-            // Tolerance of the violation test: eps * (max(1, |h_i|) + |G_i|).
-            const T hi = rowvalid[s] ? hs[row] : T(0);
-            viol[s] = rowvalid[s] ? (vi0 + vi1) - hi : T(-1);
-            vtol[s] = Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2));
-            ginv[s] = g2 > T(0) ? rsqrt_(g2) : T(1e30);
-        }
-        fsolve2<T, NP, L::LDL>(Lc, dv, acc[0], acc[1]);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int s = s0 + u;
-            T m0 = T(0), m1 = T(0);
-#pragma unroll
-            for (int c = 0; c < NP; c += 2) {
-                m0 += acc[u][c] * acc[u][c];
-                m1 += acc[u][c + 1] * acc[u][c + 1];
-            }
-            mn2[s] = m0 + m1;
-            if (MREG) {
-#pragma unroll
-                for (int c = 0; c < NP; ++c) Mrow[MREG ? s : 0][c] = acc[u][c];
-            } else {
-                // In place: this lane is the only reader and writer of its rows of G.
+            for (int u = 0; u < 2; ++u) {
+                const int s = s0 + u;
                 const int row = l + s * NP;
+                rowvalid[s] = row < m;
+                T g2 = T(0), g21 = T(0);
+                // (k, r) of this row and its slice of the Toeplitz table
+                const int rk = rowvalid[s] ? row / p.nc : 0, rr = rowvalid[s] ? row - rk * p.nc : 0;
+                const T *Dk = (toep && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
 #pragma unroll
-                for (int c = 0; c < NP; ++c) Gc[c * L::LDG + row] = acc[u][c];
+                for (int k = 0; k < NP; k += 2) {
+                    T ga = T(0), gb = T(0);
+                    if (rowvalid[s]) {
+                        if (toep) {
+                            ga = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k);
+                            gb = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k + 1);
+                        } else {
+                            ga = Gc[k * L::LDG + row];
+                            gb = Gc[(k + 1) * L::LDG + row];
+                        }
+                    }
+                    rhs[1 + u][k] = ga;
+                    rhs[1 + u][k + 1] = gb;
+                    g2 += ga * ga;
+                    g21 += gb * gb;
+                }
+                g2 += g21;
+                // Tolerance of the violation test: eps * (max(1, |h_i|) + |G_i|).
+                const T hi = rowvalid[s] ? hs[row] : T(0);
+                viol[s] = -hi;
+                vtol[s] = Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2));
+                ginv[s] = g2 > T(0) ? frsqrt_(g2) : T(1e30);
+            }
+        };
+        // finishes rows s0, s0+1: M t (= -G x), |M_i|^2, and stores the rows
+        auto store_rows = [&](int s0) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int s = s0 + u;
+                T m0 = T(0), m1 = T(0), v0 = T(0), v1 = T(0);
+#pragma unroll
+                for (int c = 0; c < NP; c += 2) {
+                    m0 += rhs[1 + u][c] * rhs[1 + u][c];
+                    m1 += rhs[1 + u][c + 1] * rhs[1 + u][c + 1];
+                    v0 += rhs[1 + u][c] * rhs[0][c];
+                    v1 += rhs[1 + u][c + 1] * rhs[0][c + 1];
+                }
+                mn2[s] = m0 + m1;
+                // G x - h with x = -P^-1 q = -J t: G x = -(G J) t = -M t
+                viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : T(-1);
+                if (MREG) {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) Mrow[MREG ? s : 0][c] = rhs[1 + u][c];
+                } else {
+                    // In place: this lane is the only reader and writer of its rows of G.
+                    const int row = l + s * NP;
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) Gc[c * L::LDG + row] = rhs[1 + u][c];
+                }
+            }
+        };
+        if (HASJ) {
+            // t and the J row first; then the rows of M two at a time
+#pragma unroll
+            for (int c = 0; c < NP; ++c) rhs[1][c] = (c == l) ? T(1) : T(0);
+            {
+                T pair[2][NP];
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    pair[0][c] = rhs[0][c];
+                    pair[1][c] = rhs[1][c];
+                }
+                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
+                T x0 = T(0), x1 = T(0);
+#pragma unroll
+                for (int c = 0; c < NP; c += 2) {
+                    x0 -= pair[1][c] * pair[0][c];
+                    x1 -= pair[1][c + 1] * pair[0][c + 1];
+                }
+                x = x0 + x1;
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    rhs[0][c] = pair[0][c];
+                    Jrow[HASJ ? c : 0] = pair[1][c];
+                }
+            }
+#pragma unroll
+            for (int s0 = 0; s0 < MR; s0 += 2) {
+                load_rows(s0);
+                T pair[2][NP];
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    pair[0][c] = rhs[1][c];
+                    pair[1][c] = rhs[2][c];
+                }
+                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    rhs[1][c] = pair[0][c];
+                    rhs[2][c] = pair[1][c];
+                }
+                store_rows(s0);
+            }
+        } else {
+            // t rides along with the first two rows of M
+            load_rows(0);
+            fsolve<T, NP, L::LDL, 3>(Lc, dv, rhs);
+            store_rows(0);
+#pragma unroll
+            for (int s0 = 2; s0 < MR; s0 += 2) {
+                load_rows(s0);
+                T pair[2][NP];
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    pair[0][c] = rhs[1][c];
+                    pair[1][c] = rhs[2][c];
+                }
+                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    rhs[1][c] = pair[0][c];
+                    rhs[2][c] = pair[1][c];
+                }
+                store_rows(s0);
             }
         }
     }
@@ -594,9 +735,15 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
         else
             Gc[c * L::LDG + l + s * NP] = v;
     };
-    __syncwarp();  // G (when MREG) and Lc are dead from here on: R^-1 and R take their place
+    __syncwarp();
 
     // ---- phase C: dual active-set iteration ---------------------------------  // @phase C select row (step 1)
+    // R^-1 starts as the zero matrix: its product with the zero-padded d1 then
+    // needs no guards (entries below the diagonal stay zero throughout).  When
+    // J is kept, L is dead and R^-1 takes its place; otherwise L survives for
+    // the final solve and R^-1 has a region of its own.
+#pragma unroll
+    for (int k = 0; k < NP; ++k) Ri[k * NP + l] = T(0);
     const int max_iter = p.max_iter;
     int na = 0, it = 0;
     int st = spd ? 0 : 3;
@@ -607,29 +754,30 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
     int aidx = -1;
     unsigned actbits = 0;
     const T INF = Num<T>::inf();
+    __syncwarp();
 
     while (true) {
         {
             // step 1: most violated inactive row, relative to its norm
             const bool sel = !done && !cont;
-            unsigned long long key = 0ull;
+            T best = T(0);
+            int bi = 0;
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
-                if (sel && rowvalid[s] && !((actbits >> s) & 1) && viol[s] > vtol[s]) {
-                    const unsigned long long ks = score_key(viol[s] * ginv[s], l + s * NP);
-                    key = ks > key ? ks : key;
+                const T score = viol[s] * ginv[s];
+                if (sel && rowvalid[s] && !((actbits >> s) & 1) && viol[s] > vtol[s] && score > best) {
+                    best = score;
+                    bi = l + s * NP;
                 }
             }
-#pragma unroll
-            for (int off = NP / 2; off > 0; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(FULL_MASK, key, off, NP);
-                key = o > key ? o : key;
-            }
+            const T top = group_max_pos<T, NP>(best, segmask);
+            const unsigned win = __ballot_sync(FULL_MASK, best == top) & segmask;
+            const int cand_p = __shfl_sync(FULL_MASK, bi, __ffs(win) - 1);
             if (sel) {
-                if (key == 0ull) {
+                if (!(top > T(0))) {
                     done = true;  // primal feasible: optimal
                 } else {
-                    pidx = 127 - (int)(key & 127ull);
+                    pidx = cand_p;
                     lamp = T(0);
                 }
             }
@@ -644,7 +792,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
                 act = false;
             }
         }
-        // d = J' n_p = -(row p of M): dd holds d, d2 its part beyond the active columns.  // @phase C publish d
+        // d = J' n_p = -(row p of M): dd holds its active part d1 (zero-padded), d2 the rest.  // @phase C publish d
         const int owner = pidx % NP, pslot = pidx / NP;
         T dl;
         if (MREG) {
@@ -668,7 +816,6 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
             dl = dd[l];
         } else {
             dl = -Gc[l * L::LDG + pidx];
-            dd[l] = dl;
             if (act && l == owner) {
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
@@ -679,9 +826,10 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
                 }
             }
         }
+        dd[l] = (l < na) ? dl : T(0);
         d2[l] = (l >= na) ? dl : T(0);
         __syncwarp();
-        // z = J2 d2 (this lane's component), G z (owned rows), |d2|^2  // @phase C z, Gz
+        // G z = M2 d2 (owned rows), |d2|^2, and z = J2 d2 when J is kept  // @phase C z, Gz
         T z = T(0), z1 = T(0), a2 = T(0), a21 = T(0);
         T gz[MR];
 #pragma unroll
@@ -689,8 +837,10 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
 #pragma unroll
         for (int c = 0; c < NP; c += 2) {
             const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-            z += Jrow[c] * v.x;
-            z1 += Jrow[c + 1] * v.y;
+            if (HASJ) {
+                z += Jrow[HASJ ? c : 0] * v.x;
+                z1 += Jrow[HASJ ? c + 1 : 0] * v.y;
+            }
             a2 += v.x * v.x;
             a21 += v.y * v.y;
 #pragma unroll
@@ -701,50 +851,51 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
         }
         z += z1;
         a2 += a21;
-        // r = R^-1 d1 (component l on lane l < na)  // @phase C r=R^-1 d
+        // r = R^-1 d1 (component l; zero on lanes >= na)  // @phase C r=R^-1 d
         T rv = T(0);
         {
+            T rv1 = T(0);
             const int namax = __reduce_max_sync(FULL_MASK, act ? na : 0);
-            for (int k = 0; k < namax; ++k) {
-                const T dk = dd[k];
-                const T ri = Ri[k * NP + l];
-                if (l <= k && k < na) rv += ri * dk;
+            for (int k = 0; k < namax; k += 2) {
+                const T2 dk = *reinterpret_cast<const T2 *>(dd + k);
+                rv += Ri[k * NP + l] * dk.x;
+                rv1 += Ri[(k + 1) * NP + l] * dk.y;
             }
+            rv += rv1;
         }
         // step lengths  // @phase C step length, move
-        const T cand = (act && l < na && rv > T(0)) ? lam * rcp_(rv) : INF;
-        T t1 = cand;
-#pragma unroll
-        for (int off = NP / 2; off > 0; off >>= 1) t1 = fmin(t1, __shfl_xor_sync(FULL_MASK, t1, off, NP));
-        const unsigned bal = __ballot_sync(FULL_MASK, cand == t1 && cand < INF);
-        const unsigned segbits = (NP == 32) ? bal : ((bal >> seg_shift) & ((1u << (NP & 31)) - 1u));
-        const int lidx = segbits ? (__ffs(segbits) - 1) : 0;
+        const T cand = (act && l < na && rv > T(0)) ? fmax(lam, T(0)) * rcp_(rv) : INF;
+        const T t1 = group_min_pos<T, NP>(cand, segmask);
+        const unsigned bal = __ballot_sync(FULL_MASK, cand == t1 && cand < INF) & segmask;
+        const int lidx = bal ? (__ffs(bal) - 1 - seg_shift) : 0;
         const T violp = sc[0], dn2 = sc[1];
         const bool zzero = !(a2 > Num<T>::dep_eps * dn2);
-        const T t2 = zzero ? INF : violp * rcp_(a2);
+        const T ainv = frsqrt_(a2);  // 1 / |d2|
+        const T t2 = zzero ? INF : violp * (ainv * ainv);
         if (act && t1 == INF && t2 == INF) {
             st = 2;  // infeasible
             done = true;
             act = false;
         }
         const T t = fmin(t1, t2);
-        if (act) {
-            if (!zzero) {
-                x += t * z;
+        {
+            // unconditional updates with a zero step where nothing moves (all
+            // operands are finite on finished instances, so 0 * v adds nothing)
+            const T tp = (act && !zzero) ? t : T(0);
+            const T td = act ? t : T(0);
+            if (HASJ) x += tp * z;
 #pragma unroll
-                for (int s = 0; s < MR; ++s) viol[s] += t * gz[s];
-            }
-            if (l < na) lam -= t * rv;
-            lamp += t;
+            for (int s = 0; s < MR; ++s) viol[s] += tp * gz[s];
+            lam -= td * rv;
+            lamp += td;
         }
         const bool full = act && !zzero && t2 <= t1;
         const bool part = act && !full;
 
         if (__any_sync(FULL_MASK, full)) {  // @phase C add constraint (Householder)
             // Constraint p enters: reflect d2 onto its first entry.  H = I - tau v v',
-            // v = d2 - beta e_na, applied to columns >= na of J and M.
+            // v = d2 - beta e_na, applied to columns >= na of M (and of J).
             const T dna = d2[na < NP ? na : NP - 1];
-            const T ainv = rsqrt_(a2);
             const T alpha = a2 * ainv;
             const T beta = (dna > T(0)) ? -alpha : alpha;
             const T binv = (dna > T(0)) ? -ainv : ainv;
@@ -759,8 +910,10 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
 #pragma unroll
             for (int c = 0; c < NP; c += 2) {
                 const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-                dj += Jrow[c] * v.x;
-                dj1 += Jrow[c + 1] * v.y;
+                if (HASJ) {
+                    dj += Jrow[HASJ ? c : 0] * v.x;
+                    dj1 += Jrow[HASJ ? c + 1 : 0] * v.y;
+                }
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
                     dm[s] += mget(s, c) * v.x;
@@ -773,8 +926,10 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
 #pragma unroll
             for (int c = 0; c < NP; c += 2) {
                 const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-                Jrow[c] -= dj * v.x;
-                Jrow[c + 1] -= dj * v.y;
+                if (HASJ) {
+                    Jrow[HASJ ? c : 0] -= dj * v.x;
+                    Jrow[HASJ ? c + 1 : 0] -= dj * v.y;
+                }
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
                     mset(s, c, mget(s, c) - dm[s] * v.x);
@@ -782,13 +937,9 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
                 }
             }
             if (full) {
-                // new column of R: [d1; beta]; of R^-1: [-r / beta; 1 / beta]
-                if (l < na) {
-                    Rc[na * L::LDR + l] = dl;
-                    Ri[na * NP + l] = -rv * binv;
-                }
+                // R gains the column [d1; beta]: R^-1 gains [-r / beta; 1 / beta]
+                if (l < na) Ri[na * NP + l] = -rv * binv;
                 if (l == na) {
-                    Rc[na * L::LDR + na] = beta;
                     Ri[na * NP + na] = binv;
                     lam = lamp;
                     aidx = pidx;
@@ -810,40 +961,36 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
                 lam = lam_n;
                 aidx = aidx_n;
             }
-            // shift columns lidx+1.. of R one to the left
-            const int namax = __reduce_max_sync(FULL_MASK, part ? na : 0);
-            for (int row = 0; row < namax; ++row) {
-                T v = T(0);
-                const bool mv = mover && row <= l + 1;
-                if (mv) v = Rc[(l + 1) * L::LDR + row];
-                __syncwarp();
-                if (mv) Rc[l * L::LDR + row] = v;
-            }
-            __syncwarp();
-            // Givens rotations of rows (j, j+1) of R restore the triangle; the
-            // same rotations act on columns (j, j+1) of J and M.
+            if (part && l == nan_) lam = T(0);  // the vacated position carries no multiplier
+            // Downdate through R^-1 alone: rotations of adjacent columns (j, j+1),
+            // j = lidx .. na-2, that zero row lidx of R^-1 Q up to its last entry;
+            // Q is the factor that re-triangularises R without column lidx, so the
+            // same rotations act on columns (j, j+1) of M (and J), and R'^-1 is
+            // R^-1 Q with row lidx and the last column removed.
+            T a = part ? Ri[lidx * NP + lidx] : T(1);
 #pragma unroll
             for (int j = 0; j < NP - 1; ++j) {
                 const bool rot = part && j >= lidx && j < nan_;
                 if (!__any_sync(FULL_MASK, rot)) continue;
-                T a = T(1), b = T(0);
-                if (rot) {
-                    a = Rc[j * L::LDR + j];
-                    b = Rc[j * L::LDR + j + 1];
-                }
+                const T b = rot ? Ri[(j + 1) * NP + lidx] : T(0);
+                __syncwarp();  // b is read before its owner rotates it
                 const T h2 = a * a + b * b;
-                const T hinv = h2 > T(0) ? rsqrt_(h2) : T(0);
-                const T cs = h2 > T(0) ? a * hinv : T(1);
-                const T sn = b * hinv;
-                if (rot && l >= j && l < nan_) {
-                    const T u = Rc[l * L::LDR + j], v = Rc[l * L::LDR + j + 1];
-                    Rc[l * L::LDR + j] = cs * u + sn * v;
-                    Rc[l * L::LDR + j + 1] = cs * v - sn * u;
-                }
+                const T hinv = h2 > T(0) ? frsqrt_(h2) : T(0);
+                const T cs = h2 > T(0) ? b * hinv : T(1);
+                const T sn = -a * hinv;
                 if (rot) {
-                    const T u = Jrow[j], v = Jrow[j + 1];
-                    Jrow[j] = cs * u + sn * v;
-                    Jrow[j + 1] = cs * v - sn * u;
+                    a = h2 * hinv;
+                    if (l <= j + 1) {
+                        // R^-1 is upper triangular: entry (j+1, j) is zero
+                        const T u = (l <= j) ? Ri[j * NP + l] : T(0), v = Ri[(j + 1) * NP + l];
+                        Ri[j * NP + l] = cs * u + sn * v;
+                        Ri[(j + 1) * NP + l] = cs * v - sn * u;
+                    }
+                    if (HASJ) {
+                        const T u = Jrow[HASJ ? j : 0], v = Jrow[HASJ ? j + 1 : 0];
+                        Jrow[HASJ ? j : 0] = cs * u + sn * v;
+                        Jrow[HASJ ? j + 1 : 0] = cs * v - sn * u;
+                    }
 #pragma unroll
                     for (int s = 0; s < MR; ++s) {
                         const T mu = mget(s, j), mv = mget(s, j + 1);
@@ -851,16 +998,18 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
                         mset(s, j + 1, cs * mv - sn * mu);
                     }
                 }
-                __syncwarp();
             }
-            // R^-1 of the reduced factor: lane j solves R y = e_j into column j.
-            if (part && l < nan_) {
-                const int j = l;
-                Ri[j * NP + j] = T(1) / Rc[j * L::LDR + j];
-                for (int i = j - 1; i >= 0; --i) {
-                    T s = T(0);
-                    for (int k = i + 1; k <= j; ++k) s += Rc[k * L::LDR + i] * Ri[j * NP + k];
-                    Ri[j * NP + i] = -s / Rc[i * L::LDR + i];
+            __syncwarp();
+            // remove row lidx: rows above move down one position
+            {
+                const int kmax = __reduce_max_sync(FULL_MASK, part ? nan_ : 0);
+                for (int k = 0; k < kmax; ++k) {
+                    const bool mv = mover && l <= k;
+                    T v = T(0);
+                    if (mv) v = Ri[k * NP + l + 1];
+                    __syncwarp();
+                    if (mv) Ri[k * NP + l] = v;
+                    if (part && l == k + 1 && l > lidx) Ri[k * NP + l] = T(0);  // keep R^-1 upper triangular
                 }
             }
             if (part) {
@@ -869,6 +1018,49 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
             }
         }
         __syncwarp();
+    }
+
+    // ---- x from the multipliers (J not kept): x = -P^-1 (q + G_A' lambda)  // @phase D x from multipliers
+    if (!HASJ) {
+        // w_l = q_l + sum_i lambda_i G[a_i, l]
+        T w = qs[l];
+        {
+            const int nc = p.nc > 0 ? p.nc : 1;
+            const int ak = (aidx >= 0) ? aidx / nc : 0, ar = (aidx >= 0) ? aidx - ak * nc : 0;
+            const int namax = __reduce_max_sync(FULL_MASK, st == 0 ? na : 0);
+            for (int i = 0; i < namax; ++i) {
+                const T li = __shfl_sync(FULL_MASK, lam, i, NP);
+                const int ai = __shfl_sync(FULL_MASK, aidx, i, NP);
+                const int ki = __shfl_sync(FULL_MASK, ak, i, NP), ri = __shfl_sync(FULL_MASK, ar, i, NP);
+                if (i < na && st == 0) {
+                    T g;
+                    if (toep) {
+                        const T *Dk = in[OP_D] ? in[OP_D] + ki * p.op[OP_D].step : nullptr;
+                        g = g_toeplitz<T>(gt, Dk, n, p.nu, ki, ri, l);
+                    } else {
+                        g = Gc[l * L::LDG + ai];
+                    }
+                    w += li * g;
+                }
+            }
+        }
+        // forward: L y = w, lane c finalises y_c and broadcasts it
+        const T dinv = dv[l];
+        T y = T(0);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+            const T yc = __shfl_sync(FULL_MASK, w * dinv, c, NP);
+            if (l == c) y = yc;
+            if (l > c) w -= Lc[c * L::LDL + l] * yc;
+        }
+        // backward: L' x = -y
+        T s2 = -y;
+#pragma unroll
+        for (int c = NP - 1; c >= 0; --c) {
+            const T xc = __shfl_sync(FULL_MASK, s2 * dinv, c, NP);
+            if (l == c) x = xc;
+            if (l < c) s2 -= Lc[l * L::LDL + c] * xc;
+        }
     }
 
     // ---- phase D: outputs ---------------------------------------------------  // @phase D outputs
@@ -896,7 +1088,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? 3 : 1) mpc_solve_ker
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR>  // @phase condense-only kernel
 __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) {
-    using L = Lay<T, NP, MR>;
+    using L = Lay<T, NP, MR, false>;
     constexpr int IPW = 32 / NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -915,10 +1107,10 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     T *inbase = work + (size_t)ipc * p.inst_stride;
     stage_inputs<T>(p, inbase, inst0, cnt, bar);
     T *wk = work + (size_t)iic * p.inst_stride;
-    T *Gc = wk + L::oG;
+    T *Gc = wk + p.g_off;
+    T *gt = p.op[OP_C].ptr ? wk + p.gt_off : nullptr;
     T *hs = wk + L::oH;
     T *xch = wk + L::oRL;
-    T *tail = wk + L::fixed;
     const T *in[OP_COUNT];
 #pragma unroll
     for (int o = 0; o < OP_COUNT; ++o) {
@@ -927,7 +1119,7 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     }
     T Prow[NP];
     T qj;
-    condense_dispatch<T, NP, MR, true>(p, in, Gc, hs, xch, tail, l, Prow, qj, inst, valid);
+    condense_dispatch<T, NP, MR, true>(p, in, Gc, gt, hs, xch, wk + p.scr_off, l, Prow, qj, inst, valid);
     if (!valid) return;
     if (p.P && l < n) {
         T *Pb = static_cast<T *>(p.P) + ((size_t)inst * n + l) * n;
@@ -938,7 +1130,16 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     if (p.q && l < n) static_cast<T *>(p.q)[(size_t)inst * n + l] = qj;
     if (p.G && l < n) {
         T *Gb = static_cast<T *>(p.G) + (size_t)inst * m * n;
-        for (int r = 0; r < m; ++r) Gb[(size_t)r * n + l] = Gc[l * L::LDG + r];
+        if (p.toeplitz) {
+            // the fused kernel's own view of G: rebuilt from the Toeplitz table
+            for (int r = 0; r < m; ++r) {
+                const int rk = r / p.nc, rr = r - rk * p.nc;
+                const T *Dk = in[OP_D] ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
+                Gb[(size_t)r * n + l] = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, l);
+            }
+        } else {
+            for (int r = 0; r < m; ++r) Gb[(size_t)r * n + l] = Gc[l * L::LDG + r];
+        }
     }
     if (p.h) {
         T *hb = static_cast<T *>(p.h) + (size_t)inst * m;

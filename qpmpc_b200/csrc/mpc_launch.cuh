@@ -28,9 +28,14 @@ namespace qpmpc {
 
 // Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
 template <typename T>
-size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc, bool mreg) {
-    p->tail_elems = tail_elems(np, p->nx, mreg);
-    p->inst_stride = fixed_elems + p->tail_elems;
+size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bool mreg) {
+    const bool lti = p->op[OP_A].step == 0 && p->op[OP_B].step == 0 && (!p->op[OP_C].ptr || p->op[OP_C].step == 0);
+    p->toeplitz = (lti && nx_in_registers(p->nx) && p->nc > 0 && env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0) ? 1 : 0;
+    const TailLay t = tail_layout(fixed_elems, szG, np, p->nx, p->nc, p->n, p->toeplitz != 0, mreg);
+    p->gt_off = t.gt_off;
+    p->g_off = t.g_off;
+    p->scr_off = t.scr_off;
+    p->inst_stride = t.total;
     int off = 0;
     for (int o = 0; o < OP_COUNT; ++o) {
         OperandView &v = p->op[o];
@@ -45,14 +50,14 @@ size_t layout_smem(SolveParams *p, int fixed_elems, int np, int ipc, bool mreg) 
 
 template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR>;
+    using L = Lay<T, NP, MR, MREG>;
     constexpr int IPW = 32 / NP;
     int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 4 : 1);
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
     size_t smem = 0;
     for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, MREG);
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, MREG);
         if (smem <= 227 * 1024 || wpc == 1) break;
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
@@ -72,12 +77,12 @@ int launch_solve(SolveParams p, cudaStream_t stream) {
 
 template <typename T, int NP, int MR>
 int launch_condense(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR>;
+    using L = Lay<T, NP, MR, false>;
     constexpr int IPW = 32 / NP;
     int wpc = 2;
     size_t smem = 0;
     for (;; --wpc) {
-        smem = layout_smem<T>(&p, L::fixed, NP, IPW * wpc, true);
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, false);
         if (smem <= 227 * 1024 || wpc == 1) break;
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
