@@ -31,7 +31,7 @@
 // Resident CTAs of 128 threads per SM the register-resident variants are
 // compiled for (caps registers per thread at 65536 / (128 * QPMPC_MINB)).
 #ifndef QPMPC_MINB
-#define QPMPC_MINB 3
+#define QPMPC_MINB 4
 #endif
 
 namespace qpmpc {
@@ -194,7 +194,47 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
     int row = 0;
 #pragma unroll
     for (int t = 0; t < NX * NX; ++t) Ar[t] = Ak[t];
-    for (int k = 0; k < N; ++k) {
+    // Fast path (every BASELINE config without a stage cost): A, B, C are time
+    // invariant (Toeplitz mode), two inequality rows per step, no stage cost.
+    // A, B, C sit in registers; a step is the two recursions and the two h rows.
+    const bool fast = !DUMP && toep && nc == 2 && !p.has_wx && !p.q_wx;
+    if (fast) {
+        T Bl[NX], Cr[2 * NX];
+#pragma unroll
+        for (int t = 0; t < NX; ++t) {
+            Bl[t] = Bk[t * nu + jb];
+            Cr[t] = hasC ? Ck[t] : T(0);
+            Cr[NX + t] = hasC ? Ck[NX + t] : T(0);
+        }
+        for (int k = 0; k < N; ++k) {
+            T h0 = ek[0], h1 = ek[1];
+            T pn[NX], xn[NX];
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {
+                h0 -= Cr[t] * xb[t];
+                h1 -= Cr[NX + t] * xb[t];
+                T a = T(0), b = T(0);
+#pragma unroll
+                for (int s = 0; s < NX; ++s) {
+                    a += Ar[t * NX + s] * psi[s];
+                    b += Ar[t * NX + s] * xb[s];
+                }
+                pn[t] = (k == kb) ? Bl[t] : a;
+                xn[t] = b;
+            }
+            if (l == 0) {
+                hs[2 * k] = h0;
+                hs[2 * k + 1] = h1;
+            }
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {
+                psi[t] = pn[t];
+                xb[t] = xn[t];
+            }
+            ek += stepE;
+        }
+    }
+    for (int k = fast ? N : 0; k < N; ++k) {
         if (stepA != 0 && k > 0) {
 #pragma unroll
             for (int t = 0; t < NX * NX; ++t) Ar[t] = Ak[t];
@@ -444,34 +484,39 @@ __device__ __forceinline__ void condense_dispatch(const SolveParams &p, const T 
 }
 
 // ---------------------------------------------------------------------------
-// Forward substitution L y = rhs for NR right-hand sides held in registers,
-// L by columns in shared memory (Lc), 1/L_kk in dv.  Lane-local: every lane
-// solves its own systems; all lanes read the same L entries (broadcast).
+// Forward substitution L y = rhs, in place, for up to three right-hand sides
+// held in registers (NR of a, b, c are used); L by columns in shared memory
+// (Lc), 1/L_kk in dv.  Lane-local: every lane solves its own systems and all
+// lanes read the same L entries (broadcast).
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int LDL, int NR>
-__device__ __forceinline__ void fsolve(const T *Lc, const T *dv, T (&a)[NR][NP]) {
+__device__ __forceinline__ void fsolve(const T *Lc, const T *dv, T (&a)[NP], T (&b)[NP], T (&c)[NP]) {
     using T2 = typename Pair<T>::type;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const T dk = dv[k];
-        T ak[NR];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            ak[i] = a[i][k] * dk;
-            a[i][k] = ak[i];
-        }
+        const T ak = a[k] * dk, bk = (NR > 1) ? b[k] * dk : T(0), ck = (NR > 2) ? c[k] * dk : T(0);
+        a[k] = ak;
+        if (NR > 1) b[k] = bk;
+        if (NR > 2) c[k] = ck;
         if (((k + 1) & 1) && k + 1 < NP) {
             const T lv = Lc[k * LDL + k + 1];
-#pragma unroll
-            for (int i = 0; i < NR; ++i) a[i][k + 1] -= lv * ak[i];
+            a[k + 1] -= lv * ak;
+            if (NR > 1) b[k + 1] -= lv * bk;
+            if (NR > 2) c[k + 1] -= lv * ck;
         }
 #pragma unroll
-        for (int c = (k + 2) & ~1; c < NP; c += 2) {
-            const T2 lv = *reinterpret_cast<const T2 *>(Lc + k * LDL + c);
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                a[i][c] -= lv.x * ak[i];
-                a[i][c + 1] -= lv.y * ak[i];
+        for (int j = (k + 2) & ~1; j < NP; j += 2) {
+            const T2 lv = *reinterpret_cast<const T2 *>(Lc + k * LDL + j);
+            a[j] -= lv.x * ak;
+            a[j + 1] -= lv.y * ak;
+            if (NR > 1) {
+                b[j] -= lv.x * bk;
+                b[j + 1] -= lv.y * bk;
+            }
+            if (NR > 2) {
+                c[j] -= lv.x * ck;
+                c[j + 1] -= lv.y * ck;
             }
         }
     }
@@ -592,139 +637,103 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
     T viol[MR], mn2[MR], vtol[MR], ginv[MR];
     bool rowvalid[MR];
     {
-        T rhs[3][NP];  // [0] = t, [1..2] = J row / rows of G
+        T tq[NP];
 #pragma unroll
         for (int c = 0; c < NP; c += 2) {
             const T2 v = *reinterpret_cast<const T2 *>(qs + c);
-            rhs[0][c] = v.x;
-            rhs[0][c + 1] = v.y;
+            tq[c] = v.x;
+            tq[c + 1] = v.y;
         }
-        // loads the rows s0, s0+1 of G into rhs[1..2]; row norms and tolerances
-        auto load_rows = [&](int s0) {
+        // row s of G into dst; row norm and tolerance of the violation test
+        auto load_row = [&](int s, T(&dst)[NP]) {
+            const int row = l + s * NP;
+            rowvalid[s] = row < m;
+            T g2 = T(0), g21 = T(0);
+            // (k, r) of this row and its slice of the Toeplitz table
+            const int rk = rowvalid[s] ? row / p.nc : 0, rr = rowvalid[s] ? row - rk * p.nc : 0;
+            const T *Dk = (toep && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int s = s0 + u;
-                const int row = l + s * NP;
-                rowvalid[s] = row < m;
-                T g2 = T(0), g21 = T(0);
-                // (k, r) of this row and its slice of the Toeplitz table
-                const int rk = rowvalid[s] ? row / p.nc : 0, rr = rowvalid[s] ? row - rk * p.nc : 0;
-                const T *Dk = (toep && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
-#pragma unroll
-                for (int k = 0; k < NP; k += 2) {
-                    T ga = T(0), gb = T(0);
-                    if (rowvalid[s]) {
-                        if (toep) {
-                            ga = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k);
-                            gb = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k + 1);
-                        } else {
-                            ga = Gc[k * L::LDG + row];
-                            gb = Gc[(k + 1) * L::LDG + row];
-                        }
+            for (int k = 0; k < NP; k += 2) {
+                T ga = T(0), gb = T(0);
+                if (rowvalid[s]) {
+                    if (toep) {
+                        ga = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k);
+                        gb = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k + 1);
+                    } else {
+                        ga = Gc[k * L::LDG + row];
+                        gb = Gc[(k + 1) * L::LDG + row];
                     }
-                    rhs[1 + u][k] = ga;
-                    rhs[1 + u][k + 1] = gb;
-                    g2 += ga * ga;
-                    g21 += gb * gb;
                 }
-                g2 += g21;
-                // Tolerance of the violation test: eps * (max(1, |h_i|) + |G_i|).
-                const T hi = rowvalid[s] ? hs[row] : T(0);
-                viol[s] = -hi;
-                vtol[s] = Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2));
-                ginv[s] = g2 > T(0) ? frsqrt_(g2) : T(1e30);
+                dst[k] = ga;
+                dst[k + 1] = gb;
+                g2 += ga * ga;
+                g21 += gb * gb;
+            }
+            g2 += g21;
+            // eps * (max(1, |h_i|) + |G_i|)
+            const T hi = rowvalid[s] ? hs[row] : T(0);
+            viol[s] = -hi;
+            vtol[s] = Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2));
+            ginv[s] = g2 > T(0) ? frsqrt_(g2) : T(1e30);
+        };
+        // after the solve src is row s of M: M t (= -G x) and |M_s|^2
+        auto finish_row = [&](int s, const T(&src)[NP]) {
+            T m0 = T(0), m1 = T(0), v0 = T(0), v1 = T(0);
+#pragma unroll
+            for (int c = 0; c < NP; c += 2) {
+                m0 += src[c] * src[c];
+                m1 += src[c + 1] * src[c + 1];
+                v0 += src[c] * tq[c];
+                v1 += src[c + 1] * tq[c + 1];
+            }
+            mn2[s] = m0 + m1;
+            // G x - h with x = -P^-1 q = -J t: G x = -(G J) t = -M t
+            viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : T(-1);
+            if (!MREG) {
+                // In place: this lane is the only reader and writer of its rows of G.
+                const int row = l + s * NP;
+#pragma unroll
+                for (int c = 0; c < NP; ++c) Gc[c * L::LDG + row] = src[c];
             }
         };
-        // finishes rows s0, s0+1: M t (= -G x), |M_i|^2, and stores the rows
-        auto store_rows = [&](int s0) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int s = s0 + u;
-                T m0 = T(0), m1 = T(0), v0 = T(0), v1 = T(0);
-#pragma unroll
-                for (int c = 0; c < NP; c += 2) {
-                    m0 += rhs[1 + u][c] * rhs[1 + u][c];
-                    m1 += rhs[1 + u][c + 1] * rhs[1 + u][c + 1];
-                    v0 += rhs[1 + u][c] * rhs[0][c];
-                    v1 += rhs[1 + u][c + 1] * rhs[0][c + 1];
-                }
-                mn2[s] = m0 + m1;
-                // G x - h with x = -P^-1 q = -J t: G x = -(G J) t = -M t
-                viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : T(-1);
-                if (MREG) {
-#pragma unroll
-                    for (int c = 0; c < NP; ++c) Mrow[MREG ? s : 0][c] = rhs[1 + u][c];
-                } else {
-                    // In place: this lane is the only reader and writer of its rows of G.
-                    const int row = l + s * NP;
-#pragma unroll
-                    for (int c = 0; c < NP; ++c) Gc[c * L::LDG + row] = rhs[1 + u][c];
-                }
-            }
-        };
-        if (HASJ) {
-            // t and the J row first; then the rows of M two at a time
-#pragma unroll
-            for (int c = 0; c < NP; ++c) rhs[1][c] = (c == l) ? T(1) : T(0);
-            {
-                T pair[2][NP];
-#pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    pair[0][c] = rhs[0][c];
-                    pair[1][c] = rhs[1][c];
-                }
-                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
-                T x0 = T(0), x1 = T(0);
-#pragma unroll
-                for (int c = 0; c < NP; c += 2) {
-                    x0 -= pair[1][c] * pair[0][c];
-                    x1 -= pair[1][c + 1] * pair[0][c + 1];
-                }
-                x = x0 + x1;
-#pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    rhs[0][c] = pair[0][c];
-                    Jrow[HASJ ? c : 0] = pair[1][c];
-                }
-            }
-#pragma unroll
-            for (int s0 = 0; s0 < MR; s0 += 2) {
-                load_rows(s0);
-                T pair[2][NP];
-#pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    pair[0][c] = rhs[1][c];
-                    pair[1][c] = rhs[2][c];
-                }
-                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
-#pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    rhs[1][c] = pair[0][c];
-                    rhs[2][c] = pair[1][c];
-                }
-                store_rows(s0);
-            }
-        } else {
-            // t rides along with the first two rows of M
-            load_rows(0);
-            fsolve<T, NP, L::LDL, 3>(Lc, dv, rhs);
-            store_rows(0);
+        if (MREG) {
+            // t rides along with the first two rows of M, solved in place in Mrow
+            load_row(0, Mrow[0]);
+            load_row(1, Mrow[MREG ? 1 : 0]);
+            fsolve<T, NP, L::LDL, 3>(Lc, dv, tq, Mrow[0], Mrow[MREG ? 1 : 0]);
+            finish_row(0, Mrow[0]);
+            finish_row(1, Mrow[MREG ? 1 : 0]);
 #pragma unroll
             for (int s0 = 2; s0 < MR; s0 += 2) {
-                load_rows(s0);
-                T pair[2][NP];
+                load_row(s0, Mrow[MREG ? s0 : 0]);
+                load_row(s0 + 1, Mrow[MREG ? s0 + 1 : 0]);
+                fsolve<T, NP, L::LDL, 2>(Lc, dv, Mrow[MREG ? s0 : 0], Mrow[MREG ? s0 + 1 : 0], tq);
+                finish_row(s0, Mrow[MREG ? s0 : 0]);
+                finish_row(s0 + 1, Mrow[MREG ? s0 + 1 : 0]);
+            }
+        } else {
+            // t and row l of J (column l of L^-1: solve L y = e_l), x = -J t
+            T jr[NP];
 #pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    pair[0][c] = rhs[1][c];
-                    pair[1][c] = rhs[2][c];
-                }
-                fsolve<T, NP, L::LDL, 2>(Lc, dv, pair);
+            for (int c = 0; c < NP; ++c) jr[c] = (c == l) ? T(1) : T(0);
+            fsolve<T, NP, L::LDL, 2>(Lc, dv, tq, jr, jr);
+            T x0 = T(0), x1 = T(0);
 #pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    rhs[1][c] = pair[0][c];
-                    rhs[2][c] = pair[1][c];
-                }
-                store_rows(s0);
+            for (int c = 0; c < NP; c += 2) {
+                x0 -= jr[c] * tq[c];
+                x1 -= jr[c + 1] * tq[c + 1];
+            }
+            x = x0 + x1;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) Jrow[HASJ ? c : 0] = jr[c];
+#pragma unroll
+            for (int s0 = 0; s0 < MR; s0 += 2) {
+                T r0[NP], r1[NP];
+                load_row(s0, r0);
+                load_row(s0 + 1, r1);
+                fsolve<T, NP, L::LDL, 2>(Lc, dv, r0, r1, r1);
+                finish_row(s0, r0);
+                finish_row(s0 + 1, r1);
             }
         }
     }
@@ -792,7 +801,8 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
                 act = false;
             }
         }
-        // d = J' n_p = -(row p of M): dd holds its active part d1 (zero-padded), d2 the rest.  // @phase C publish d
+        // Row p of M is -d (d = J' n_p): the iteration works with m = -d directly.
+        // dd holds its active part m1 (zero-padded), d2 the rest m2.  // @phase C publish d
         const int owner = pidx % NP, pslot = pidx / NP;
         T dl;
         if (MREG) {
@@ -803,8 +813,8 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
 #pragma unroll
                         for (int c = 0; c < NP; c += 2) {
                             T2 v;
-                            v.x = -Mrow[MREG ? s : 0][c];
-                            v.y = -Mrow[MREG ? s : 0][c + 1];
+                            v.x = Mrow[MREG ? s : 0][c];
+                            v.y = Mrow[MREG ? s : 0][c + 1];
                             *reinterpret_cast<T2 *>(dd + c) = v;
                         }
                         sc[0] = viol[s];
@@ -815,7 +825,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
             __syncwarp();
             dl = dd[l];
         } else {
-            dl = -Gc[l * L::LDG + pidx];
+            dl = Gc[l * L::LDG + pidx];
             if (act && l == owner) {
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
@@ -829,7 +839,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
         dd[l] = (l < na) ? dl : T(0);
         d2[l] = (l >= na) ? dl : T(0);
         __syncwarp();
-        // G z = M2 d2 (owned rows), |d2|^2, and z = J2 d2 when J is kept  // @phase C z, Gz
+        // -G z = M2 m2 (owned rows), |m2|^2, and -z = J2 m2 when J is kept  // @phase C z, Gz
         T z = T(0), z1 = T(0), a2 = T(0), a21 = T(0);
         T gz[MR];
 #pragma unroll
@@ -851,7 +861,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
         }
         z += z1;
         a2 += a21;
-        // r = R^-1 d1 (component l; zero on lanes >= na)  // @phase C r=R^-1 d
+        // -r = R^-1 m1 (component l; zero on lanes >= na)  // @phase C r=R^-1 d
         T rv = T(0);
         {
             T rv1 = T(0);
@@ -864,7 +874,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
             rv += rv1;
         }
         // step lengths  // @phase C step length, move
-        const T cand = (act && l < na && rv > T(0)) ? fmax(lam, T(0)) * rcp_(rv) : INF;
+        const T cand = (act && l < na && rv < T(0)) ? fmax(lam, T(0)) * rcp_(-rv) : INF;
         const T t1 = group_min_pos<T, NP>(cand, segmask);
         const unsigned bal = __ballot_sync(FULL_MASK, cand == t1 && cand < INF) & segmask;
         const int lidx = bal ? (__ffs(bal) - 1 - seg_shift) : 0;
@@ -883,25 +893,25 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
             // operands are finite on finished instances, so 0 * v adds nothing)
             const T tp = (act && !zzero) ? t : T(0);
             const T td = act ? t : T(0);
-            if (HASJ) x += tp * z;
+            if (HASJ) x -= tp * z;
 #pragma unroll
-            for (int s = 0; s < MR; ++s) viol[s] += tp * gz[s];
-            lam -= td * rv;
+            for (int s = 0; s < MR; ++s) viol[s] -= tp * gz[s];
+            lam += td * rv;
             lamp += td;
         }
         const bool full = act && !zzero && t2 <= t1;
         const bool part = act && !full;
 
         if (__any_sync(FULL_MASK, full)) {  // @phase C add constraint (Householder)
-            // Constraint p enters: reflect d2 onto its first entry.  H = I - tau v v',
-            // v = d2 - beta e_na, applied to columns >= na of M (and of J).
-            const T dna = d2[na < NP ? na : NP - 1];
+            // Constraint p enters: reflect d2 = -m2 onto beta e_na.  H = I - tau v v',
+            // v = d2 - beta e_na = -(m2 + beta e_na), applied to columns >= na of M (and J).
+            const T mna = d2[na < NP ? na : NP - 1];
             const T alpha = a2 * ainv;
-            const T beta = (dna > T(0)) ? -alpha : alpha;
-            const T binv = (dna > T(0)) ? -ainv : ainv;
-            const T tau = full ? rcp_(a2 - beta * dna) : T(0);
+            const T beta = (mna < T(0)) ? -alpha : alpha;
+            const T binv = (mna < T(0)) ? -ainv : ainv;
+            const T tau = full ? rcp_(a2 + beta * mna) : T(0);
             __syncwarp();
-            if (full && l == na) d2[l] = dna - beta;  // d2 becomes v
+            if (full && l == na) d2[l] = mna + beta;  // d2 becomes -v
             __syncwarp();
             T dj = T(0), dj1 = T(0);
             T dm[MR];
@@ -938,7 +948,7 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
             }
             if (full) {
                 // R gains the column [d1; beta]: R^-1 gains [-r / beta; 1 / beta]
-                if (l < na) Ri[na * NP + l] = -rv * binv;
+                if (l < na) Ri[na * NP + l] = rv * binv;  // rv holds -r
                 if (l == na) {
                     Ri[na * NP + na] = binv;
                     lam = lamp;
