@@ -35,6 +35,7 @@ struct SolveParams {
     int toeplitz;        // 1: A, B, C time-invariant and nx in registers -> G kept as a table
     int gt_off, g_off, scr_off;  // tail regions of the work region (TailLay)
     int input_elems;     // CTA-level input region
+    int present_mask;    // bit o set: operand o is present (staged)
     // outputs
     void *U;
     int *status;

@@ -101,45 +101,49 @@ __device__ __forceinline__ T g_toeplitz(const T *gt, const T *Dk, int n, int nu,
 template <typename T>  // @phase 0 stage inputs
 __device__ __forceinline__ void stage_inputs(const SolveParams &p, T *inbase, int inst0, int cnt,
                                              uint64_t *bar) {
+    // One thread does the address arithmetic and issues the bulk copies; it
+    // leaves the set of operands it could copy next to the barrier.
+    unsigned *mask_slot = reinterpret_cast<unsigned *>(bar + 1);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
-    }
-    __syncthreads();
-    unsigned tx = 0;
-    unsigned tma_mask = 0;
+        unsigned tx = 0, tma_mask = 0;
 #pragma unroll
-    for (int o = 0; o < OP_COUNT; ++o) {
-        const OperandView &v = p.op[o];
-        if (v.ptr == nullptr) continue;
-        const T *src = static_cast<const T *>(v.ptr) + (v.per_instance ? (size_t)inst0 * v.sz : 0);
-        unsigned bytes = (unsigned)((v.per_instance ? cnt : 1) * v.sz * (int)sizeof(T));
-        if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes > 0) {
-            tx += bytes;
-            tma_mask |= 1u << o;
+        for (int o = 0; o < OP_COUNT; ++o) {
+            const OperandView &v = p.op[o];
+            if (v.ptr == nullptr) continue;
+            const T *src = static_cast<const T *>(v.ptr) + (v.per_instance ? (size_t)inst0 * v.sz : 0);
+            const unsigned bytes = (unsigned)((v.per_instance ? cnt : 1) * v.sz * (int)sizeof(T));
+            if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes > 0) {
+                tx += bytes;
+                tma_mask |= 1u << o;
+            }
         }
-    }
-    if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar, tx);
 #pragma unroll
         for (int o = 0; o < OP_COUNT; ++o) {
             if (!(tma_mask >> o & 1)) continue;
             const OperandView &v = p.op[o];
             const T *src = static_cast<const T *>(v.ptr) + (v.per_instance ? (size_t)inst0 * v.sz : 0);
-            unsigned bytes = (unsigned)((v.per_instance ? cnt : 1) * v.sz * (int)sizeof(T));
+            const unsigned bytes = (unsigned)((v.per_instance ? cnt : 1) * v.sz * (int)sizeof(T));
             bulk_g2s(inbase + v.smem_off, src, bytes, bar);
         }
-    }
-    // Operands a bulk copy cannot take (odd tail counts, unaligned views).
-#pragma unroll
-    for (int o = 0; o < OP_COUNT; ++o) {
-        const OperandView &v = p.op[o];
-        if (v.ptr == nullptr || (tma_mask >> o & 1)) continue;
-        const T *src = static_cast<const T *>(v.ptr) + (v.per_instance ? (size_t)inst0 * v.sz : 0);
-        int count = (v.per_instance ? cnt : 1) * v.sz;
-        for (int i = threadIdx.x; i < count; i += blockDim.x) inbase[v.smem_off + i] = src[i];
+        *mask_slot = tma_mask;
     }
     __syncthreads();
+    const unsigned tma_mask = *mask_slot;
+    if (tma_mask != (unsigned)p.present_mask) {
+        // Operands a bulk copy cannot take (odd tail counts, unaligned views).
+#pragma unroll
+        for (int o = 0; o < OP_COUNT; ++o) {
+            const OperandView &v = p.op[o];
+            if (v.ptr == nullptr || (tma_mask >> o & 1)) continue;
+            const T *src = static_cast<const T *>(v.ptr) + (v.per_instance ? (size_t)inst0 * v.sz : 0);
+            const int count = (v.per_instance ? cnt : 1) * v.sz;
+            for (int i = threadIdx.x; i < count; i += blockDim.x) inbase[v.smem_off + i] = src[i];
+        }
+        __syncthreads();
+    }
     mbar_wait(bar, 0);
 }
 
@@ -649,20 +653,31 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
             const int row = l + s * NP;
             rowvalid[s] = row < m;
             T g2 = T(0), g21 = T(0);
-            // (k, r) of this row and its slice of the Toeplitz table
+            // (k, r) of this row; its slice of the Toeplitz table runs backwards
+            // from gtr[0] = G[row, k nu - 1] (see g_toeplitz)
             const int rk = rowvalid[s] ? row / p.nc : 0, rr = rowvalid[s] ? row - rk * p.nc : 0;
-            const T *Dk = (toep && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
+            const int kb = (toep && rowvalid[s]) ? rk * p.nu : 0;
+            const T *gtr = gt ? gt + rr * n + kb - 1 : nullptr;
+            const T *Dr = (toep && rowvalid[s] && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step + rr * p.nu - kb : nullptr;
+            const int kd = Dr ? kb + p.nu : kb;  // block column k holds D_k
 #pragma unroll
             for (int k = 0; k < NP; k += 2) {
                 T ga = T(0), gb = T(0);
-                if (rowvalid[s]) {
-                    if (toep) {
+                if (toep && NP >= 32) {
+                    // (branches, not predicated loads: keeps the live range short where registers are scarce)
+                    if (rowvalid[s]) {
+                        const T *Dk = in[OP_D] ? in[OP_D] + rk * p.op[OP_D].step : nullptr;
                         ga = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k);
                         gb = g_toeplitz<T>(gt, Dk, n, p.nu, rk, rr, k + 1);
-                    } else {
-                        ga = Gc[k * L::LDG + row];
-                        gb = Gc[(k + 1) * L::LDG + row];
                     }
+                } else if (toep) {
+                    if (gtr && k < kb) ga = gtr[-k];
+                    if (gtr && k + 1 < kb) gb = gtr[-(k + 1)];
+                    if (k >= kb && k < kd) ga = Dr[k];
+                    if (k + 1 >= kb && k + 1 < kd) gb = Dr[k + 1];
+                } else if (rowvalid[s]) {
+                    ga = Gc[k * L::LDG + row];
+                    gb = Gc[(k + 1) * L::LDG + row];
                 }
                 dst[k] = ga;
                 dst[k + 1] = gb;
@@ -779,11 +794,13 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
                     bi = l + s * NP;
                 }
             }
-            const T top = group_max_pos<T, NP>(best, segmask);
-            const unsigned win = __ballot_sync(FULL_MASK, best == top) & segmask;
+            // single-precision keys: the ranking is a heuristic, any violated row is a valid pivot
+            const float bestf = (float)best;
+            const float top = group_max_pos<float, NP>(best > T(0) ? fmaxf(bestf, 1e-37f) : 0.f, segmask);
+            const unsigned win = __ballot_sync(FULL_MASK, best > T(0) && fmaxf(bestf, 1e-37f) == top) & segmask;
             const int cand_p = __shfl_sync(FULL_MASK, bi, __ffs(win) - 1);
             if (sel) {
-                if (!(top > T(0))) {
+                if (!(top > 0.f)) {
                     done = true;  // primal feasible: optimal
                 } else {
                     pidx = cand_p;

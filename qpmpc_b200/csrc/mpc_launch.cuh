@@ -37,9 +37,11 @@ size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bo
     p->scr_off = t.scr_off;
     p->inst_stride = t.total;
     int off = 0;
+    p->present_mask = 0;
     for (int o = 0; o < OP_COUNT; ++o) {
         OperandView &v = p->op[o];
         if (!v.ptr) continue;
+        p->present_mask |= 1 << o;
         v.smem_off = off;
         int elems = v.sz * (v.per_instance ? ipc : 1);
         off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
