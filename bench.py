@@ -48,8 +48,8 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=1024)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--horizon", type=int, default=HORIZON)
@@ -309,11 +309,13 @@ def run_b200(args, rank, local_rank, world):
     achieved_gbs = bytes_per_solve * B / (kernel_ms * 1e-3) / 1e9
     tf = ctypes.c_double(0.0)
     lib.qpmpc_b200_fp64_peak(local_rank, ctypes.byref(tf))
-    # algorithmic flops of what the kernel executes per solve:
-    # condensing + setup (Cholesky, J, M = G J) + iterations * per-iteration.
+    # flops the kernel's algorithm needs per solve: condensing
+    # recursions, Cholesky, forward substitutions for t and the m rows of M,
+    # the final two triangular solves, and per active-set iteration one
+    # matrix-vector product with M plus one Householder update of M.
     nn, mm = n, 2 * N
-    f_setup = 11e3 + nn**3 / 3 + nn**3 / 3 + 2 * nn * nn + mm * nn * nn + 2 * mm * nn
-    f_iter = 2 * (nn * nn + mm * nn) * 2 + 2 * nn * nn
+    f_setup = N * (4 * 9 + 2 * 2 * 3) * nn + nn**3 / 3 + (mm + 1) * nn * nn + 2 * nn * nn
+    f_iter = 6 * mm * nn
     flops_per_solve = f_setup + iters_mean * f_iter
     achieved_tf = flops_per_solve * B / (kernel_ms * 1e-3) / 1e12
 
@@ -329,11 +331,13 @@ def run_b200(args, rank, local_rank, world):
         "config": config_dict(args, world),
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "call": "qpmpc_b200_solve_host (pinned host buffers, sync per step)"},
+                "call": "qpmpc_b200_solve_host (pinned host buffers; H2D, kernel, D2H pipelined over "
+                        "3 streams in 16384-instance chunks; sync per step)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "mpc_solve_kernel<double,16,2,true>", "kernel_ms": kernel_ms,
+                     "kernel": "mpc_solve_kernel<double,NP=%d,MR=2>" % (8 if n <= 8 else 16 if n <= 16 else 32)
+                     if n <= 32 else "mpc_solve_cta_kernel<double>", "kernel_ms": kernel_ms,
                      "bytes_per_solve": bytes_per_solve,
                      "note": "latency/FP64-issue bound by design (SURVEY 8d): HBM fraction is "
                              "necessarily tiny; see fp64"},

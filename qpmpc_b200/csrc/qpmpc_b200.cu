@@ -180,8 +180,10 @@ int dispatch_condense(const SolveParams &p, const Variant &v, cudaStream_t s) {
 
 // ---- host-buffer entry: cached device buffers, one set per calling thread ----
 struct HostCache {
+    static constexpr int NSTREAM = 3;
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream[NSTREAM] = {nullptr, nullptr, nullptr};
+    cudaEvent_t shared_ready = nullptr;
     void *buf[OP_COUNT] = {nullptr};
     size_t cap[OP_COUNT] = {0};
     void *U = nullptr, *Z = nullptr;
@@ -424,45 +426,82 @@ int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *i
     if (c.device != device) {
         c = HostCache();
         c.device = device;
-        e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+        for (int i = 0; i < HostCache::NSTREAM; ++i) {
+            e = cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return (int)e;
+        }
+        e = cudaEventCreateWithFlags(&c.shared_ready, cudaEventDisableTiming);
         if (e != cudaSuccess) return (int)e;
     }
     SolveParams p;
     fill_params(d, in, &p);
     const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
-    const void *host[OP_COUNT] = {in->A, in->B, in->C, in->D, in->e, in->x0, in->goal, in->targets};
-    qpmpc_b200_operands dev;
-    const void **devp[OP_COUNT] = {&dev.A, &dev.B, &dev.C, &dev.D, &dev.e, &dev.x0, &dev.goal, &dev.targets};
+    const char *host[OP_COUNT] = {(const char *)in->A, (const char *)in->B, (const char *)in->C, (const char *)in->D,
+                                  (const char *)in->e, (const char *)in->x0, (const char *)in->goal,
+                                  (const char *)in->targets};
+    // Device copies of the operands and outputs, cached per calling thread.
     for (int o = 0; o < OP_COUNT; ++o) {
-        *devp[o] = nullptr;
         const OperandView &v = p.op[o];
         if (!v.ptr) continue;
         const size_t bytes = (size_t)v.sz * (v.per_instance ? d->batch : 1) * es;
-        e = ensure(&c.buf[o], &c.cap[o], bytes);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaMemcpyAsync(c.buf[o], host[o], bytes, cudaMemcpyHostToDevice, c.stream);
-        if (e != cudaSuccess) return (int)e;
-        *devp[o] = c.buf[o];
+        if ((e = ensure(&c.buf[o], &c.cap[o], bytes)) != cudaSuccess) return (int)e;
     }
-    const size_t bU = (size_t)d->batch * p.n * es, bZ = (size_t)d->batch * p.m * es, bS = (size_t)d->batch * 4;
-    if ((e = ensure(&c.U, &c.capU, bU)) != cudaSuccess) return (int)e;
-    if ((e = ensure((void **)&c.status, &c.capS, bS)) != cudaSuccess) return (int)e;
-    qpmpc_b200_outputs dout = {c.U, c.status, nullptr, nullptr};
-    if (out->iters) {
-        if ((e = ensure((void **)&c.iters, &c.capI, bS)) != cudaSuccess) return (int)e;
-        dout.iters = c.iters;
+    const size_t rU = (size_t)p.n * es, rZ = (size_t)p.m * es;
+    if ((e = ensure(&c.U, &c.capU, rU * d->batch)) != cudaSuccess) return (int)e;
+    if ((e = ensure((void **)&c.status, &c.capS, (size_t)d->batch * 4)) != cudaSuccess) return (int)e;
+    if (out->iters && (e = ensure((void **)&c.iters, &c.capI, (size_t)d->batch * 4)) != cudaSuccess) return (int)e;
+    const bool wantZ = out->Z && rZ;
+    if (wantZ && (e = ensure(&c.Z, &c.capZ, rZ * d->batch)) != cudaSuccess) return (int)e;
+    // Operands shared by the batch go up once; every chunk waits for them.
+    bool any_shared = false;
+    for (int o = 0; o < OP_COUNT; ++o) {
+        const OperandView &v = p.op[o];
+        if (!v.ptr || v.per_instance) continue;
+        cudaMemcpyAsync(c.buf[o], host[o], (size_t)v.sz * es, cudaMemcpyHostToDevice, c.stream[0]);
+        any_shared = true;
     }
-    if (out->Z && bZ) {
-        if ((e = ensure(&c.Z, &c.capZ, bZ)) != cudaSuccess) return (int)e;
-        dout.Z = c.Z;
+    if (any_shared) cudaEventRecord(c.shared_ready, c.stream[0]);
+    // Chunks of the batch round-robin over the streams so that the upload of
+    // one chunk, the kernel of the previous one and the download of the one
+    // before overlap (host buffers should be pinned for that).
+    int chunk = env_int("QPMPC_B200_HOST_CHUNK", 16384);
+    if (chunk < 256) chunk = 256;
+    int idx = 0;
+    for (int lo = 0; lo < d->batch; lo += chunk, ++idx) {
+        const int cnt = d->batch - lo < chunk ? d->batch - lo : chunk;
+        cudaStream_t s = c.stream[idx % HostCache::NSTREAM];
+        if (any_shared && idx % HostCache::NSTREAM != 0 && idx < HostCache::NSTREAM)
+            cudaStreamWaitEvent(s, c.shared_ready, 0);
+        qpmpc_b200_operands dev;
+        const void **devp[OP_COUNT] = {&dev.A, &dev.B, &dev.C, &dev.D, &dev.e, &dev.x0, &dev.goal, &dev.targets};
+        for (int o = 0; o < OP_COUNT; ++o) {
+            *devp[o] = nullptr;
+            const OperandView &v = p.op[o];
+            if (!v.ptr) continue;
+            if (!v.per_instance) {
+                *devp[o] = c.buf[o];
+                continue;
+            }
+            const size_t off = (size_t)lo * v.sz * es, bytes = (size_t)cnt * v.sz * es;
+            e = cudaMemcpyAsync((char *)c.buf[o] + off, host[o] + off, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return (int)e;
+            *devp[o] = (char *)c.buf[o] + off;
+        }
+        qpmpc_b200_desc dc = *d;
+        dc.batch = cnt;
+        qpmpc_b200_outputs dout = {(char *)c.U + rU * lo, c.status + lo, out->iters ? c.iters + lo : nullptr,
+                                   wantZ ? (char *)c.Z + rZ * lo : nullptr};
+        rc = qpmpc_b200_solve(&dc, &dev, &dout, s);
+        if (rc) return rc;
+        cudaMemcpyAsync((char *)out->U + rU * lo, dout.U, rU * cnt, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(out->status + lo, dout.status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
+        if (dout.iters) cudaMemcpyAsync(out->iters + lo, dout.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
+        if (dout.Z) cudaMemcpyAsync((char *)out->Z + rZ * lo, dout.Z, rZ * cnt, cudaMemcpyDeviceToHost, s);
     }
-    rc = qpmpc_b200_solve(d, &dev, &dout, c.stream);
-    if (rc) return rc;
-    cudaMemcpyAsync(out->U, c.U, bU, cudaMemcpyDeviceToHost, c.stream);
-    cudaMemcpyAsync(out->status, c.status, bS, cudaMemcpyDeviceToHost, c.stream);
-    if (dout.iters) cudaMemcpyAsync(out->iters, c.iters, bS, cudaMemcpyDeviceToHost, c.stream);
-    if (dout.Z) cudaMemcpyAsync(out->Z, c.Z, bZ, cudaMemcpyDeviceToHost, c.stream);
-    e = cudaStreamSynchronize(c.stream);
+    for (int i = 0; i < HostCache::NSTREAM; ++i) {
+        cudaError_t ei = cudaStreamSynchronize(c.stream[i]);
+        if (ei != cudaSuccess) e = ei;
+    }
     return (int)e;
 }
 
