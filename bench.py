@@ -65,7 +65,7 @@ def config_dict(args, world):
         "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "horizon": args.horizon, "method": "dual active set (Goldfarb-Idnani), exact",
         "l2": f"inputs rotate over {ROTATE} distinct sets ({ROTATE}x{args.batch * 208 / 1e6:.1f} MB > L2)",
-        "parallelism": f"batch-sharded x{world}, one all-gather of U per step" if world > 1 else "single GPU",
+        "parallelism": f"batch-sharded x{world}, U gathered on every rank each step" if world > 1 else "single GPU",
     }
 
 
@@ -147,6 +147,11 @@ def cpu_arm(workload, seconds, min_reps=1):
     return B * reps / dt, threads, f"{reps} x {B} instances of the bench workload in {dt:.1f} s"
 
 
+class _StepResult:
+    def __init__(self, status, iters):
+        self.status, self.iters = status, iters
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -210,8 +215,25 @@ def run_b200(args, rank, local_rank, world):
     problems = [to_batched(w, device=dev) for w in sets]
     U_out = torch.empty((B, n), dtype=torch.float64, device=dev)
     U_all = torch.empty((world * B, n), dtype=torch.float64, device=dev) if world > 1 else None
+    # N > 1: the kernel's epilogue stores every U row into all ranks' buffers
+    # over NVLink (fused gather); NCCL all-gather only if symmetric memory is
+    # unavailable on the box.
+    gather, gather_kind = None, "none"
+    if world > 1:
+        gather_kind = "nccl all_gather_into_tensor"
+        if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer":
+            try:
+                from qpmpc_b200.distributed import PeerGather
+
+                gather = PeerGather(B, n)
+                gather_kind = "peer stores from the solve kernel (fused) + barrier"
+            except Exception as exc:  # noqa: BLE001
+                gather_kind += f" (symmetric memory unavailable: {type(exc).__name__})"
 
     def step(i):
+        if gather is not None:
+            _, status, iters = gather.solve(problems[i % ROTATE])
+            return _StepResult(status[rank * B:(rank + 1) * B], iters)
         plan = solve_mpc_batch(problems[i % ROTATE], out=U_out)
         if world > 1:
             dist.all_gather_into_tensor(U_all, U_out)
@@ -344,7 +366,7 @@ def run_b200(args, rank, local_rank, world):
         "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": tf.value,
                  "frac": achieved_tf / tf.value if tf.value > 0 else None,
                  "flops_per_solve": flops_per_solve, "peak_source": "qpmpc_b200_fp64_peak (DFMA probe)"},
-        "iters_mean": iters_mean,
+        "iters_mean": iters_mean, "gather": gather_kind,
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }

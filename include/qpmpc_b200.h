@@ -118,6 +118,27 @@ typedef struct qpmpc_b200_outputs {
 int qpmpc_b200_solve(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
                      const qpmpc_b200_outputs *out, void *stream);
 
+/* Condense + solve with a FUSED GATHER: besides (or instead of: out->U and
+ * out->status may be NULL) the local outputs, every instance's U row and status
+ * are stored by the kernel's epilogue into rows [row_offset, row_offset + batch)
+ * of each of `count` destination buffers.  With peer-mapped destinations (CUDA
+ * IPC / symmetric memory of the other GPUs of the box) the stores travel over
+ * NVLink while the remaining instances are still being solved: this replaces
+ * the all-gather of the stacked U trajectories that follows a batch-sharded
+ * solve (one rank per GPU, rank r solves rows [r*batch, (r+1)*batch)).  The
+ * caller synchronises the ranks afterwards (any barrier). */
+typedef struct qpmpc_b200_peers {
+    int32_t count;      /* destinations, 1..8 */
+    int32_t reserved;
+    int64_t row_offset; /* first destination row of this call's instances */
+    void *U[8];         /* [total_rows, N*nu] each, dtype of desc */
+    int32_t *status[8]; /* [total_rows] each, or NULL */
+} qpmpc_b200_peers;
+
+int qpmpc_b200_solve_scatter(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                             const qpmpc_b200_outputs *out, const qpmpc_b200_peers *peers,
+                             void *stream);
+
 /* Same with HOST buffers: copies operands to the device (pinned staging,
  * buffers cached inside the library per calling thread), solves, copies the
  * outputs back and synchronises.  This is the call a host program that has no

@@ -23,6 +23,7 @@ EXPORTS = (
     "qpmpc_b200_integrate", "qpmpc_b200_workspace_bytes", "qpmpc_b200_max_vars",
     "qpmpc_b200_max_rows", "qpmpc_b200_launch_count", "qpmpc_b200_strerror",
     "qpmpc_b200_version", "qpmpc_b200_fp64_peak", "qpmpc_b200_pendulum_closed_loop",
+    "qpmpc_b200_solve_scatter",
 )
 
 
@@ -66,6 +67,16 @@ class QPFields(ctypes.Structure):
                 ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")]
 
 
+class Peers(ctypes.Structure):
+    """``qpmpc_b200_peers``."""
+
+    _fields_ = [
+        ("count", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("row_offset", ctypes.c_int64),
+        ("U", ctypes.c_void_p * 8), ("status", ctypes.c_void_p * 8),
+    ]
+
+
 class ClosedLoop(ctypes.Structure):
     """``qpmpc_b200_closed_loop``."""
 
@@ -100,8 +111,10 @@ def load():
         P(Desc), P(Operands), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.qpmpc_b200_pendulum_closed_loop.argtypes = [
         P(Desc), P(Operands), P(Outputs), P(ClosedLoop), ctypes.c_void_p]
+    lib.qpmpc_b200_solve_scatter.argtypes = [
+        P(Desc), P(Operands), P(Outputs), P(Peers), ctypes.c_void_p]
     for name in ("solve", "solve_host", "condense", "integrate", "version",
-                 "max_vars", "max_rows", "pendulum_closed_loop"):
+                 "max_vars", "max_rows", "pendulum_closed_loop", "solve_scatter"):
         getattr(lib, f"qpmpc_b200_{name}").restype = ctypes.c_int
     lib.qpmpc_b200_max_vars.argtypes = [ctypes.c_int]
     lib.qpmpc_b200_max_rows.argtypes = [ctypes.c_int, ctypes.c_int]

@@ -41,6 +41,12 @@ struct SolveParams {
     int *status;
     int *iters;
     void *Z;
+    // peer destinations of the fused gather (qpmpc_b200_solve_scatter): rows
+    // [row_off, row_off + batch) of every peer buffer receive U and status
+    int npeers;
+    long long row_off;
+    void *peerU[8];
+    int *peer_status[8];
     // condensed-field dump (condense kernel only)
     void *P, *q, *G, *h, *Phi, *Psi, *phi_last, *psi_last;
 };

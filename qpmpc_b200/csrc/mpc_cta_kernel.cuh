@@ -506,10 +506,16 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
 
     // ---- outputs  // @phase CTA outputs
     __syncthreads();
-    for (int l = tid; l < n; l += nt) static_cast<T *>(p.U)[(size_t)inst * n + l] = (st == 0) ? x[l] : Num<T>::nan();
+    for (int l = tid; l < n; l += nt) {
+        const T xo = (st == 0) ? x[l] : Num<T>::nan();
+        if (p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;
+        for (int r = 0; r < p.npeers; ++r) static_cast<T *>(p.peerU[r])[(size_t)(p.row_off + inst) * n + l] = xo;
+    }
     if (tid == 0) {
-        p.status[inst] = st;
+        if (p.status) p.status[inst] = st;
         if (p.iters) p.iters[inst] = it;
+        for (int r = 0; r < p.npeers; ++r)
+            if (p.peer_status[r]) p.peer_status[r][p.row_off + inst] = st;
     }
     if (p.Z) {
         T *Zb = static_cast<T *>(p.Z) + (size_t)inst * m;

@@ -1092,10 +1092,17 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
 
     // ---- phase D: outputs ---------------------------------------------------  // @phase D outputs
     if (valid) {
-        if (l < n) static_cast<T *>(p.U)[(size_t)inst * n + l] = (st == 0) ? x : Num<T>::nan();
+        const T xo = (st == 0) ? x : Num<T>::nan();
+        if (l < n && p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;
         if (l == 0) {
-            p.status[inst] = st;
+            if (p.status) p.status[inst] = st;
             if (p.iters) p.iters[inst] = it;
+        }
+        // fused gather: the same row goes straight into every peer's buffer
+        // (peer-mapped pointers: the stores travel over NVLink)
+        for (int r = 0; r < p.npeers; ++r) {
+            if (l < n) static_cast<T *>(p.peerU[r])[(size_t)(p.row_off + inst) * n + l] = xo;
+            if (l == 0 && p.peer_status[r]) p.peer_status[r][p.row_off + inst] = st;
         }
         if (p.Z) {
             T *Zb = static_cast<T *>(p.Z) + (size_t)inst * m;

@@ -290,11 +290,13 @@ const char *qpmpc_b200_strerror(int code) {
     return "unknown error";
 }
 
-int qpmpc_b200_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
-                     void *stream) {
+static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                      const qpmpc_b200_peers *peers, void *stream) {
     int rc = check_desc(d, in);
     if (rc) return rc;
-    if (!out || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    if (!out) return QPMPC_B200_EINVAL;
+    if (!peers && (!out->U || !out->status)) return QPMPC_B200_EINVAL;
+    if (peers && (peers->count < 1 || peers->count > 8 || peers->row_offset < 0)) return QPMPC_B200_EINVAL;
     if (d->method != QPMPC_B200_ACTIVE_SET) return QPMPC_B200_EUNSUPPORTED;
     if (d->batch == 0) return 0;
     SolveParams p;
@@ -303,11 +305,31 @@ int qpmpc_b200_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, co
     p.status = out->status;
     p.iters = out->iters;
     p.Z = out->Z;
+    if (peers) {
+        p.npeers = peers->count;
+        p.row_off = peers->row_offset;
+        for (int r = 0; r < peers->count; ++r) {
+            if (!peers->U[r]) return QPMPC_B200_EINVAL;
+            p.peerU[r] = peers->U[r];
+            p.peer_status[r] = peers->status[r];
+        }
+    }
     Variant v;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_cta(p.n, p.m, &v))
         return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);
+}
+
+int qpmpc_b200_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                     void *stream) {
+    return solve_impl(d, in, out, nullptr, stream);
+}
+
+int qpmpc_b200_solve_scatter(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                             const qpmpc_b200_peers *peers, void *stream) {
+    if (!peers) return QPMPC_B200_EINVAL;
+    return solve_impl(d, in, out, peers, stream);
 }
 
 int qpmpc_b200_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_qp_fields *out,

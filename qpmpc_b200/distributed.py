@@ -7,6 +7,7 @@ is the all-gather of the stacked input trajectories U (+ status) so that every
 rank ends with the full result -- NCCL over NVLink on GPUs, gloo in CPU tests.
 """
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
@@ -62,3 +63,62 @@ def solve_mpc_sharded(workload: dict, rank: Optional[int] = None, world: Optiona
     plan = solve_mpc_batch(to_batched(slice_workload(workload, lo, hi), dtype=dtype))
     U_local = plan.inputs.reshape(hi - lo, -1)
     return gather_plans(U_local, plan.status, workload["batch"], group)
+
+
+class PeerGather:
+    """Fused solve + all-gather over NVLink: every rank's kernel stores its U
+    rows (and status) directly into the symmetric buffers of ALL ranks
+    (``qpmpc_b200_solve_scatter``), so no collective moves data afterwards; one
+    barrier makes the rows visible.  Replaces ``solve_mpc_batch`` followed by
+    ``all_gather_into_tensor`` for equal shards of ``rows_per_rank`` instances.
+
+    Needs ``torch.distributed._symmetric_memory`` (CUDA VMM handles shared
+    across the processes of one node); raises ``RuntimeError`` if the buffers
+    cannot be set up, in which case callers fall back to :func:`gather_plans`.
+    """
+
+    def __init__(self, rows_per_rank: int, nb_vars: int, dtype=torch.float64, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("the fused gather addresses at most 8 peers")
+        self.rows, self.n = int(rows_per_rank), int(nb_vars)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        total = self.world * self.rows
+        self.U_all = symm_mem.empty((total, self.n), dtype=dtype, device=dev)
+        self.status_all = symm_mem.empty((total,), dtype=torch.int32, device=dev)
+        self._hU = symm_mem.rendezvous(self.U_all, self.group)
+        self._hS = symm_mem.rendezvous(self.status_all, self.group)
+        self._ptrU = [int(v) for v in self._hU.buffer_ptrs]
+        self._ptrS = [int(v) for v in self._hS.buffer_ptrs]
+        if len(self._ptrU) != self.world or not all(self._ptrU):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+
+    def solve(self, problem, max_iter: int = 0):
+        """Solve this rank's ``rows_per_rank`` instances; on return (stream
+        order) ``U_all`` / ``status_all`` hold the rows of every rank."""
+        from . import _capi
+        from .batched import _ptr
+
+        if problem.batch_size != self.rows or problem.nb_vars != self.n:
+            raise ValueError("problem does not match the gather buffers")
+        lib = _capi.load()
+        desc = problem.desc(_capi.ACTIVE_SET, max_iter, 0.0)
+        peers = _capi.Peers()
+        peers.count = self.world
+        peers.row_offset = self.rank * self.rows
+        for r in range(self.world):
+            peers.U[r] = self._ptrU[r]
+            peers.status[r] = self._ptrS[r]
+        iters = torch.empty(self.rows, dtype=torch.int32, device=problem.device)
+        outs = _capi.Outputs(None, None, _ptr(iters), None)
+        ops = problem.operands()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        rc = lib.qpmpc_b200_solve_scatter(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs),
+                                          ctypes.byref(peers), stream)
+        _capi.check(rc, "qpmpc_b200_solve_scatter")
+        self._hU.barrier()  # every rank's stores have landed everywhere
+        return self.U_all, self.status_all, iters

@@ -358,3 +358,38 @@ def test_pendulum_closed_loop_200_cycles_stays_upright():
     upright = np.abs(X[:, :, 1]).max(axis=0) < 1.2
     assert upright.mean() > 0.9, upright.mean()
     assert np.abs(X[-1, upright, 2] - w["v_target"][upright]).max() < 5e-2
+
+
+def test_solve_scatter_entry_writes_every_destination():
+    """qpmpc_b200_solve_scatter (fused gather): rows land at row_offset in all
+    destination buffers and equal the plain entry's output (single GPU: the
+    'peers' are two local buffers)."""
+    import ctypes
+
+    import torch
+
+    from qpmpc_b200 import _capi
+    from qpmpc_b200.workloads import to_batched, triple_integrator_batch
+
+    w = triple_integrator_batch(333, seed=4)
+    prob, plan = _solve(w)
+    ref = plan.inputs.reshape(333, 16)
+    lib = _capi.load()
+    desc = prob.desc()
+    bufs = [torch.full((1000, 16), -7.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+    sts = [torch.full((1000,), -7, dtype=torch.int32, device="cuda") for _ in range(2)]
+    peers = _capi.Peers()
+    peers.count, peers.row_offset = 2, 500
+    for r in range(2):
+        peers.U[r] = bufs[r].data_ptr()
+        peers.status[r] = sts[r].data_ptr()
+    outs = _capi.Outputs(None, None, None, None)
+    ops = prob.operands()
+    rc = lib.qpmpc_b200_solve_scatter(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs),
+                                      ctypes.byref(peers), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for r in range(2):
+        assert torch.equal(bufs[r][500:833], ref)
+        assert (bufs[r][:500] == -7).all() and (bufs[r][833:] == -7).all()
+        assert (sts[r][500:833] == 0).all() and (sts[r][:500] == -7).all()
