@@ -54,7 +54,7 @@ template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream) {
     using L = Lay<T, NP, MR, MREG>;
     constexpr int IPW = 32 / NP;
-    int wpc = env_int("QPMPC_B200_WPC", NP <= 16 ? 4 : 1);
+    int wpc = env_int("QPMPC_B200_WPC", 4);
     if (wpc < 1) wpc = 1;
     if (wpc > 4) wpc = 4;
     size_t smem = 0;

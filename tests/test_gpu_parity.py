@@ -272,8 +272,9 @@ def test_solve_host_entry_matches_device_entry():
 
 
 def test_fp32_humanoid_within_stated_tolerance():
-    """BASELINE config 4 runs in fp32: |du|_inf <= 2e-3 * max(1, |u|_inf) vs the
-    fp64 oracle (the reference itself is float64 only, mpc_qp.py:93-98)."""
+    """BASELINE config 4 runs in fp32: |du|_inf <= 1e-4 * max(1, |u|_inf) vs the
+    fp64 oracle (measured 1e-5; the reference itself is float64 only,
+    mpc_qp.py:93-98)."""
     import torch
 
     from qpmpc_b200 import solve_mpc_batch
@@ -288,7 +289,7 @@ def test_fp32_humanoid_within_stated_tolerance():
     assert ok.mean() > 0.99
     scale = np.maximum(1.0, np.abs(ref["U"][ok]).max(axis=1))
     err = np.abs(U[ok] - ref["U"][ok]).max(axis=1) / scale
-    assert err.max() <= 2e-3, err.max()
+    assert err.max() <= 1e-4, err.max()
 
 
 def _cpu_closed_loop(w, cycles, substeps=15):
