@@ -168,11 +168,12 @@ __device__ void cta_condense(const SolveParams &p, const CtaLay &L, T *sm, long 
         }
         // cost terms: P += w psi' psi, q += w psi'(xb - ref)
         if (inP) {
-            for (int idx = tid; idx < n * n; idx += nt) {
-                const int i = idx / n, j = idx - i * n;
-                T acc = T(0);
-                for (int t = 0; t < nx; ++t) acc += (w * ps[t * n + i]) * ps[t * n + j];
-                PL[i * ld + j] += acc;
+            for (int i = tid >> 4; i < n; i += nt >> 4) {
+                for (int j = tid & 15; j < n; j += 16) {
+                    T acc = T(0);
+                    for (int t = 0; t < nx; ++t) acc += (w * ps[t * n + i]) * ps[t * n + j];
+                    PL[i * ld + j] += acc;
+                }
             }
         }
         if (inq) {
@@ -376,17 +377,28 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
             rv[l] = a;
             cand[l] = a > T(0) ? lam[l] / a : INF;
         }
-        T a2 = T(0);
-        for (int c = na; c < n; ++c) a2 += d2[c] * d2[c];
         __syncthreads();
-        // step lengths: t1 = min cand (lowest index on ties), t2 = viol_p / |d2|^2
+        // |d2|^2 and the step-length minimum, per warp (every warp gets the same values)
+        const int lane = tid & 31;
+        T a2 = T(0);
+        for (int c = na + lane; c < n; c += 32) a2 += d2[c] * d2[c];
         T t1 = INF;
         int lidx = 0;
-        for (int l = 0; l < na; ++l) {
+        for (int l = lane; l < na; l += 32) {
             const T c = cand[l];
             if (c < t1) {
                 t1 = c;
                 lidx = l;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a2 += __shfl_xor_sync(FULL_MASK, a2, off);
+            const T ot = __shfl_xor_sync(FULL_MASK, t1, off);
+            const int ol = __shfl_xor_sync(FULL_MASK, lidx, off);
+            if (ot < t1 || (ot == t1 && ol < lidx)) {
+                t1 = ot;
+                lidx = ol;
             }
         }
         const T violp = viol[pidx], dn2 = mn2[pidx];
