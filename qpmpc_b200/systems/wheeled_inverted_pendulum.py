@@ -66,28 +66,22 @@ class WheeledInvertedPendulum:
     ) -> MPCProblem:
         """MPC problem with |u| <= max_ground_accel and no state constraint."""
         A, B = self.discretized_dynamics()
-        a_max = self.max_ground_accel
-        return MPCProblem(
-            transition_state_matrix=A,
-            transition_input_matrix=B,
-            ineq_state_matrix=None,
-            ineq_input_matrix=np.array([[1.0], [-1.0]]),
-            ineq_vector=np.array([a_max, a_max], dtype=float),
-            nb_timesteps=self.nb_timesteps,
-            terminal_cost_weight=terminal_cost_weight,
-            stage_state_cost_weight=stage_state_cost_weight,
-            stage_input_cost_weight=stage_input_cost_weight,
-        )
+        bound = float(self.max_ground_accel)
+        # two-sided input bound  -bound <= u <= bound  as  [1; -1] u <= [bound; bound]
+        D, e = np.array([[1.0], [-1.0]]), np.array([bound, bound])
+        return MPCProblem(A, B, None, D, e, self.nb_timesteps, terminal_cost_weight,
+                          stage_state_cost_weight, stage_input_cost_weight)
 
     def integrate(self, state: np.ndarray, ground_accel, dt: float) -> np.ndarray:
         """One plant step of duration dt under a constant ground acceleration."""
-        r, theta, rd, thetad = state
-        rdd = ground_accel
-        thetadd = self.omega**2 * (
-            np.sin(theta) - (rdd / self.GRAVITY) * np.cos(theta)
-        )
-        r_next = r + dt * (rd + dt * (rdd / 2))
-        rd_next = rd + dt * rdd
-        theta_next = theta + dt * (thetad + dt * (thetadd / 2))
-        thetad_next = thetad + dt * thetadd
-        return np.array([r_next, theta_next, rd_next, thetad_next]).flatten()
+        pos, pitch, vel, pitch_rate = np.asarray(state, dtype=float).flatten()
+        accel = float(np.asarray(ground_accel).reshape(-1)[0])
+        # theta_ddot = omega^2 (sin(theta) - (u / g) cos(theta)); second-order Taylor step
+        pitch_accel = self.omega**2 * (np.sin(pitch) - (accel / self.GRAVITY) * np.cos(pitch))
+        half = 0.5 * dt * dt
+        return np.array([
+            pos + dt * vel + half * accel,
+            pitch + dt * pitch_rate + half * pitch_accel,
+            vel + dt * accel,
+            pitch_rate + dt * pitch_accel,
+        ])
