@@ -168,8 +168,8 @@ __device__ __forceinline__ void prow_axpy(T (&Prow)[NP], T a, const T *v) {
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, int NX, bool DUMP>  // @phase A condense (registers)
 __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *const (&in)[OP_COUNT], T *Gc,
-                                             T *gt, T *hs, T *xch, int l, T (&Prow)[NP], T &qj, long long inst,
-                                             bool valid) {
+                                             T *gt, T *hs, T *xch, T *tscr, int l, T (&Prow)[NP], T &qj,
+                                             long long inst, bool valid) {
     using L = Lay<T, NP, MR, false>;  // only LDG is used here
     const int nu = p.nu, nc = p.nc, N = p.N, n = p.n;
     const bool toep = p.toeplitz != 0;
@@ -198,10 +198,13 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
     int row = 0;
 #pragma unroll
     for (int t = 0; t < NX * NX; ++t) Ar[t] = Ak[t];
-    // Fast path (every BASELINE config without a stage cost): A, B, C are time
-    // invariant (Toeplitz mode), two inequality rows per step, no stage cost.
-    // A, B, C sit in registers; a step is the two recursions and the two h rows.
-    const bool fast = !DUMP && toep && nc == 2 && !p.has_wx && !p.q_wx;
+    // Fast path (every BASELINE config): A, B, C are time invariant (Toeplitz
+    // mode) and there are two inequality rows per step.  A, B, C sit in
+    // registers; a step is the two recursions, the two h rows and, with a stage
+    // cost, this lane's share of q.  The stage-cost Hessian is added after the
+    // loop from prefix sums over the Toeplitz columns (nu = 1 only).
+    const bool stageP = p.has_wx != 0, stageq = p.q_wx != 0;
+    const bool fast = !DUMP && toep && nc == 2 && (!stageP || nu == 1);
     if (fast) {
         T Bl[NX], Cr[2 * NX];
 #pragma unroll
@@ -230,12 +233,44 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
                 hs[2 * k] = h0;
                 hs[2 * k + 1] = h1;
             }
+            if (stageq) {
+                // q += w_x psi_k'(phi_k x0 - target_k), column l of psi_k is in registers
+                const T *tg = in[OP_TGT] + k * NX;
+#pragma unroll
+                for (int t = 0; t < NX; ++t) qj += (w_x * psi[t]) * (xb[t] - tg[t]);
+            }
 #pragma unroll
             for (int t = 0; t < NX; ++t) {
                 psi[t] = pn[t];
                 xb[t] = xn[t];
             }
             ek += stepE;
+        }
+        if (stageP) {
+            // P += w_x sum_k psi_k' psi_k with psi_k[:, c] = v_(k-1-c), v_e = A^e B = psi_N[:, n-1-e]:
+            //   P[i][j] += w_x T_|i-j|[N-2-max(i,j)],  T_d[u] = sum_{a<=u} v_a . v_(a+d).
+            // Lane d runs the prefix sum T_d; the table goes through `tscr` (N x NP).
+            T *W = xch + NX * NP;  // v_e by rows of t: W[t*NP + e]
+            if (l < n) {
+#pragma unroll
+                for (int t = 0; t < NX; ++t) W[t * NP + (n - 1 - l)] = psi[t];
+            }
+            __syncwarp();
+            if (l < N) {
+                T acc = T(0);
+                for (int u = 0; u + l < N; ++u) {
+#pragma unroll
+                    for (int t = 0; t < NX; ++t) acc += W[t * NP + u] * W[t * NP + u + l];
+                    tscr[l * NP + u] = acc;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const int hi = l > j ? l : j, d = l > j ? l - j : j - l;
+                if (hi <= N - 2 && l < n && j < n) Prow[j] += w_x * tscr[d * NP + (N - 2 - hi)];
+            }
+            __syncwarp();
         }
     }
     for (int k = fast ? N : 0; k < N; ++k) {
@@ -477,12 +512,12 @@ __device__ __forceinline__ void condense_generic(const SolveParams &p, const T *
 
 template <typename T, int NP, int MR, bool DUMP>
 __device__ __forceinline__ void condense_dispatch(const SolveParams &p, const T *const (&in)[OP_COUNT], T *Gc,
-                                                  T *gt, T *hs, T *xch, T *scr, int l, T (&Prow)[NP], T &qj,
-                                                  long long inst, bool valid) {
+                                                  T *gt, T *hs, T *xch, T *tscr, T *scr, int l, T (&Prow)[NP],
+                                                  T &qj, long long inst, bool valid) {
     switch (p.nx) {
-        case 2: condense_reg<T, NP, MR, 2, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
-        case 3: condense_reg<T, NP, MR, 3, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
-        case 4: condense_reg<T, NP, MR, 4, DUMP>(p, in, Gc, gt, hs, xch, l, Prow, qj, inst, valid); break;
+        case 2: condense_reg<T, NP, MR, 2, DUMP>(p, in, Gc, gt, hs, xch, tscr, l, Prow, qj, inst, valid); break;
+        case 3: condense_reg<T, NP, MR, 3, DUMP>(p, in, Gc, gt, hs, xch, tscr, l, Prow, qj, inst, valid); break;
+        case 4: condense_reg<T, NP, MR, 4, DUMP>(p, in, Gc, gt, hs, xch, tscr, l, Prow, qj, inst, valid); break;
         default: condense_generic<T, NP, MR, DUMP>(p, in, Gc, hs, scr, l, Prow, qj, inst, valid); break;
     }
 }
@@ -604,7 +639,9 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
     // ---- phase A -----------------------------------------------------------
     T Prow[NP];
     T qj;
-    condense_dispatch<T, NP, MR, false>(p, in, Gc, gt, hs, Lc, wk + p.scr_off, l, Prow, qj, inst, valid);
+    // prefix-sum table of the stage-cost Hessian: any NP x NP scratch that is free before phase B
+    condense_dispatch<T, NP, MR, false>(p, in, Gc, gt, hs, Lc, MREG ? Ri : Gc, wk + p.scr_off, l, Prow, qj, inst,
+                                        valid);
 
     // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----  // @phase B cholesky
     bool spd = true;
@@ -1153,7 +1190,7 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     }
     T Prow[NP];
     T qj;
-    condense_dispatch<T, NP, MR, true>(p, in, Gc, gt, hs, xch, wk + p.scr_off, l, Prow, qj, inst, valid);
+    condense_dispatch<T, NP, MR, true>(p, in, Gc, gt, hs, xch, Gc, wk + p.scr_off, l, Prow, qj, inst, valid);
     if (!valid) return;
     if (p.P && l < n) {
         T *Pb = static_cast<T *>(p.P) + ((size_t)inst * n + l) * n;

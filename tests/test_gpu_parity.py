@@ -68,7 +68,8 @@ def test_condense_matches_reference_fields(name):
 @pytest.mark.parametrize("name", ["triple_integrator", "humanoid", "pendulum",
                                   "random_ltv_cd", "random_ltv_c", "random_ltv_d",
                                   "triple_integrator_N8", "triple_integrator_N32",
-                                  "triple_integrator_N64"])
+                                  "triple_integrator_N64", "triple_integrator_stage",
+                                  "triple_integrator_tiny_wt"])
 def test_solve_mpc_single_matches_oracle(name):
     """solve_mpc(problem, "b200") on the golden problems vs the exact QP oracle
     applied to the REFERENCE's condensed matrices."""
