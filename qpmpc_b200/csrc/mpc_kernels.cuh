@@ -1157,7 +1157,9 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
 // for the MPCQP host class (qpmpc/mpc_qp.py:28-37).  Same phase-A code as the
 // fused kernel.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR>  // @phase condense-only kernel
+// DUMP = false runs exactly the phase-A code of the fused kernel (fast paths
+// included) for P, q, G, h; DUMP = true adds the Phi / Psi stacks.
+template <typename T, int NP, int MR, bool DUMP>  // @phase condense-only kernel
 __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, false>;
     constexpr int IPW = 32 / NP;
@@ -1190,7 +1192,7 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     }
     T Prow[NP];
     T qj;
-    condense_dispatch<T, NP, MR, true>(p, in, Gc, gt, hs, xch, Gc, wk + p.scr_off, l, Prow, qj, inst, valid);
+    condense_dispatch<T, NP, MR, DUMP>(p, in, Gc, gt, hs, xch, Gc, wk + p.scr_off, l, Prow, qj, inst, valid);
     if (!valid) return;
     if (p.P && l < n) {
         T *Pb = static_cast<T *>(p.P) + ((size_t)inst * n + l) * n;

@@ -89,16 +89,32 @@ int launch_condense(SolveParams p, cudaStream_t stream) {
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     const int ipc = IPW * wpc;
-    auto kern = mpc_condense_kernel<T, NP, MR>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
     const int grid = (p.batch + ipc - 1) / ipc;
     if (grid == 0) return 0;
-    kern<<<grid, wpc * 32, smem, stream>>>(p);
-    count_launch();
+    // P, q, G, h come from the same phase-A code the fused kernel runs; the
+    // Phi / Psi stacks need the instrumented variant: two launches if both.
+    const bool want_qp = p.P || p.q || p.G || p.h;
+    const bool want_dump = p.Phi || p.Psi || p.phi_last || p.psi_last;
+    if (want_qp) {
+        SolveParams a = p;
+        a.Phi = a.Psi = a.phi_last = a.psi_last = nullptr;
+        auto kern = mpc_condense_kernel<T, NP, MR, false>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        kern<<<grid, wpc * 32, smem, stream>>>(a);
+        count_launch();
+    }
+    if (want_dump) {
+        SolveParams b = p;
+        b.P = b.q = b.G = b.h = nullptr;
+        auto kern = mpc_condense_kernel<T, NP, MR, true>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        kern<<<grid, wpc * 32, smem, stream>>>(b);
+        count_launch();
+    }
     return (int)cudaGetLastError();
 }
-
 
 #define QPMPC_INSTANTIATE_VARIANT(T, NP, MR, MREG)                               \
     template int launch_solve<T, NP, MR, MREG>(SolveParams, cudaStream_t);      \
