@@ -25,7 +25,7 @@ struct CtaLay {
     int ld, oM, oJ, oPL, oRi, oV, total;  // offsets in elements of T
     int o_hs, o_viol, o_vtol, o_ginv, o_mn2, o_gz;
     int o_q, o_x, o_z, o_dd, o_d2, o_lam, o_rv, o_dv, o_tq, o_cand, o_cs, o_sn;
-    int o_aidx, o_actf, o_red;  // int / int / 16 x 8-byte reduction slots
+    int o_aidx, o_actf, o_red, o_sc;  // int / int / 16 x 8-byte reduction slots / 8 scalars
 };
 
 __host__ __device__ inline int even_up(int v) { return (v + 1) & ~1; }
@@ -36,7 +36,8 @@ __host__ __device__ inline CtaLay cta_layout(int n, int m, int nx, int esz) {
     CtaLay L;
     L.ld = n | 1;
     const int mat = even_up(n * L.ld);
-    const int scratch = even_up(2 * nx * n + 2 * nx + 2 * nx * nx);
+    // generic condensing: psi[2][nx][n], xbar[2][nx], phi[2][nx][nx]; LTI path: W[nx][n], XB[N+1][nx] (N <= n)
+    const int scratch = even_up(2 * nx * n + 2 * nx + 3 * nx * nx + nx);
     L.oM = 0;
     L.oJ = L.oM + even_up(m * L.ld);
     L.oPL = L.oJ + mat;
@@ -65,23 +66,27 @@ __host__ __device__ inline CtaLay cta_layout(int n, int m, int nx, int esz) {
     L.o_aidx = o, o += even_up((ne * 4 + esz - 1) / esz);
     L.o_actf = o, o += even_up((me * 4 + esz - 1) / esz);
     L.o_red = o, o += even_up((16 * 8 + esz - 1) / esz);
+    L.o_sc = o, o += 8;
     L.total = o;
     return L;
 }
 
 // ---- block-wide reductions over 64-bit keys ---------------------------------
-__device__ __forceinline__ unsigned long long block_reduce_max(unsigned long long key, unsigned long long *red) {
+__device__ __forceinline__ unsigned long long block_reduce_max(unsigned long long key, unsigned long long *red,
+                                                               int parity) {
+    // `red` has two sets of 8 slots used alternately, so one barrier per call is
+    // enough (a warp can only be one call ahead of the slowest reader).
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long o = __shfl_xor_sync(FULL_MASK, key, off);
         key = o > key ? o : key;
     }
+    unsigned long long *slot = red + (parity & 1) * 8;
     const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) red[warp] = key;
+    if ((threadIdx.x & 31) == 0) slot[warp] = key;
     __syncthreads();
     unsigned long long r = 0ull;
-    for (int w = 0; w < nw; ++w) r = red[w] > r ? red[w] : r;
-    __syncthreads();
+    for (int w = 0; w < nw; ++w) r = slot[w] > r ? slot[w] : r;
     return r;
 }
 
@@ -105,6 +110,127 @@ __device__ __forceinline__ const T *operand(const SolveParams &p, int o, long lo
 // rolls column c of psi_k through the scratch region; G goes to M (row-major),
 // P to PL (full symmetric matrix), q and h to their vectors.
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Condensing of a time-invariant model (A, B, C constant over the horizon; D, e
+// may vary) without the N-step barrier loop.  psi_k[:, c] = A^(k-1-j) B[:, jj]
+// (c = j nu + jj) depends on e = k nu - 1 - c only, so two serial chains, run
+// by one thread each, produce everything the rest needs:
+//   W[:, e] = A^d B[:, jj],  e = d nu + (nu - 1 - jj)      (thread 0)
+//   XB[k]  = A^k x0,  k = 0..N                             (thread 32)
+// and then, in parallel over entries,
+//   G[(k, r), c] = C_r W[:, k nu - 1 - c]  (c < k nu),  D_k on block column k,
+//   h[(k, r)]    = e_k[r] - C_r XB[k],
+//   P = w_u I + w_t psi_N' psi_N + w_x sum_k psi_k' psi_k  (the last term from
+//       prefix sums along the Toeplitz diagonals, nu = 1), q likewise.
+// Scratch: W, XB in the R^-1 region, the prefix-sum table in the J region.
+// ---------------------------------------------------------------------------
+template <typename T>  // @phase CTA condense (time-invariant model)
+__device__ void cta_condense_lti(const SolveParams &p, const CtaLay &L, T *sm, long long inst) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nx = p.nx, nu = p.nu, nc = p.nc, N = p.N, n = p.n, m = p.m, ld = L.ld;
+    T *M = sm + L.oM, *PL = sm + L.oPL, *Tt = sm + L.oJ;
+    T *W = sm + L.oRi;            // [nx][n]
+    T *XB = W + nx * n;           // [N + 1][nx]
+    T *hs = sm + L.o_hs, *q = sm + L.o_q;
+    const T *A = operand<T>(p, OP_A, inst), *B = operand<T>(p, OP_B, inst);
+    const T *C = operand<T>(p, OP_C, inst), *D = operand<T>(p, OP_D, inst);
+    const T *e = operand<T>(p, OP_E, inst), *x0 = operand<T>(p, OP_X0, inst);
+    const T *goal = operand<T>(p, OP_GOAL, inst), *tgt = operand<T>(p, OP_TGT, inst);
+    const T w_t = (T)p.w_t, w_x = (T)p.w_x;
+    // Thread jj < nu runs the chain of input column jj, thread 32 the free
+    // response; vectors stay in registers (nx <= 8), A is read from shared memory.
+    T *As = XB + (N + 1) * nx;
+    for (int i = tid; i < nx * nx; i += nt) As[i] = A[i];
+    __syncthreads();
+    const int chain = tid < nu ? tid : ((tid == 32 || (nt <= 32 && tid == nu)) ? nu : -1);
+    if (chain >= 0) {
+        T v[8], w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = t < nx ? (chain < nu ? B[t * nu + chain] : x0[t]) : T(0);
+        const int steps = chain < nu ? N - 1 : N;
+        for (int d = 0; d <= steps; ++d) {
+            // store the current vector, then advance it by A
+            if (chain < nu) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < nx) W[t * n + d * nu + (nu - 1 - chain)] = v[t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < nx) XB[d * nx + t] = v[t];
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                T acc = T(0);
+#pragma unroll
+                for (int s2 = 0; s2 < 8; ++s2)
+                    if (t < nx && s2 < nx) acc += As[t * nx + s2] * v[s2];
+                w[t] = acc;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = w[t];
+        }
+    }
+    __syncthreads();
+    // G and h
+    for (int idx = tid; idx < m * n; idx += nt) {
+        const int row = idx / n, c = idx - row * n;
+        const int k = row / nc, r = row - k * nc, kb = k * nu;
+        T g = T(0);
+        if (c < kb) {
+            if (C)
+                for (int t = 0; t < nx; ++t) g += C[r * nx + t] * W[t * n + kb - 1 - c];
+        } else if (D && c - kb < nu) {
+            g = D[k * p.op[OP_D].step + r * nu + c - kb];
+        }
+        M[row * ld + c] = g;
+    }
+    for (int row = tid; row < m; row += nt) {
+        const int k = row / nc, r = row - k * nc;
+        T hv = e[k * p.op[OP_E].step + r];
+        if (C)
+            for (int t = 0; t < nx; ++t) hv -= C[r * nx + t] * XB[k * nx + t];
+        hs[row] = hv;
+    }
+    // prefix sums T_d[u] = sum_{a <= u} v_a . v_(a+d) for the stage-cost Hessian (nu = 1)
+    if (p.has_wx)
+        for (int d = tid; d < N; d += nt) {
+            T acc = T(0);
+            for (int u = 0; u + d < N; ++u) {
+                for (int t = 0; t < nx; ++t) acc += W[t * n + u] * W[t * n + u + d];
+                Tt[d * ld + u] = acc;
+            }
+        }
+    __syncthreads();
+    // P (full symmetric matrix) and q
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx - i * n;
+        T acc = (i == j) ? (T)p.w_u : T(0);
+        if (p.has_wt) {
+            T a = T(0);
+            for (int t = 0; t < nx; ++t) a += (w_t * W[t * n + n - 1 - i]) * W[t * n + n - 1 - j];
+            acc += a;
+        }
+        if (p.has_wx) {
+            const int hi = i > j ? i : j, d = i > j ? i - j : j - i;
+            if (hi <= N - 2) acc += w_x * Tt[d * ld + (N - 2 - hi)];
+        }
+        PL[i * ld + j] = acc;
+    }
+    for (int c = tid; c < n; c += nt) {
+        T acc = T(0);
+        if (p.q_wt)
+            for (int t = 0; t < nx; ++t) acc += (w_t * W[t * n + n - 1 - c]) * (XB[N * nx + t] - goal[t]);
+        if (p.q_wx)
+            for (int k = c / nu + 1; k < N; ++k) {
+                const int e1 = k * nu - 1 - c;
+                for (int t = 0; t < nx; ++t) acc += (w_x * W[t * n + e1]) * (XB[k * nx + t] - tgt[k * nx + t]);
+            }
+        q[c] = acc;
+    }
+    __syncthreads();
+}
+
 template <typename T, bool DUMP>  // @phase CTA condense
 __device__ void cta_condense(const SolveParams &p, const CtaLay &L, T *sm, long long inst) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -264,19 +390,26 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
     int *aidx = reinterpret_cast<int *>(sm + L.o_aidx);
     int *actf = reinterpret_cast<int *>(sm + L.o_actf);
     unsigned long long *red = reinterpret_cast<unsigned long long *>(sm + L.o_red);
+    T *sc = sm + L.o_sc;
 
-    cta_condense<T, false>(p, L, sm, inst);
+    {
+        const bool lti = p.op[OP_A].step == 0 && p.op[OP_B].step == 0 && (!p.op[OP_C].ptr || p.op[OP_C].step == 0);
+        if (lti && p.nc > 0 && p.nx <= 8 && p.nu < 32 && (!p.has_wx || p.nu == 1) && p.toeplitz)
+            cta_condense_lti<T>(p, L, sm, inst);
+        else
+            cta_condense<T, false>(p, L, sm, inst);
+    }
 
     // ---- Cholesky in place on PL (lower triangle)  // @phase CTA cholesky
     bool spd = true;
     {
         const int ti = tid >> 4, tj = tid & 15, rows = nt >> 4;
         for (int c = 0; c < n; ++c) {
+            // the diagonal entry keeps the pivot (nothing reads L_cc: 1/L_cc is in dv)
             const T piv = PL[c * ld + c];
             spd = spd && (piv > T(0));
             const T inv = rsqrt_(piv);
-            __syncthreads();
-            for (int i = c + tid; i < n; i += nt) PL[i * ld + c] *= inv;
+            for (int i = c + 1 + tid; i < n; i += nt) PL[i * ld + c] *= inv;
             if (tid == 0) dv[c] = inv;
             __syncthreads();
             for (int i = c + 1 + ti; i < n; i += rows) {
@@ -340,7 +473,7 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
                     key = ks > key ? ks : key;
                 }
             }
-            key = block_reduce_max(key, red);
+            key = block_reduce_max(key, red, it);
             if (key == 0ull) break;  // primal feasible: optimal
             pidx = 4095 - (int)(key & 4095ull);
             lamp = T(0);
@@ -354,6 +487,11 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
             const T dl = -M[pidx * ld + c];
             dd[c] = dl;
             d2[c] = (c >= na) ? dl : T(0);
+            if (c == na) sc[2] = dl;
+        }
+        if (tid == 0) {
+            sc[0] = viol[pidx];
+            sc[1] = mn2[pidx];
         }
         __syncthreads();
         // z = J2 d2, G z = M2 d2, r = R^-1 d1, |d2|^2
@@ -401,7 +539,8 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
                 lidx = ol;
             }
         }
-        const T violp = viol[pidx], dn2 = mn2[pidx];
+        // scalars published with d: nothing read below is written again before the closing barrier
+        const T violp = sc[0], dn2 = sc[1];
         const bool zzero = !(a2 > Num<T>::dep_eps * dn2);
         const T t2 = zzero ? INF : violp / a2;
         if (t1 == INF && t2 == INF) {
@@ -410,8 +549,7 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
         }
         const T t = fmin(t1, t2);
         const bool full = !zzero && t2 <= t1;
-        const T dna = d2[na < n ? na : n - 1];
-        __syncthreads();  // everyone has read cand, viol[pidx], d2[na]
+        const T dna = na < n ? sc[2] : T(0);
         if (!zzero) {
             for (int l = tid; l < n; l += nt) x[l] += t * z[l];
             for (int r = tid; r < m; r += nt) viol[r] += t * gzv[r];
@@ -425,19 +563,19 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
             const T beta = (dna > T(0)) ? -alpha : alpha;
             const T binv = (dna > T(0)) ? -ainv : ainv;
             const T tau = T(1) / (a2 - beta * dna);
-            if (tid == 0) d2[na] = dna - beta;
-            __syncthreads();
+            const T vna = dna - beta;  // v differs from d2 in entry na only
             for (int task = tid; task < n + m; task += nt) {
                 T *row = task < n ? J + task * ld : M + (task - n) * ld;
-                T a0 = T(0), a1 = T(0);
-                int c = na;
+                T a0 = row[na] * vna, a1 = T(0);
+                int c = na + 1;
                 for (; c + 1 < n; c += 2) {
                     a0 += row[c] * d2[c];
                     a1 += row[c + 1] * d2[c + 1];
                 }
                 if (c < n) a0 += row[c] * d2[c];
                 const T s = (a0 + a1) * tau;
-                for (c = na; c < n; ++c) row[c] -= s * d2[c];
+                row[na] -= s * vna;
+                for (c = na + 1; c < n; ++c) row[c] -= s * d2[c];
             }
             for (int l = tid; l <= na; l += nt) {
                 if (l < na) {

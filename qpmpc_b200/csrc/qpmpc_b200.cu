@@ -129,7 +129,8 @@ size_t cta_smem_bytes(int n, int m, int nx) {
 }
 
 template <typename T>
-int launch_solve_cta(const SolveParams &p, cudaStream_t stream) {
+int launch_solve_cta(SolveParams p, cudaStream_t stream) {
+    p.toeplitz = env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0;  // the time-invariant condensing path may be used
     const size_t smem = cta_smem_bytes<T>(p.n, p.m, p.nx);
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     auto kern = mpc_solve_cta_kernel<T>;
