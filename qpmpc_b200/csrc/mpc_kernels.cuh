@@ -33,6 +33,9 @@
 #ifndef QPMPC_MINB
 #define QPMPC_MINB 4
 #endif
+#ifndef QPMPC_SYNC_TAIL
+#define QPMPC_SYNC_TAIL 1
+#endif
 
 namespace qpmpc {
 
@@ -588,7 +591,7 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool MREG>  // @phase kernel prologue
-__global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_solve_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, MREG>;
     using T2 = typename Pair<T>::type;
     constexpr bool HASJ = !MREG;
@@ -1084,6 +1087,10 @@ __global__ void __launch_bounds__(128, (NP <= 16 && MREG) ? QPMPC_MINB : 1) mpc_
         __syncwarp();
     }
 
+    // The warps of the CTA leave the iteration at different times but hold the
+    // CTA's resources until the last one is done: let them run the (unrolled,
+    // one-shot) recovery code together so that they share instruction fetches.
+    if (!HASJ && QPMPC_SYNC_TAIL) __syncthreads();
     // ---- x from the multipliers (J not kept): x = -P^-1 (q + G_A' lambda)  // @phase D x from multipliers
     if (!HASJ) {
         // w_l = q_l + sum_i lambda_i G[a_i, l]

@@ -54,9 +54,9 @@ template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream) {
     using L = Lay<T, NP, MR, MREG>;
     constexpr int IPW = 32 / NP;
-    int wpc = env_int("QPMPC_B200_WPC", 4);
+    int wpc = env_int("QPMPC_B200_WPC", 8);
     if (wpc < 1) wpc = 1;
-    if (wpc > 4) wpc = 4;
+    if (wpc > 8) wpc = 8;
     size_t smem = 0;
     for (;; --wpc) {
         smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, MREG);
