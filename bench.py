@@ -7,12 +7,15 @@
 Workload (BASELINE.json configs[1]): triple integrator (nx=3, nu=1, nc=2, N=16),
 fp64, 65 536 instances per GPU, per-instance A, B, C, e, x0, goal records
 (seed 0).  A "step" condenses and solves the whole batch once.
-Weak scaling: every rank owns its own 65 536 instances; for N > 1 each step
-ends with the one all-gather of the stacked U the north star names.
+Weak scaling: every rank owns its own 65 536 instances; for N > 1 every rank
+ends each step with the stacked U of ALL ranks -- the all-gather the north star
+names, fused into the solve kernel (its epilogue stores each row into every
+rank's symmetric buffer over NVLink; NCCL all-gather is the fallback).
 
 `value`     device-resident throughput (inputs already in HBM), CUDA events.
 `e2e`       the same batch through qpmpc_b200_solve_host with pinned HOST
-            buffers: H2D of every operand + kernel + D2H of U/status per step.
+            buffers: H2D of every operand + kernel + D2H of U/status per step
+            (pipelined over three streams in chunks, one sync per step).
 `roofline`  algorithmic bytes per launch / measured kernel time vs the HBM
             peak -- by construction tiny: the path is FP64-issue bound, so the
             FP64 fraction is reported next to it (`fp64`).

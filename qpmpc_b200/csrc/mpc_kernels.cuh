@@ -2,28 +2,31 @@
 //
 // One group of NP lanes (NP = 8, 16 or 32, the padded number of decision
 // variables n = N*nu) owns one MPC instance; a warp carries 32/NP instances.
-// Lane l is variable l and owns row l of every n x n matrix of the instance
-// in REGISTERS; it also owns MR constraint rows (l, l+NP, ...).  Lanes talk
-// through a small shared-memory region per instance and warp shuffles; there
-// is no block-level synchronisation after the inputs have been staged.
+// Lane l is variable l; it owns MR constraint rows (l, l+NP, ...) and keeps
+// its rows of the n-column matrices in REGISTERS.  Lanes talk through a small
+// shared-memory region per instance and warp shuffles; between the staging of
+// the inputs and the tail there is no block-level synchronisation.
 //
 // Phases (reference citations relative to /root/reference):
 //   0  stage A,B,C,D,e,x0,goal,targets of the CTA's instances into shared
 //      memory: one 1-D bulk TMA copy per operand (cp.async.bulk + mbarrier).
 //   A  condensing, qpmpc/mpc_qp.py:53-105 and :139-149.  Lane l rolls column
 //      l of psi_k and the free response phi_k x0 in registers (nx = 2, 3, 4
-//      compiled; other nx go through shared memory), emits column l of every
-//      G row and h, accumulates row l of P and q_l.
+//      compiled; other nx go through shared memory), emits h and q_l and row l
+//      of P.  Time-invariant A, B, C: G is kept as a Toeplitz table (nc x n
+//      numbers) instead of the dense m x n matrix.
 //   B  Cholesky P = L L' (row per lane, columns published in shared memory),
-//      then forward substitutions with L, all lane-local: row l of J = L^-T,
-//      t = J'q, x = -J t, the owned rows of M = G J; violations G x - h.
-//   C  Goldfarb-Idnani dual active-set iteration on (J, M, R, R^-1) -- the
-//      algorithm of the quadprog backend behind qpsolvers.solve_problem
-//      (qpmpc/solve_mpc.py:43) -- with a Householder reflection instead of a
-//      Givens sweep when a constraint enters, and R^-1 kept explicitly (its
-//      new column is -r/beta, free).  Exact on exit: x solves the KKT system
-//      of its active set to rounding error.
-//   D  write U (coalesced), status, iterations and optionally multipliers.
+//      then lane-local forward substitutions with L: t = L^-1 q and the owned
+//      rows of M = G L^-T; violations at the unconstrained optimum are -M t - h.
+//   C  Goldfarb-Idnani dual active-set iteration -- the algorithm of the
+//      quadprog backend behind qpsolvers.solve_problem (qpmpc/solve_mpc.py:43)
+//      -- on (M, R^-1): a Householder reflection when a constraint enters,
+//      Givens rotations derived from R^-1 alone when one leaves; R^-1 gains the
+//      column [-r/beta; 1/beta] for free.  J = L^-T Q is never formed when M
+//      lives in registers.  Exact on exit.
+//   D  x = -P^-1 (q + G_A' lambda) from the multipliers (two triangular solves
+//      with L), then U (coalesced), status, iterations, optional multipliers,
+//      optional stores into peer buffers (fused gather).
 #pragma once
 
 #include "mpc_common.cuh"
@@ -216,6 +219,7 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
             Cr[t] = hasC ? Ck[t] : T(0);
             Cr[NX + t] = hasC ? Ck[NX + t] : T(0);
         }
+#pragma unroll 2
         for (int k = 0; k < N; ++k) {
             T h0 = ek[0], h1 = ek[1];
             T pn[NX], xn[NX];
