@@ -22,7 +22,8 @@
  *  <0   bad argument / unsupported shape (QPMPC_B200_E*),
  *  >0   a cudaError_t.
  * Per-instance outcome is written to status[batch]:
- *   0 solved, 1 iteration limit, 2 infeasible, 3 Hessian not positive definite;
+ *   0 solved, 1 iteration limit, 2 infeasible, 3 numerical failure (Hessian not
+ *   positive definite, or non-finite operands);
  * Plan.is_empty  <=>  status != 0  (qpmpc/plan.py:36,45-48).  U of an
  * unsolved instance is filled with NaN.
  *

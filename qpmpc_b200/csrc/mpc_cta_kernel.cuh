@@ -656,6 +656,12 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
 
     // ---- outputs  // @phase CTA outputs
     __syncthreads();
+    {
+        // non-finite data: report a numerical failure instead of NaN inputs with status 0
+        int bad = 0;
+        for (int l = tid; l < n; l += nt) bad |= !(abs_(x[l]) < Num<T>::inf());
+        if (st == 0 && __syncthreads_or(bad)) st = 3;
+    }
     for (int l = tid; l < n; l += nt) {
         const T xo = (st == 0) ? x[l] : Num<T>::nan();
         if (p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;

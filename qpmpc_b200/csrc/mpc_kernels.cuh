@@ -1139,6 +1139,12 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
     }
 
     // ---- phase D: outputs ---------------------------------------------------  // @phase D outputs
+    // Non-finite data (NaN / inf operands) slip through every comparison above:
+    // an instance whose solution is not finite is reported as a numerical failure.
+    {
+        const unsigned nonfinite = __ballot_sync(FULL_MASK, !(abs_(x) < Num<T>::inf())) & segmask;  // all lanes vote
+        if (st == 0 && nonfinite) st = 3;
+    }
     if (valid) {
         const T xo = (st == 0) ? x : Num<T>::nan();
         if (l < n && p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;

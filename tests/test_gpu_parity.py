@@ -395,3 +395,30 @@ def test_solve_scatter_entry_writes_every_destination():
         assert torch.equal(bufs[r][500:833], ref)
         assert (bufs[r][:500] == -7).all() and (bufs[r][833:] == -7).all()
         assert (sts[r][500:833] == 0).all() and (sts[r][:500] == -7).all()
+
+
+def test_non_finite_operands_are_flagged_not_returned():
+    """NaN / inf in an instance's data gives status 3 and NaN inputs for that
+    instance only; its warp neighbours are solved as usual."""
+    from qpmpc_b200.workloads import triple_integrator_batch
+
+    for force_cta in (False, True):
+        w = triple_integrator_batch(40, seed=13)
+        w["x0"][3, 1] = np.nan
+        w["goal"][8, 0] = np.inf
+        w["A"][21, 0, 1] = np.nan
+        import os
+
+        if force_cta:
+            os.environ["QPMPC_B200_FORCE_CTA"] = "1"
+        try:
+            prob, plan = _solve(w)
+        finally:
+            os.environ.pop("QPMPC_B200_FORCE_CTA", None)
+        st = plan.status.cpu().numpy()
+        U = plan.inputs.reshape(40, -1).cpu().numpy()
+        bad = np.array([3, 8, 21])
+        assert (st[bad] != 0).all(), st[bad]
+        assert np.isnan(U[bad]).all()
+        good = np.setdiff1d(np.arange(40), bad)
+        assert (st[good] == 0).all() and np.isfinite(U[good]).all()
