@@ -55,7 +55,11 @@ struct Lay {
     static constexpr int oRi = MREG ? oRL + szRL : oRL;
     static constexpr int oV = oRL + szRL + (MREG ? NP * NP : 0);  // qs, xs, dv, dd, d2 [NP each], sc[8]
     static constexpr int szV = 5 * NP + 8;
-    static constexpr int fixed = oV + szV;  // runtime-sized tail follows (TailLay)
+    // per-row constants of the iteration (vtol, ginv, |M_i|^2, MP each) live in shared memory
+    // where registers are the scarce resource (NP = 16 with M in registers), else in registers
+    static constexpr bool ROWS_IN_SMEM = (NP == 16 && MREG);
+    static constexpr int oW = oV + szV;
+    static constexpr int fixed = oW + (ROWS_IN_SMEM ? 3 * MP : 0);  // runtime-sized tail follows (TailLay)
     static_assert(NP * NP <= szRL, "R^-1 must fit in the L region");
     static_assert(8 * NP <= szRL, "psi exchange buffers must fit in the L region");
 };
@@ -682,7 +686,19 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
     T Jrow[HASJ ? NP : 1];
     T Mrow[MREG ? MR : 1][NP];
     T x = T(0);
-    T viol[MR], mn2[MR], vtol[MR], ginv[MR];
+    T viol[MR];
+    constexpr bool RS = L::ROWS_IN_SMEM;
+    T rowc[RS ? 1 : 3][RS ? 1 : MR];                  // vtol, ginv, |M_i|^2 in registers ...
+    T *rowc_s = wk + L::oW;                            // ... or in shared memory [3][MP]
+    auto rc_set = [&](int which, int s, T v) {
+        if (RS)
+            rowc_s[which * L::MP + l + s * NP] = v;
+        else
+            rowc[RS ? 0 : which][RS ? 0 : s] = v;
+    };
+    auto rc_get = [&](int which, int s) -> T {
+        return RS ? rowc_s[which * L::MP + l + s * NP] : rowc[RS ? 0 : which][RS ? 0 : s];
+    };
     bool rowvalid[MR];
     {
         T tq[NP];
@@ -732,8 +748,8 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
             // eps * (max(1, |h_i|) + |G_i|)
             const T hi = rowvalid[s] ? hs[row] : T(0);
             viol[s] = -hi;
-            vtol[s] = Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2));
-            ginv[s] = g2 > T(0) ? frsqrt_(g2) : T(1e30);
+            rc_set(0, s, Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2)));
+            rc_set(1, s, g2 > T(0) ? frsqrt_(g2) : T(1e30));
         };
         // after the solve src is row s of M: M t (= -G x) and |M_s|^2
         auto finish_row = [&](int s, const T(&src)[NP]) {
@@ -745,7 +761,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
                 v0 += src[c] * tq[c];
                 v1 += src[c + 1] * tq[c + 1];
             }
-            mn2[s] = m0 + m1;
+            rc_set(2, s, m0 + m1);
             // G x - h with x = -P^-1 q = -J t: G x = -(G J) t = -M t
             viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : T(-1);
             if (!MREG) {
@@ -832,8 +848,8 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
             int bi = 0;
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
-                const T score = viol[s] * ginv[s];
-                if (sel && rowvalid[s] && !((actbits >> s) & 1) && viol[s] > vtol[s] && score > best) {
+                const T score = viol[s] * rc_get(1, s);
+                if (sel && rowvalid[s] && !((actbits >> s) & 1) && viol[s] > rc_get(0, s) && score > best) {
                     best = score;
                     bi = l + s * NP;
                 }
@@ -879,7 +895,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
                             *reinterpret_cast<T2 *>(dd + c) = v;
                         }
                         sc[0] = viol[s];
-                        sc[1] = mn2[s];
+                        sc[1] = rc_get(2, s);
                     }
                 }
             }
@@ -892,7 +908,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
                 for (int s = 0; s < MR; ++s) {
                     if (s == pslot) {
                         sc[0] = viol[s];
-                        sc[1] = mn2[s];
+                        sc[1] = rc_get(2, s);
                     }
                 }
             }
