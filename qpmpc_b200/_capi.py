@@ -10,7 +10,8 @@ import os
 from .exceptions import BackendError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqpmpc_b200.so")
+# QPMPC_B200_LIB selects another build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("QPMPC_B200_LIB") or os.path.join(_HERE, "lib", "libqpmpc_b200.so")
 
 ABSENT, SHARED_LTI, SHARED_LTV, BATCH_LTI, BATCH_LTV = range(5)
 VEC_ABSENT, VEC_SHARED, VEC_BATCH = range(3)

@@ -24,8 +24,9 @@ NVCC_FLAGS = [
     "-std=c++17", "-Xcompiler", "-fPIC",
 ]
 # tuning experiments: QPMPC_MINB=<resident CTAs/SM> overrides the kernels' default
-if os.environ.get("QPMPC_MINB"):
-    NVCC_FLAGS.append("-DQPMPC_MINB=" + os.environ["QPMPC_MINB"])
+for _macro in ("QPMPC_MINB", "QPMPC_SYNC_TAIL", "QPMPC_ROWS_SMEM"):
+    if os.environ.get(_macro):
+        NVCC_FLAGS.append(f"-D{_macro}=" + os.environ[_macro])
 
 
 def _nvcc() -> str:

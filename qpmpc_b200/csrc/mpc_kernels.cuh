@@ -40,9 +40,10 @@
 #define QPMPC_SYNC_TAIL 1
 #endif
 
+
 namespace qpmpc {
 
-template <typename T, int NP, int MR, bool MREG>
+template <typename T, int NP, int MR, bool MREG, bool RS = false>
 struct Lay {
     static constexpr int MP = MR * NP;     // padded constraint rows
     static constexpr int LDG = MP + 1;     // G / M by columns: Gc[c*LDG + row]
@@ -55,9 +56,9 @@ struct Lay {
     static constexpr int oRi = MREG ? oRL + szRL : oRL;
     static constexpr int oV = oRL + szRL + (MREG ? NP * NP : 0);  // qs, xs, dv, dd, d2 [NP each], sc[8]
     static constexpr int szV = 5 * NP + 8;
-    // per-row constants of the iteration (vtol, ginv, |M_i|^2, MP each) live in shared memory
-    // where registers are the scarce resource (NP = 16 with M in registers), else in registers
-    static constexpr bool ROWS_IN_SMEM = (NP == 16 && MREG);
+    // RS: the per-row constants of the iteration (vtol, ginv, |M_i|^2, MP each) live in shared
+    // memory instead of registers (an option of the NP = 16 register-resident variant)
+    static constexpr bool ROWS_IN_SMEM = RS;
     static constexpr int oW = oV + szV;
     static constexpr int fixed = oW + (ROWS_IN_SMEM ? 3 * MP : 0);  // runtime-sized tail follows (TailLay)
     static_assert(NP * NP <= szRL, "R^-1 must fit in the L region");
@@ -598,9 +599,9 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     shared memory, row l of J is kept in registers and x moves with every
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR, bool MREG>  // @phase kernel prologue
+template <typename T, int NP, int MR, bool MREG, bool RS>  // @phase kernel prologue
 __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) mpc_solve_kernel(const SolveParams p) {
-    using L = Lay<T, NP, MR, MREG>;
+    using L = Lay<T, NP, MR, MREG, RS>;
     using T2 = typename Pair<T>::type;
     constexpr bool HASJ = !MREG;
     constexpr int IPW = 32 / NP;  // instances per warp
@@ -687,7 +688,6 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) 
     T Mrow[MREG ? MR : 1][NP];
     T x = T(0);
     T viol[MR];
-    constexpr bool RS = L::ROWS_IN_SMEM;
     T rowc[RS ? 1 : 3][RS ? 1 : MR];                  // vtol, ginv, |M_i|^2 in registers ...
     T *rowc_s = wk + L::oW;                            // ... or in shared memory [3][MP]
     auto rc_set = [&](int which, int s, T v) {

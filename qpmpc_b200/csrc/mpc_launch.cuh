@@ -50,9 +50,9 @@ size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bo
     return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
 }
 
-template <typename T, int NP, int MR, bool MREG>
-int launch_solve(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR, MREG>;
+template <typename T, int NP, int MR, bool MREG, bool RS>
+int launch_solve_variant(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, MR, MREG, RS>;
     constexpr int IPW = 32 / NP;
     int wpc = env_int("QPMPC_B200_WPC", 8);
     if (wpc < 1) wpc = 1;
@@ -67,7 +67,7 @@ int launch_solve(SolveParams p, cudaStream_t stream) {
     const size_t pad = (size_t)env_int("QPMPC_B200_SMEM_PAD_KB", 0) * 1024;
     if (pad && smem + pad <= 227 * 1024) smem += pad;
     const int ipc = IPW * wpc;
-    auto kern = mpc_solve_kernel<T, NP, MR, MREG>;
+    auto kern = mpc_solve_kernel<T, NP, MR, MREG, RS>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const int grid = (p.batch + ipc - 1) / ipc;
@@ -75,6 +75,20 @@ int launch_solve(SolveParams p, cudaStream_t stream) {
     kern<<<grid, wpc * 32, smem, stream>>>(p);
     count_launch();
     return (int)cudaGetLastError();
+}
+
+// The NP = 16 register-resident kernel exists in two builds: with the per-row
+// constants of the iteration in shared memory (8 fewer live registers: +4 % on
+// iteration-dominated workloads such as config 2) or in registers (smaller
+// shared-memory footprint, hence a larger L1 for the spills of the heavier
+// condensing phase: +10 % on stage-cost problems such as config 3).
+template <typename T, int NP, int MR, bool MREG>
+int launch_solve(SolveParams p, cudaStream_t stream) {
+    if constexpr (NP == 16 && MREG) {
+        const int rs = env_int("QPMPC_B200_ROWS_SMEM", -1);
+        if (rs > 0 || (rs < 0 && !p.has_wx)) return launch_solve_variant<T, NP, MR, MREG, true>(p, stream);
+    }
+    return launch_solve_variant<T, NP, MR, MREG, false>(p, stream);
 }
 
 template <typename T, int NP, int MR>
