@@ -361,8 +361,8 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak,
-                     # dram__bytes_read + write of one launch, ncu --set full (profiles/r01p_solve_ti16_f64.txt)
-                     "traffic": 14210304 if (B, N) == (65536, 16) else None, "peak_source": peak_src,
+                     # dram__bytes_read + write of one launch, ncu --set full (profiles/r01r_solve_ti16_f64.txt)
+                     "traffic": 13774336 if (B, N) == (65536, 16) else None, "peak_source": peak_src,
                      "kernel": "mpc_solve_kernel<double,NP=%d,MR=2>" % (8 if n <= 8 else 16 if n <= 16 else 32)
                      if n <= 32 else "mpc_solve_cta_kernel<double>", "kernel_ms": kernel_ms,
                      "bytes_per_solve": bytes_per_solve,
