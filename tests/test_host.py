@@ -189,6 +189,19 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert lib.qpmpc_b200_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), None) == -3
     d.w_u, d.has_wt, d.w_t = 1e-3, 1, 1.0
     assert lib.qpmpc_b200_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), None) == -1
+    # the other entry points validate before touching a device, too
+    peers, loop = _capi.Peers(), _capi.ClosedLoop()
+    assert lib.qpmpc_b200_solve_scatter(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), None, None) == -1
+    peers.count = 9
+    assert lib.qpmpc_b200_solve_scatter(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs),
+                                        ctypes.byref(peers), None) == -1
+    assert lib.qpmpc_b200_pendulum_closed_loop(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs),
+                                               ctypes.byref(loop), None) == -2  # needs nx = 4, nu = 1
+    assert lib.qpmpc_b200_condense(ctypes.byref(d), ctypes.byref(ops), None, None) == -1
+    assert lib.qpmpc_b200_integrate(ctypes.byref(d), ctypes.byref(ops), None, None, None) == -1
+    assert lib.qpmpc_b200_fp64_peak(0, None) == -1
+    assert b"invalid argument" in lib.qpmpc_b200_strerror(-1)
+    assert lib.qpmpc_b200_max_vars(0) >= 64 and lib.qpmpc_b200_max_rows(0, 64) >= 128  # N = 64 sweep point
 
 
 def test_product_path_fails_loudly_without_cuda():
