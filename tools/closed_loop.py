@@ -20,23 +20,38 @@ ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--cycles", type=int, default=200)
 ap.add_argument("--ltv", action="store_true", help="pass A, B as per-step stacks (LTV code path)")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--graph", action="store_true", help="capture the 2*cycles+1 launches in one CUDA graph")
 a = ap.parse_args()
 w = pendulum_batch(a.batch, seed=1, ltv_model=a.ltv)
 x0 = torch.as_tensor(w["x0"]).cuda()
+v_dev = torch.as_tensor(w["v_target"]).cuda()  # on the device already: the loop is then capturable
 prob = to_batched(w)
 times = []
+graph = None
+if a.graph:
+    # warm-up outside capture (module loading, function attributes), then capture once
+    pendulum_closed_loop(prob, v_dev, 2)
+    torch.cuda.synchronize()
+    prob.x0.copy_(x0)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan, traj, unsolved = pendulum_closed_loop(prob, v_dev, a.cycles)
 for rep in range(a.reps + 1):
     prob.x0.copy_(x0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    plan, traj, unsolved = pendulum_closed_loop(prob, w["v_target"], a.cycles)
+    if graph is not None:
+        graph.replay()
+    else:
+        plan, traj, unsolved = pendulum_closed_loop(prob, v_dev, a.cycles)
     e1.record()
     torch.cuda.synchronize()
     if rep:
         times.append(e0.elapsed_time(e1))
 ms = sum(times) / len(times)
-print(json.dumps({"workload": "wheeled_inverted_pendulum closed loop" + (" (LTV stacks)" if a.ltv else ""),
+print(json.dumps({"workload": "wheeled_inverted_pendulum closed loop" + (" (LTV stacks)" if a.ltv else "")
+                  + (" [CUDA graph]" if a.graph else ""),
                   "batch": a.batch, "cycles": a.cycles, "ms": ms, "ms_per_cycle": ms / a.cycles,
                   "solves_per_s": a.batch * a.cycles / ms * 1e3, "unsolved": int(unsolved.item()),
                   "iters_mean_last_cycle": float(plan.iters.float().mean()),
