@@ -36,6 +36,10 @@
 #ifndef QPMPC_MINB
 #define QPMPC_MINB 4
 #endif
+// single precision needs half the registers for the same arrays: 3 CTAs of 8 warps per SM
+#ifndef QPMPC_MINB_F32
+#define QPMPC_MINB_F32 3
+#endif
 #ifndef QPMPC_SYNC_TAIL
 #define QPMPC_SYNC_TAIL 1
 #endif
@@ -600,7 +604,8 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool MREG, bool RS>  // @phase kernel prologue
-__global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? QPMPC_MINB / 2 : 1) mpc_solve_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : QPMPC_MINB / 2) : 1)
+    mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, MREG, RS>;
     using T2 = typename Pair<T>::type;
     constexpr bool HASJ = !MREG;
