@@ -1,0 +1,75 @@
+"""Property tests (hypothesis) of the CPU oracle: the exact active-set solver
+returns THE minimiser of random strictly convex QPs -- KKT certificates on
+random data -- and the C and NumPy restatements of the condensing agree on
+random problem shapes (ragged operand patterns included)."""
+
+import numpy as np
+import pytest
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+import oracle  # noqa: E402
+from oracle import condense_np  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(1, 12), m=st.integers(0, 20), seed=st.integers(0, 2**31 - 1),
+       feasible=st.booleans())
+def test_active_set_solution_is_a_kkt_point(n, m, seed, feasible):
+    rng = np.random.default_rng(seed)
+    F = rng.standard_normal((n, n))
+    P = F @ F.T + 1e-3 * np.eye(n)
+    q = rng.standard_normal(n)
+    G = rng.standard_normal((m, n))
+    x_in = rng.standard_normal(n)
+    # a point known to satisfy G x <= h makes the QP feasible; otherwise anything goes
+    h = G @ x_in + rng.random(m) if feasible else rng.standard_normal(m)
+    status, x, z, iters = oracle.qp_gi(P, q, G, h)
+    if feasible:
+        assert status == 0
+    if status != 0:
+        return
+    k = oracle.kkt(P, q, G, h, x, z)
+    scale = max(1.0, np.abs(q).max(), np.abs(P).max())
+    assert k[0] <= 1e-8 * scale          # stationarity
+    assert k[1] <= 1e-8 * scale          # primal feasibility
+    assert k[2] == 0.0                   # dual feasibility
+    assert k[3] <= 1e-8 * scale          # complementarity
+    # no feasible descent direction from x towards the unconstrained optimum either
+    if m == 0:
+        assert np.abs(x + np.linalg.solve(P, q)).max() <= 1e-8 * scale
+
+
+@settings(max_examples=40, deadline=None)
+@given(N=st.integers(1, 9), nx=st.integers(1, 6), nu=st.integers(1, 3), nc=st.integers(1, 4),
+       ltv=st.booleans(), with_C=st.booleans(), with_D=st.booleans(), stage=st.booleans(),
+       seed=st.integers(0, 2**31 - 1))
+def test_c_and_numpy_condensing_agree(N, nx, nu, nc, ltv, with_C, with_D, stage, seed):
+    from qpmpc_b200 import MPCProblem
+
+    rng = np.random.default_rng(seed)
+
+    def stack(shape):
+        if ltv:
+            return [rng.standard_normal(shape) for _ in range(N)]
+        return rng.standard_normal(shape)
+
+    A, B = stack((nx, nx)), stack((nx, nu))
+    C = stack((nc, nx)) if with_C else None
+    D = stack((nc, nu)) if with_D else None
+    e = [rng.random(nc) + 1.0 for _ in range(N)] if ltv else rng.random(nc) + 1.0
+    problem = MPCProblem(A, B, C, D, e, N, terminal_cost_weight=0.7,
+                         stage_state_cost_weight=0.3 if stage else None,
+                         stage_input_cost_weight=1e-2, initial_state=rng.standard_normal(nx),
+                         goal_state=rng.standard_normal(nx),
+                         target_states=rng.standard_normal(N * nx))
+    ref = condense_np.condense(problem)
+    arr = lambda op: None if op is None else (np.stack(op) if isinstance(op, list) else np.asarray(op))  # noqa: E731
+    got = oracle.condense(N, nx, nu, nc, arr(A), arr(B), arr(C), arr(D), arr(e),
+                          problem.initial_state, problem.goal_state, problem.target_states,
+                          0.7, 0.3 if stage else None, 1e-2)
+    for key in ("P", "q", "G", "h"):
+        a, b = np.asarray(ref[key], dtype=float), np.asarray(got[key], dtype=float)
+        assert a.shape == b.shape, key
+        assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), key
