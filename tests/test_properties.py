@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 hypothesis = pytest.importorskip("hypothesis")
-from hypothesis import given, settings, strategies as st  # noqa: E402
+from hypothesis import example, given, settings, strategies as st  # noqa: E402
 
 import oracle  # noqa: E402
 from oracle import condense_np  # noqa: E402
@@ -87,6 +87,10 @@ _N_EX = int(os.environ.get("QPMPC_PROP_EXAMPLES", "40"))
        ltv=st.booleans(), with_C=st.booleans(), with_D=st.booleans(),
        cost=st.sampled_from(["terminal", "stage", "both"]), shared=st.booleans(),
        seed=st.integers(0, 2**31 - 1))
+# found by the randomised search: instance 25 is infeasible (an LP confirms it) with 12 active rows
+# in 12 variables; the kernel said so, the oracle of the time "solved" it with |x| ~ 1e13
+@example(N=12, nx=6, nu=1, nc=3, ltv=False, with_C=True, with_D=False, cost="terminal", shared=True,
+         seed=2_147_483_646)
 def test_cuda_path_matches_oracle_on_random_problems(N, nx, nu, nc, ltv, with_C, with_D, cost, shared, seed):
     """Random shapes / operand patterns through the C ABI against the oracle:
     same solved set, |dU|_inf <= 1e-6 (every kernel variant is reachable:
@@ -116,3 +120,44 @@ def test_cuda_path_matches_oracle_on_random_problems(N, nx, nu, nc, ltv, with_C,
     ok = st_ == 0
     if ok.any():
         assert np.abs(U[ok] - ref["U"][ok]).max() <= 1e-6
+
+
+def _lp_min_violation(G, h):
+    """min over x of max_i (G x - h)_i, by linear programming (feasible iff <= 0)."""
+    from scipy.optimize import linprog
+
+    m, n = G.shape
+    res = linprog(np.r_[np.zeros(n), 1.0], A_ub=np.c_[G, -np.ones(m)], b_ub=h,
+                  bounds=[(None, None)] * n + [(-10.0, None)], method="highs")
+    assert res.status == 0
+    return res.fun
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(1, 8), extra=st.integers(1, 12), seed=st.integers(0, 2**31 - 1),
+       shift=st.floats(-0.5, 0.5))
+def test_oracle_feasibility_verdict_agrees_with_an_lp(n, extra, seed, shift):
+    """More rows than variables, many of them nearly binding together: the
+    solver's solved / infeasible verdict is the LP's, and 'solved' comes with a
+    KKT certificate (regression for a near-dependent-normal case the kernels
+    got right and the oracle got wrong)."""
+    rng = np.random.default_rng(seed)
+    m = n + extra
+    F = rng.standard_normal((n, n))
+    P = F @ F.T + 1e-2 * np.eye(n)
+    q = rng.standard_normal(n)
+    G = rng.standard_normal((m, n))
+    G[rng.integers(0, m)] = 0.0  # a row that does not depend on x (k = 0 rows without D)
+    x_in = rng.standard_normal(n)
+    h = G @ x_in + shift + 0.2 * rng.random(m)  # shift < 0: often infeasible
+    status, x, z, _ = oracle.qp_gi(P, q, G, h)
+    worst = _lp_min_violation(G, h)
+    if abs(worst) < 1e-7:
+        return  # on the boundary of feasibility either verdict is defensible
+    if status == 0:
+        assert worst < 0.0
+        k = oracle.kkt(P, q, G, h, x, z)
+        scale = max(1.0, np.abs(q).max(), np.abs(P).max())
+        assert k[0] <= 1e-7 * scale and k[1] <= 1e-7 * scale and k[2] == 0.0 and k[3] <= 1e-7 * scale
+    else:
+        assert status == 2 and worst > 0.0
