@@ -59,7 +59,16 @@ enum {
 };
 enum { QPMPC_B200_VEC_ABSENT = 0, QPMPC_B200_VEC_SHARED = 1, QPMPC_B200_VEC_BATCH = 2 };
 enum { QPMPC_B200_F64 = 0, QPMPC_B200_F32 = 1 };
+/* Solver behind the condensed QP (what qpsolvers.solve_problem's `solver`
+ * string selects in the reference, qpmpc/solve_mpc.py:43):
+ *   ACTIVE_SET  Goldfarb-Idnani dual active set: exact, every shape.
+ *   PDIP        Mehrotra predictor-corrector interior point + active-set
+ *               polish (exact when the polish is accepted), stopped at
+ *               desc.tol: QPMPC_B200_F64, N*nu <= 32 and N*nc <= 128 only, not
+ *               available through qpmpc_b200_solve_scatter
+ *               (QPMPC_B200_EUNSUPPORTED otherwise). */
 enum { QPMPC_B200_ACTIVE_SET = 0, QPMPC_B200_PDIP = 1 };
+enum { QPMPC_B200_FLAG_NO_POLISH = 1 /* PDIP: skip the polish */ };
 
 enum {
     QPMPC_B200_STATUS_SOLVED = 0,
@@ -94,7 +103,7 @@ typedef struct qpmpc_b200_desc {
     int32_t paired;     /* 1: every C_k, D_k, has rows [M; -M] (two-sided
                            bounds); lets the kernel keep one row per pair.
                            0 is always valid. */
-    int32_t reserved;
+    int32_t flags;      /* QPMPC_B200_FLAG_*; 0 is always valid */
 } qpmpc_b200_desc;
 
 /* Inputs of the path (device pointers for the device entry points, host

@@ -15,11 +15,18 @@ with r_d = P u + q + G'z, r_p = G u + s - h, r_c = s z (predictor) or
 s z + ds_a dz_a - sigma mu (corrector).  One step length for primal and dual,
 so r_d and r_p shrink by exactly (1 - alpha).
 
-Polish: rows with z > s are taken as the active set A; the equality QP on A is
-solved by a few proximal multiplier steps that reuse the same factorisation
-code,  (P + G_A' G_A / delta) u+ = -q - G_A'(lam - h_A / delta),
-lam+ = lam + (G_A u+ - h_A) / delta.  The polished point is kept only if it is
-primal feasible and its multipliers are non-negative to tolerance.
+Polish (a primal-dual active-set finish): rows with z > s are taken as the
+active set A; the equality QP on A is solved by a few proximal multiplier steps
+in residual form, which reuse the same factorisation code,
+    r1 = P u + q + G_A' lam,  r2 = G_A u - h_A,
+    (P + G_A' G_A / delta) du = -(r1 + G_A' r2 / delta),  dlam = (r2 + G_A du) / delta
+(the residuals are evaluated exactly, so the ill-conditioning of the proximal
+matrix only slows convergence, it does not limit the accuracy).  The polished
+point is accepted if it is primal feasible, its multipliers are non-negative
+and its stationarity residual is small; otherwise A is updated -- rows with a
+negative multiplier leave, violated rows enter -- and the polish is repeated,
+up to ``polish_rounds`` times.  An accepted point is the exact solution on its
+active set, i.e. what the active-set oracle returns.
 """
 
 import numpy as np
@@ -31,7 +38,7 @@ def _solve(L, b):
 
 
 def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
-               delta=1e-7):
+               delta=1e-7, polish_rounds=4):
     """Solve a batch of QPs.  P [B,n,n], q [B,n], G [B,m,n], h [B,m].
 
     Returns dict(U, z, status, iters): status 0 solved, 1 max_iter, 2 numerical.
@@ -89,11 +96,13 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
         s = s + alpha * ds
         z = z + alpha * dz
     if polish:
-        up, zp, ok = _polish(P, q, G, h, u, s, z, polish_steps, delta)
+        up, zp, ok = _polish(P, q, G, h, u, s, z, polish_steps, delta, polish_rounds)
         ok &= status == 0
         u = np.where(ok[:, None], up, u)
         z = np.where(ok[:, None], zp, z)
-    return dict(U=u, z=z, status=status, iters=iters)
+    else:
+        ok = np.zeros(B, dtype=bool)
+    return dict(U=u, z=z, status=status, iters=iters, polished=ok)
 
 
 def _step(s, z, ds, dz, frac):
@@ -104,22 +113,38 @@ def _step(s, z, ds, dz, frac):
     return np.minimum(1.0, frac * np.minimum(a_s, a_z))
 
 
-def _polish(P, q, G, h, u, s, z, steps, delta):
+def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9):
+    B = q.shape[0]
     act = z > s
-    Wa = act / delta
-    H = P + np.einsum("bmi,bm,bmj->bij", G, Wa, G)
-    L = np.linalg.cholesky(H)
     lam = np.where(act, z, 0.0)
-    up = u
-    for _ in range(steps):
-        rhs = -q - np.einsum("bmn,bm->bn", G, np.where(act, lam - h / delta, 0.0))
-        up = _solve(L, rhs)
+    up = u.copy()
+    u_out, z_out = u.copy(), z.copy()
+    accepted = np.zeros(B, dtype=bool)
+    hscale = np.maximum(1.0, np.abs(h).max(axis=1, initial=0.0))[:, None]
+    qscale = np.maximum(1.0, np.abs(q).max(axis=1))
+    for _ in range(rounds):
+        if accepted.all():
+            break
+        H = P + np.einsum("bmi,bm,bmj->bij", G, act / delta, G)
+        L = np.linalg.cholesky(H)
+        lam = np.where(act, lam, 0.0)
+        for _ in range(steps):
+            r1 = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
+            r2 = np.where(act, np.einsum("bmn,bn->bm", G, up) - h, 0.0)
+            du = _solve(L, -(r1 + np.einsum("bmn,bm->bn", G, r2 / delta)))
+            lam = lam + np.where(act, (r2 + np.einsum("bmn,bn->bm", G, du)) / delta, 0.0)
+            up = up + du
         viol = np.einsum("bmn,bn->bm", G, up) - h
-        lam = np.where(act, lam + viol / delta, 0.0)
-    viol = np.einsum("bmn,bn->bm", G, up) - h
-    hscale = np.maximum(1.0, np.abs(h).max(axis=1))[:, None]
-    zscale = np.maximum(1.0, np.abs(lam).max(axis=1))[:, None]
-    ok = (viol <= 1e-9 * hscale).all(axis=1) & (lam >= -1e-9 * zscale).all(axis=1)
-    r_d = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
-    ok &= np.abs(r_d).max(axis=1) <= 1e-9 * np.maximum(1.0, np.abs(q).max(axis=1))
-    return up, lam, ok
+        zscale = np.maximum(1.0, np.abs(lam).max(axis=1, initial=0.0))[:, None]
+        r_d = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
+        ok = (
+            (viol <= eps * hscale).all(axis=1)
+            & (np.abs(np.where(act, viol, 0.0)) <= eps * hscale).all(axis=1)
+            & (lam >= -eps * zscale).all(axis=1)
+            & (np.abs(r_d).max(axis=1) <= eps * qscale)
+        )
+        new = ok & ~accepted
+        u_out[new], z_out[new] = up[new], lam[new]
+        accepted |= ok
+        act = np.where(act, lam > 0.0, viol > 0.0)
+    return u_out, z_out, accepted

@@ -17,6 +17,7 @@ ABSENT, SHARED_LTI, SHARED_LTV, BATCH_LTI, BATCH_LTV = range(5)
 VEC_ABSENT, VEC_SHARED, VEC_BATCH = range(3)
 F64, F32 = 0, 1
 ACTIVE_SET, PDIP = 0, 1
+FLAG_NO_POLISH = 1  # desc.flags: PDIP without the active-set polish
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NOT_SPD = range(4)
 
 EXPORTS = (
@@ -44,7 +45,7 @@ class Desc(ctypes.Structure):
         ("w_t", ctypes.c_double), ("w_x", ctypes.c_double), ("w_u", ctypes.c_double),
         ("method", ctypes.c_int32), ("max_iter", ctypes.c_int32),
         ("tol", ctypes.c_double),
-        ("paired", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("paired", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
 
 

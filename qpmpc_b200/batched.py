@@ -213,7 +213,8 @@ class BatchedMPCProblem:
 
     # -- C ABI views ----------------------------------------------------------
 
-    def desc(self, method: int = _capi.ACTIVE_SET, max_iter: int = 0, tol: float = 0.0) -> _capi.Desc:
+    def desc(self, method: int = _capi.ACTIVE_SET, max_iter: int = 0, tol: float = 0.0,
+             polish: bool = True) -> _capi.Desc:
         if self.x0 is None:
             raise ProblemDefinitionError("initial state is undefined")  # mpc_qp.py:49-51
         d = _capi.Desc()
@@ -229,6 +230,7 @@ class BatchedMPCProblem:
         d.w_x = float(self.stage_state_cost_weight or 0.0)
         d.w_u = self.stage_input_cost_weight
         d.method, d.max_iter, d.tol = method, int(max_iter), float(tol)
+        d.flags = 0 if polish else _capi.FLAG_NO_POLISH
         return d
 
     def operands(self) -> _capi.Operands:
@@ -385,16 +387,21 @@ def solve_mpc_batch(
     tol: float = 0.0,
     return_multipliers: bool = False,
     out: Optional[torch.Tensor] = None,
+    polish: bool = True,
 ) -> BatchedPlan:
     """Condense and solve every instance of ``problem`` on its CUDA device.
 
+    ``method="active_set"`` (default) is the exact Goldfarb-Idnani kernel;
+    ``method="pdip"`` the Mehrotra interior-point kernel stopped at ``tol``
+    (default 1e-9), followed by an active-set ``polish`` -- the role a
+    ``solver="proxqp"`` / ``"osqp"`` string plays at ``qpmpc/solve_mpc.py:43``.
     Asynchronous on the current CUDA stream, like any torch op.
     """
     lib = _capi.load()
     meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}.get(method)
     if meth is None:
         raise ProblemDefinitionError(f"unknown method {method!r}")
-    desc = problem.desc(meth, max_iter, tol)
+    desc = problem.desc(meth, max_iter, tol, polish)
     B, n, m = problem.batch_size, problem.nb_vars, problem.nb_rows
     with torch.cuda.device(problem.device):
         U = out if out is not None else torch.empty((B, n), dtype=problem.dtype, device=problem.device)

@@ -4,5 +4,7 @@
 
 namespace qpmpc {
 QPMPC_INSTANTIATE_VARIANT(double, 8, 2, true)
+QPMPC_INSTANTIATE_PDIP(8, 2)
 QPMPC_INSTANTIATE_VARIANT(double, 8, 4, true)
+QPMPC_INSTANTIATE_PDIP(8, 4)
 }  // namespace qpmpc

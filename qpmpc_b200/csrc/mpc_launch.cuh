@@ -18,19 +18,23 @@ template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
 int launch_condense(SolveParams p, cudaStream_t stream);
+template <typename T, int NP, int MR>
+int launch_pdip(SolveParams p, int polish, cudaStream_t stream);  // mpc_pdip.cuh
 
 }  // namespace qpmpc
 
 #ifdef QPMPC_INSTANTIATE
 #include "mpc_kernels.cuh"
+#include "mpc_pdip.cuh"
 
 namespace qpmpc {
 
 // Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
 template <typename T>
-size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bool mreg) {
+size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bool mreg, bool dense_g = false) {
     const bool lti = p->op[OP_A].step == 0 && p->op[OP_B].step == 0 && (!p->op[OP_C].ptr || p->op[OP_C].step == 0);
-    p->toeplitz = (lti && nx_in_registers(p->nx) && p->nc > 0 && env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0) ? 1 : 0;
+    p->toeplitz =
+        (!dense_g && lti && nx_in_registers(p->nx) && p->nc > 0 && env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0) ? 1 : 0;
     const TailLay t = tail_layout(fixed_elems, szG, np, p->nx, p->nc, p->n, p->toeplitz != 0, mreg);
     p->gt_off = t.gt_off;
     p->g_off = t.g_off;
@@ -130,9 +134,37 @@ int launch_condense(SolveParams p, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+// Interior-point kernel (desc.method = QPMPC_B200_PDIP): dense G, one work
+// region of PdipLay::fixed + szG (+ generic-condensing scratch) per instance.
+template <typename T, int NP, int MR>
+int launch_pdip(SolveParams p, int polish, cudaStream_t stream) {
+    using L = PdipLay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    int wpc = env_int("QPMPC_B200_PDIP_WPC", 4);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 8) wpc = 8;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, false, true);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_pdip_kernel<T, NP, MR>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p, polish);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 #define QPMPC_INSTANTIATE_VARIANT(T, NP, MR, MREG)                               \
     template int launch_solve<T, NP, MR, MREG>(SolveParams, cudaStream_t);      \
     template int launch_condense<T, NP, MR>(SolveParams, cudaStream_t);
+// the interior-point kernel is double precision only (qpmpc_b200.cu:solve_impl)
+#define QPMPC_INSTANTIATE_PDIP(NP, MR) template int launch_pdip<double, NP, MR>(SolveParams, int, cudaStream_t);
 
 }  // namespace qpmpc
 #endif  // QPMPC_INSTANTIATE

@@ -1,0 +1,540 @@
+// mpc_pdip.cuh -- fused condense + primal-dual interior-point QP kernel
+// (sm_100a): the method BASELINE.json's north star names, behind
+// desc.method = QPMPC_B200_PDIP.  The default method stays the exact dual
+// active set of mpc_kernels.cuh (DESIGN.md section 2 says why); this kernel
+// trades exactness for an iteration count that does not depend on the number
+// of active constraints.
+//
+// Same ownership as the active-set kernel: a group of NP lanes owns one MPC
+// instance, lane l is decision variable l and owns the constraint rows
+// l, l + NP, ... (MR of them); a warp carries 32 / NP instances in lock step.
+//
+//   0  operands staged into shared memory by bulk TMA (stage_inputs)
+//   A  condensing (condense_dispatch, qpmpc/mpc_qp.py:53-105,139-149 of the
+//      reference): G (dense, by columns), h in shared memory, row l of P and
+//      q_l in registers; P is then parked in shared memory
+//   B  Mehrotra predictor-corrector on   min 1/2 u'Pu + q'u  s.t. Gu + s = h,
+//      s, z >= 0 -- what qpsolvers.solve_problem (qpmpc/solve_mpc.py:43) does
+//      in an interior-point backend.  Per iteration: residuals, the reduced
+//      KKT matrix H = P + G' diag(z/s) G (row l per lane, in registers), its
+//      Cholesky factor (columns published in shared memory), and two
+//      forward/backward substitutions by warp shuffles
+//   C  primal-dual active-set polish: rows with z > s form the active set A; a
+//      few proximal multiplier steps in residual form on the equality QP of A
+//      reuse the same build / factor / solve code with W = 1_A / delta; a
+//      point that fails the KKT test corrects A and repeats (<= 4 rounds).
+//      An accepted point is the exact solution, as the active-set kernel
+//      returns it: this is what makes |dU| <= 1e-6 hold at w_u = 1e-6
+//   D  U (coalesced), status, iteration count, multipliers
+//
+// oracle/pdip_np.py is the NumPy statement of phases B and C, line for line.
+//
+// pdip_core() is written against a minimal set of warp primitives
+// (__syncwarp, __shfl_sync, __shfl_xor_sync, __all_sync) so that the same
+// source also compiles for the host: tests/emu/ runs it lane by lane on
+// fibers (QPMPC_HOST_EMU) and checks it against the NumPy model and the exact
+// oracle without a GPU.
+#pragma once
+
+#ifndef QPMPC_HOST_EMU
+#include "mpc_common.cuh"
+#endif
+
+namespace qpmpc {
+
+template <typename T> struct PdipNum;
+template <> struct PdipNum<double> {
+    static constexpr double tol_min = 1e-13;    // below this the residuals are rounding noise
+    static constexpr double delta = 1e-7;       // proximal parameter of the polish
+    static constexpr double polish_eps = 1e-9;  // acceptance test of the polished point
+    static constexpr double step_frac = 0.99;
+    static constexpr int polish_rounds = 4;
+};
+template <> struct PdipNum<float> {
+    static constexpr float tol_min = 1e-6f;
+    static constexpr float delta = 1e-3f;
+    static constexpr float polish_eps = 1e-4f;
+    static constexpr float step_frac = 0.99f;
+    static constexpr int polish_rounds = 4;
+};
+
+// Per-instance shared-memory regions of the interior-point kernel (elements of
+// T); the dense G and the scratch of the generic condensing follow at
+// tail_layout(fixed, szG, ..., toeplitz = false, mreg = false).
+template <typename T, int NP, int MR>
+struct PdipLay {
+    static constexpr int MP = MR * NP;    // padded constraint rows
+    static constexpr int LDG = MP + 1;    // G by columns: Gc[c*LDG + row] (as Lay::LDG)
+    static constexpr int LDL = NP + 2;    // L, P by columns
+    static constexpr int szG = ((NP * LDG + 3) / 4) * 4;
+    static constexpr int szL = ((NP * LDL + 3) / 4) * 4;
+    static constexpr int oH = 0;          // hs[MP]
+    static constexpr int oL = oH + MP;    // Lc (psi exchange buffers during phase A)
+    static constexpr int oP = oL + szL;   // Pc: P by columns (symmetric: column l is row l)
+    static constexpr int oV = oP + szL;   // xs[NP], dv[NP]
+    static constexpr int oW = oV + 2 * NP;  // wv[MP], tv[MP]
+    static constexpr int fixed = oW + 2 * MP;
+    static_assert(8 * NP <= szL, "psi exchange buffers must fit in the L region");
+};
+
+template <typename T, int NP>
+__device__ __forceinline__ T pdip_sum(T v) {
+#pragma unroll
+    for (int off = NP / 2; off > 0; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off, NP);
+    return v;
+}
+template <typename T, int NP>
+__device__ __forceinline__ T pdip_min(T v) {
+#pragma unroll
+    for (int off = NP / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
+    return v;
+}
+template <typename T, int NP>
+__device__ __forceinline__ T pdip_max(T v) {
+#pragma unroll
+    for (int off = NP / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
+    return v;
+}
+
+// Cholesky H = L L' with row l of H in this lane's registers (destroyed).
+// Column c of L is published as Lc[c*LDL + row], 1 / L_cc as dv[c].  Returns
+// false (to every lane of the group) if a pivot is not positive.
+template <typename T, int NP, int LDL>
+__device__ __forceinline__ bool pdip_cholesky(T (&Hrow)[NP], T *Lc, T *dv, int l) {
+    bool spd = true;
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+        const T piv = __shfl_sync(FULL_MASK, Hrow[c], c, NP);
+        spd = spd && (piv > T(0));
+        const T inv = frsqrt_(piv);
+        const T lc = Hrow[c] * inv;
+        Lc[c * LDL + l] = lc;
+        if (l == c) dv[c] = inv;
+        __syncwarp();
+#pragma unroll
+        for (int i = c + 1; i < NP; ++i) Hrow[i] -= lc * Lc[c * LDL + i];
+    }
+    return spd;
+}
+
+// Component l of the solution of L L' y = w (w_l per lane): lane c finalises
+// component c and broadcasts it, forwards then backwards.
+template <typename T, int NP, int LDL>
+__device__ __forceinline__ T pdip_solve(const T *Lc, const T *dv, T w, int l) {
+    const T dinv = dv[l];
+    T y = T(0);
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+        const T yc = __shfl_sync(FULL_MASK, w * dinv, c, NP);
+        if (l == c) y = yc;
+        if (l > c) w -= Lc[c * LDL + l] * yc;
+    }
+    T s2 = y, x = T(0);
+#pragma unroll
+    for (int c = NP - 1; c >= 0; --c) {
+        const T xc = __shfl_sync(FULL_MASK, s2 * dinv, c, NP);
+        if (l == c) x = xc;
+        if (l < c) s2 -= Lc[l * LDL + c] * xc;
+    }
+    return x;
+}
+
+// Row l of H = P + G' diag(wv) G into Hrow and, in the same pass over the
+// rows, g = sum_row G[row, l] tv[row].
+template <typename T, int NP, int LDG, int LDL>
+__device__ __forceinline__ T pdip_build(T (&Hrow)[NP], const T *Pc, const T *Gc, const T *wv, const T *tv, int m,
+                                        int l) {
+#pragma unroll
+    for (int c = 0; c < NP; ++c) Hrow[c] = Pc[c * LDL + l];
+    T g = T(0);
+    const T *gl = Gc + l * LDG;
+    for (int row = 0; row < m; ++row) {
+        const T glr = gl[row];
+        const T a = glr * wv[row];
+        g += glr * tv[row];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) Hrow[c] += a * Gc[c * LDG + row];
+    }
+    return g;
+}
+
+// sum_row G[row, l] v[row]
+template <typename T, int LDG>
+__device__ __forceinline__ T pdip_gt_dot(const T *Gc, const T *v, int m, int l) {
+    const T *gl = Gc + l * LDG;
+    T g0 = T(0), g1 = T(0);
+    int row = 0;
+    for (; row + 1 < m; row += 2) {
+        g0 += gl[row] * v[row];
+        g1 += gl[row + 1] * v[row + 1];
+    }
+    if (row < m) g0 += gl[row] * v[row];
+    return g0 + g1;
+}
+
+// G[row, :] . xs for the owned rows (0 for padding rows).
+template <typename T, int NP, int MR, int LDG>
+__device__ __forceinline__ void pdip_g_dot(const T *Gc, const T *xs, const bool (&rowvalid)[MR], int l,
+                                           T (&out)[MR]) {
+#pragma unroll
+    for (int s = 0; s < MR; ++s) {
+        T a0 = T(0), a1 = T(0);
+        if (rowvalid[s]) {
+            const T *gr = Gc + l + s * NP;
+#pragma unroll
+            for (int c = 0; c < NP; c += 2) {
+                a0 += gr[c * LDG] * xs[c];
+                a1 += gr[(c + 1) * LDG] * xs[c + 1];
+            }
+        }
+        out[s] = a0 + a1;
+    }
+}
+
+// Largest alpha in (0, 1] that keeps s + alpha ds and z + alpha dz positive,
+// damped by frac (oracle/pdip_np.py:_step).
+template <typename T, int NP, int MR>
+__device__ __forceinline__ T pdip_step(const T (&sl)[MR], const T (&z)[MR], const T (&ds)[MR], const T (&dz)[MR],
+                                       const bool (&rowvalid)[MR], T frac) {
+    T a = Num<T>::inf();
+#pragma unroll
+    for (int s = 0; s < MR; ++s) {
+        if (rowvalid[s] && ds[s] < T(0)) a = fmin(a, -sl[s] / ds[s]);
+        if (rowvalid[s] && dz[s] < T(0)) a = fmin(a, -z[s] / dz[s]);
+    }
+    a = pdip_min<T, NP>(a);
+    return fmin(T(1), frac * a);
+}
+
+// ---------------------------------------------------------------------------
+// Phases B and C for one instance (all NP lanes of the group call this in
+// lock step; the other groups of the warp run their own instances and the
+// loop ends when every group of the warp is done).
+//   in : Pc, Gc, hs in shared memory, qj = q_l; n, m real sizes (padding
+//        variables have P = identity, q = 0, zero columns of G)
+//   out: x (component l of U), z (multipliers of the owned rows), status,
+//        iterations
+// Scratch: Lc [NP*LDL], xs [NP], dv [NP], wv [MP], tv [MP].
+// ---------------------------------------------------------------------------
+template <typename T, int NP, int MR>
+__device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const T *hs, T *Lc, T *xs, T *dv, T *wv,
+                                          T *tv, int m, int l, bool valid, int max_iter, T tol, bool polish,
+                                          T &x_out, T (&z_out)[MR], int &st_out, int &it_out) {
+    using L = PdipLay<T, NP, MR>;
+    constexpr int LDG = L::LDG, LDL = L::LDL;
+    bool rowvalid[MR];
+    T hrow[MR], sl[MR], z[MR], rp[MR], W[MR], ds[MR], dz[MR], rc[MR], gx[MR];
+    T habs = T(0);
+#pragma unroll
+    for (int s = 0; s < MR; ++s) {
+        const int row = l + s * NP;
+        rowvalid[s] = row < m;
+        hrow[s] = rowvalid[s] ? hs[row] : T(1);
+        // start (pdip_np.py): u = 0, s = max(h, 1), z = 1
+        sl[s] = rowvalid[s] ? fmax(hrow[s], T(1)) : T(1);
+        z[s] = rowvalid[s] ? T(1) : T(0);
+        if (rowvalid[s]) habs = fmax(habs, abs_(hrow[s]));
+        rp[s] = W[s] = ds[s] = dz[s] = rc[s] = gx[s] = T(0);
+    }
+    const T hscale = fmax(T(1), pdip_max<T, NP>(habs));
+    const T qscale = fmax(T(1), pdip_max<T, NP>(abs_(qj)));
+    const T minv = m > 0 ? T(1) / (T)m : T(0);
+    tol = fmax(tol, PdipNum<T>::tol_min);
+    T x = T(0);
+    int st = 1, it = 0;
+    bool done = !valid;
+    T Hrow[NP];
+
+    while (true) {
+        // residuals: r_d = P u + q + G'z, r_p = G u + s - h, mu = s'z / m
+        xs[l] = x;
+#pragma unroll
+        for (int s = 0; s < MR; ++s)
+            if (rowvalid[s]) tv[l + s * NP] = z[s];
+        __syncwarp();
+        T px0 = T(0), px1 = T(0);
+#pragma unroll
+        for (int c = 0; c < NP; c += 2) {
+            px0 += Pc[c * LDL + l] * xs[c];
+            px1 += Pc[(c + 1) * LDL + l] * xs[c + 1];
+        }
+        const T rd = (px0 + px1) + qj + pdip_gt_dot<T, LDG>(Gc, tv, m, l);
+        pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+        T comp = T(0), rpabs = T(0);
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            rp[s] = rowvalid[s] ? gx[s] + sl[s] - hrow[s] : T(0);
+            rpabs = fmax(rpabs, abs_(rp[s]));
+            if (rowvalid[s]) comp += sl[s] * z[s];
+        }
+        const T mu = pdip_sum<T, NP>(comp) * minv;
+        const T rdmax = pdip_max<T, NP>(abs_(rd));
+        const T rpmax = pdip_max<T, NP>(rpabs);
+        const bool conv = rdmax <= tol * qscale && rpmax <= tol * hscale && mu <= tol;
+        if (!done && conv) {
+            st = 0;
+            done = true;
+        }
+        if (!done && it >= max_iter) done = true;  // st stays 1 (max_iter)
+        if (__all_sync(FULL_MASK, done)) break;
+        if (!done) ++it;
+        __syncwarp();  // every lane has read z from tv
+
+        // H = P + G'WG, W = z / s; predictor right-hand side -r_d - G'(W r_p - z)
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            W[s] = rowvalid[s] ? z[s] / sl[s] : T(0);
+            if (rowvalid[s]) {
+                wv[l + s * NP] = W[s];
+                tv[l + s * NP] = W[s] * rp[s] - z[s];
+            }
+        }
+        __syncwarp();
+        T rhs = -rd - pdip_build<T, NP, LDG, LDL>(Hrow, Pc, Gc, wv, tv, m, l);
+        const bool spd = pdip_cholesky<T, NP, LDL>(Hrow, Lc, dv, l);
+        __syncwarp();
+        if (!done && !spd) {
+            st = 3;  // numerical failure: H lost positive definiteness
+            done = true;
+        }
+        T du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+        xs[l] = du;
+        __syncwarp();
+        pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            ds[s] = rowvalid[s] ? -rp[s] - gx[s] : T(0);
+            dz[s] = rowvalid[s] ? -z[s] - W[s] * ds[s] : T(0);  // -(s z + z ds) / s
+        }
+        const T a_aff = pdip_step<T, NP, MR>(sl, z, ds, dz, rowvalid, T(1));
+        T comp_aff = T(0);
+#pragma unroll
+        for (int s = 0; s < MR; ++s)
+            if (rowvalid[s]) comp_aff += (sl[s] + a_aff * ds[s]) * (z[s] + a_aff * dz[s]);
+        const T mu_aff = pdip_sum<T, NP>(comp_aff) * minv;
+        const T ratio = mu > T(0) ? mu_aff / mu : T(0);
+        const T sigmu = ratio * ratio * ratio * mu;
+
+        // corrector: r_c = s z + ds_a dz_a - sigma mu
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            rc[s] = rowvalid[s] ? sl[s] * z[s] + ds[s] * dz[s] - sigmu : T(0);
+            if (rowvalid[s]) tv[l + s * NP] = W[s] * rp[s] - rc[s] / sl[s];
+        }
+        __syncwarp();
+        rhs = -rd - pdip_gt_dot<T, LDG>(Gc, tv, m, l);
+        du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+        xs[l] = du;
+        __syncwarp();
+        pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            ds[s] = rowvalid[s] ? -rp[s] - gx[s] : T(0);
+            dz[s] = rowvalid[s] ? -(rc[s] + z[s] * ds[s]) / sl[s] : T(0);
+        }
+        const T alpha = pdip_step<T, NP, MR>(sl, z, ds, dz, rowvalid, PdipNum<T>::step_frac);
+        if (!done) {
+            x += alpha * du;
+#pragma unroll
+            for (int s = 0; s < MR; ++s) {
+                sl[s] += alpha * ds[s];
+                z[s] += alpha * dz[s];
+            }
+        }
+        __syncwarp();  // xs, tv are rewritten at the top of the loop
+    }
+
+    // ---- phase C: primal-dual active-set polish (pdip_np.py:_polish) --------
+    // Proximal multiplier steps in residual form on the equality QP of the
+    // guessed active set A; an accepted point is the exact solution on A.  A
+    // rejected guess is corrected (negative multipliers leave, violated rows
+    // enter) and the polish repeated.
+    if (__any_sync(FULL_MASK, polish && st == 0 && m > 0)) {
+        const T delta = PdipNum<T>::delta, dinv = T(1) / delta, eps = PdipNum<T>::polish_eps;
+        bool act[MR];
+        T lam[MR], r2[MR];
+        bool accepted = false;
+        T up = x;
+#pragma unroll
+        for (int s = 0; s < MR; ++s) {
+            act[s] = rowvalid[s] && z[s] > sl[s];
+            lam[s] = act[s] ? z[s] : T(0);
+            r2[s] = T(0);
+        }
+        for (int round = 0; round < PdipNum<T>::polish_rounds; ++round) {
+            const bool need = polish && st == 0 && m > 0 && !accepted;
+            if (!__any_sync(FULL_MASK, need)) break;
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < MR; ++s) {
+                lam[s] = act[s] ? lam[s] : T(0);
+                if (rowvalid[s]) {
+                    wv[l + s * NP] = act[s] ? dinv : T(0);
+                    tv[l + s * NP] = T(0);
+                }
+            }
+            __syncwarp();
+            pdip_build<T, NP, LDG, LDL>(Hrow, Pc, Gc, wv, tv, m, l);
+            const bool spd = pdip_cholesky<T, NP, LDL>(Hrow, Lc, dv, l);
+            __syncwarp();
+            T rd = T(0);
+            // steps 0 .. 2 move (up, lam); the last pass only evaluates the residuals
+            for (int step = 0; step <= 3; ++step) {
+                xs[l] = up;
+#pragma unroll
+                for (int s = 0; s < MR; ++s)
+                    if (rowvalid[s]) tv[l + s * NP] = lam[s];
+                __syncwarp();
+                T px0 = T(0), px1 = T(0);
+#pragma unroll
+                for (int c = 0; c < NP; c += 2) {
+                    px0 += Pc[c * LDL + l] * xs[c];
+                    px1 += Pc[(c + 1) * LDL + l] * xs[c + 1];
+                }
+                rd = (px0 + px1) + qj + pdip_gt_dot<T, LDG>(Gc, tv, m, l);  // r1
+                pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+#pragma unroll
+                for (int s = 0; s < MR; ++s) gx[s] = rowvalid[s] ? gx[s] - hrow[s] : T(0);  // G up - h
+                __syncwarp();
+                if (step == 3) break;
+#pragma unroll
+                for (int s = 0; s < MR; ++s) {
+                    r2[s] = act[s] ? gx[s] : T(0);
+                    if (rowvalid[s]) tv[l + s * NP] = r2[s] * dinv;
+                }
+                __syncwarp();
+                const T rhs = -(rd + pdip_gt_dot<T, LDG>(Gc, tv, m, l));
+                const T du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+                __syncwarp();
+                xs[l] = du;
+                __syncwarp();
+                pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+#pragma unroll
+                for (int s = 0; s < MR; ++s) lam[s] += act[s] ? (r2[s] + gx[s]) * dinv : T(0);
+                up += du;
+                __syncwarp();
+            }
+            // accept a primal feasible point with non-negative multipliers, zero
+            // residual on A and a small stationarity residual
+            T worst_viol = T(0), worst_act = T(0), worst_neg = T(0), zmax = T(0);
+#pragma unroll
+            for (int s = 0; s < MR; ++s) {
+                if (rowvalid[s]) {
+                    worst_viol = fmax(worst_viol, gx[s]);
+                    if (act[s]) worst_act = fmax(worst_act, abs_(gx[s]));
+                    worst_neg = fmax(worst_neg, -lam[s]);
+                    zmax = fmax(zmax, abs_(lam[s]));
+                }
+            }
+            const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
+            const bool ok = spd && pdip_max<T, NP>(worst_viol) <= eps * hscale &&
+                            pdip_max<T, NP>(worst_act) <= eps * hscale &&
+                            pdip_max<T, NP>(worst_neg) <= eps * zscale &&
+                            pdip_max<T, NP>(abs_(rd)) <= eps * qscale;
+            if (need && ok) {
+                accepted = true;
+                x = up;
+#pragma unroll
+                for (int s = 0; s < MR; ++s) z[s] = lam[s];
+            }
+#pragma unroll
+            for (int s = 0; s < MR; ++s) act[s] = rowvalid[s] && (act[s] ? lam[s] > T(0) : gx[s] > T(0));
+        }
+        __syncwarp();
+    }
+    x_out = x;
+#pragma unroll
+    for (int s = 0; s < MR; ++s) z_out[s] = z[s];
+    st_out = st;
+    it_out = it;
+}
+
+}  // namespace qpmpc
+
+#ifndef QPMPC_HOST_EMU
+#include "mpc_kernels.cuh"
+
+namespace qpmpc {
+
+// ---------------------------------------------------------------------------
+// The fused kernel: stage, condense, interior point, outputs.
+// ---------------------------------------------------------------------------
+template <typename T, int NP, int MR>  // @phase pdip kernel
+__global__ void __launch_bounds__(256, 1) mpc_pdip_kernel(const SolveParams p, int polish) {
+    using L = PdipLay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *work = reinterpret_cast<T *>(smem_raw + 16);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int ipc = IPW * wpc;
+    const int sub = lane / NP, l = lane % NP;
+    const int iic = warp * IPW + sub;
+    const int inst0 = blockIdx.x * ipc;
+    const int cnt = min(ipc, p.batch - inst0);
+    const long long inst = (long long)inst0 + iic;
+    const bool valid = iic < cnt;
+    const int n = p.n, m = p.m;
+
+    T *inbase = work + (size_t)ipc * p.inst_stride;
+    stage_inputs<T>(p, inbase, inst0, cnt, bar);
+
+    T *wk = work + (size_t)iic * p.inst_stride;
+    T *Gc = wk + p.g_off;
+    T *hs = wk + L::oH;
+    T *Lc = wk + L::oL;
+    T *Pc = wk + L::oP;
+    T *xs = wk + L::oV;
+    T *dv = xs + NP;
+    T *wv = wk + L::oW;
+    T *tv = wv + L::MP;
+
+    const T *in[OP_COUNT];
+#pragma unroll
+    for (int o = 0; o < OP_COUNT; ++o) {
+        const OperandView &v = p.op[o];
+        in[o] = v.ptr ? inbase + v.smem_off + (v.per_instance ? (valid ? iic : 0) * v.sz : 0) : nullptr;
+    }
+
+    // phase A: dense G (p.toeplitz = 0), h, row l of P, q_l
+    T qj;
+    {
+        T Prow[NP];
+        condense_dispatch<T, NP, MR, false>(p, in, Gc, static_cast<T *>(nullptr), hs, Lc, Gc, wk + p.scr_off, l,
+                                            Prow, qj, inst, valid);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) Pc[c * L::LDL + l] = Prow[c];  // P is symmetric
+    }
+    __syncwarp();
+
+    T x, z[MR];
+    int st, it;
+    pdip_core<T, NP, MR>(Pc, qj, Gc, hs, Lc, xs, dv, wv, tv, m, l, valid, p.max_iter, (T)p.tol, polish != 0, x, z, st,
+                         it);
+
+    // phase D: outputs
+    {
+        const unsigned segmask = (NP == 32) ? FULL_MASK : (((1u << (NP & 31)) - 1u) << (sub * NP));
+        const unsigned nonfinite = __ballot_sync(FULL_MASK, !(abs_(x) < Num<T>::inf())) & segmask;
+        if (st == 0 && nonfinite) st = 3;
+    }
+    if (valid) {
+        const T xo = (st == 0) ? x : Num<T>::nan();
+        if (l < n && p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;
+        if (l == 0) {
+            if (p.status) p.status[inst] = st;
+            if (p.iters) p.iters[inst] = it;
+        }
+        if (p.Z) {
+            T *Zb = static_cast<T *>(p.Z) + (size_t)inst * m;
+#pragma unroll
+            for (int s = 0; s < MR; ++s)
+                if (l + s * NP < m) Zb[l + s * NP] = (st == 0) ? z[s] : T(0);
+        }
+    }
+}
+
+}  // namespace qpmpc
+#endif  // QPMPC_HOST_EMU

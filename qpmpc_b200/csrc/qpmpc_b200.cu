@@ -168,6 +168,16 @@ int dispatch_solve(const SolveParams &p, const Variant &v, cudaStream_t s) {
     return QPMPC_B200_ESHAPE;
 }
 
+int dispatch_pdip(const SolveParams &p, const Variant &v, int polish, cudaStream_t s) {
+    if (v.np == 8 && v.mr == 2) return launch_pdip<double, 8, 2>(p, polish, s);
+    if (v.np == 8 && v.mr == 4) return launch_pdip<double, 8, 4>(p, polish, s);
+    if (v.np == 16 && v.mr == 2) return launch_pdip<double, 16, 2>(p, polish, s);
+    if (v.np == 16 && v.mr == 4) return launch_pdip<double, 16, 4>(p, polish, s);
+    if (v.np == 32 && v.mr == 2) return launch_pdip<double, 32, 2>(p, polish, s);
+    if (v.np == 32 && v.mr == 4) return launch_pdip<double, 32, 4>(p, polish, s);
+    return QPMPC_B200_ESHAPE;
+}
+
 template <typename T>
 int dispatch_condense(const SolveParams &p, const Variant &v, cudaStream_t s) {
     if (v.np == 8 && v.mr == 2) return launch_condense<T, 8, 2>(p, s);
@@ -298,7 +308,7 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
     if (!out) return QPMPC_B200_EINVAL;
     if (!peers && (!out->U || !out->status)) return QPMPC_B200_EINVAL;
     if (peers && (peers->count < 1 || peers->count > 8 || peers->row_offset < 0)) return QPMPC_B200_EINVAL;
-    if (d->method != QPMPC_B200_ACTIVE_SET) return QPMPC_B200_EUNSUPPORTED;
+    if (d->method != QPMPC_B200_ACTIVE_SET && d->method != QPMPC_B200_PDIP) return QPMPC_B200_EINVAL;
     if (d->batch == 0) return 0;
     SolveParams p;
     fill_params(d, in, &p);
@@ -317,6 +327,16 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
     }
     Variant v;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d->method == QPMPC_B200_PDIP) {
+        // Interior point (mpc_pdip.cuh): warp kernel only (n <= 32, m <= 128), no fused
+        // gather, double precision only -- in single precision the iteration stalls
+        // above the engine's fp32 bar on 7-15 % of the humanoid instances (emulator
+        // measurement, tests/emu), so it is refused rather than offered.
+        if (peers || d->dtype != QPMPC_B200_F64 || !pick_variant(p.n, p.m, &v)) return QPMPC_B200_EUNSUPPORTED;
+        p.max_iter = d->max_iter > 0 ? d->max_iter : 50;
+        const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
+        return dispatch_pdip(p, v, polish, s);
+    }
     if (use_cta(p.n, p.m, &v))
         return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);
