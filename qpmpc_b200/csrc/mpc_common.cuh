@@ -2,12 +2,19 @@
 // helpers shared by the kernels of the batched MPC engine (sm_100a only).
 #pragma once
 
+// QPMPC_HOST_EMU: the translation unit is a host build for the fiber warp
+// emulator (tests/emu/): the CUDA surface comes from tests/emu/warp_emu.h,
+// included first, and the inline-PTX helpers below get host bodies.
+#ifndef QPMPC_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace qpmpc {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+
+int env_int(const char *name, int dflt);  // integer environment knob (qpmpc_b200.cu)
 
 // Operand slots in the staged-input table.
 enum { OP_A = 0, OP_B, OP_C, OP_D, OP_E, OP_X0, OP_GOAL, OP_TGT, OP_COUNT };
@@ -65,15 +72,22 @@ __device__ __forceinline__ float sqrt_(float v) { return sqrtf(v); }
 // subnormal / infinity handling the solver never needs; zero, subnormal and
 // negative arguments give inf / NaN, which the callers test for.
 __device__ __forceinline__ double rcp_(double v) {
+#ifdef QPMPC_HOST_EMU
+    return 1.0 / v;
+#else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
     double e = fma(-v, r, 1.0);
     r = fma(r, e, r);
     e = fma(-v, r, 1.0);
     return fma(r, e, r);
+#endif
 }
 __device__ __forceinline__ float rcp_(float v) { return __frcp_rn(v); }
 __device__ __forceinline__ double frsqrt_(double v) {
+#ifdef QPMPC_HOST_EMU
+    return 1.0 / sqrt(v);
+#else
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
     const double h = 0.5 * v;
@@ -81,6 +95,7 @@ __device__ __forceinline__ double frsqrt_(double v) {
     y = fma(y, e, y);
     e = fma(-h * y, y, 0.5);
     return fma(y, e, y);
+#endif
 }
 __device__ __forceinline__ float frsqrt_(float v) { return rsqrtf(v); }
 
@@ -121,6 +136,16 @@ template <> struct Num<float> {
     static constexpr float dep_eps = 1e-10f;
 };
 
+#ifdef QPMPC_HOST_EMU
+// ---- host stand-ins: the copy happens at issue time, the barrier is a no-op --
+__device__ __forceinline__ void mbar_init(uint64_t *, unsigned) {}
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(uint64_t *, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *) {
+    memcpy(dst, src, bytes);
+}
+#else
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -160,5 +185,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+#endif  // QPMPC_HOST_EMU
 
 }  // namespace qpmpc

@@ -1258,4 +1258,33 @@ __global__ void __launch_bounds__(128) mpc_condense_kernel(const SolveParams p) 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Host side of the layout (launch wrappers in mpc_launch.cuh, and the host
+// emulator build in tests/emu/).
+// ---------------------------------------------------------------------------
+// Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
+template <typename T>
+size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bool mreg, bool dense_g = false) {
+    const bool lti = p->op[OP_A].step == 0 && p->op[OP_B].step == 0 && (!p->op[OP_C].ptr || p->op[OP_C].step == 0);
+    p->toeplitz =
+        (!dense_g && lti && nx_in_registers(p->nx) && p->nc > 0 && env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0) ? 1 : 0;
+    const TailLay t = tail_layout(fixed_elems, szG, np, p->nx, p->nc, p->n, p->toeplitz != 0, mreg);
+    p->gt_off = t.gt_off;
+    p->g_off = t.g_off;
+    p->scr_off = t.scr_off;
+    p->inst_stride = t.total;
+    int off = 0;
+    p->present_mask = 0;
+    for (int o = 0; o < OP_COUNT; ++o) {
+        OperandView &v = p->op[o];
+        if (!v.ptr) continue;
+        p->present_mask |= 1 << o;
+        v.smem_off = off;
+        int elems = v.sz * (v.per_instance ? ipc : 1);
+        off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
+    }
+    p->input_elems = off;
+    return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
+}
+
 }  // namespace qpmpc

@@ -12,7 +12,6 @@
 namespace qpmpc {
 
 void count_launch();                        // qpmpc_b200.cu
-int env_int(const char *name, int dflt);    // qpmpc_b200.cu
 
 template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream);
@@ -28,31 +27,6 @@ int launch_pdip(SolveParams p, int polish, cudaStream_t stream);  // mpc_pdip.cu
 #include "mpc_pdip.cuh"
 
 namespace qpmpc {
-
-// Shared-memory geometry: [16 B mbarrier][ipc work regions][CTA input region].
-template <typename T>
-size_t layout_smem(SolveParams *p, int fixed_elems, int szG, int np, int ipc, bool mreg, bool dense_g = false) {
-    const bool lti = p->op[OP_A].step == 0 && p->op[OP_B].step == 0 && (!p->op[OP_C].ptr || p->op[OP_C].step == 0);
-    p->toeplitz =
-        (!dense_g && lti && nx_in_registers(p->nx) && p->nc > 0 && env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0) ? 1 : 0;
-    const TailLay t = tail_layout(fixed_elems, szG, np, p->nx, p->nc, p->n, p->toeplitz != 0, mreg);
-    p->gt_off = t.gt_off;
-    p->g_off = t.g_off;
-    p->scr_off = t.scr_off;
-    p->inst_stride = t.total;
-    int off = 0;
-    p->present_mask = 0;
-    for (int o = 0; o < OP_COUNT; ++o) {
-        OperandView &v = p->op[o];
-        if (!v.ptr) continue;
-        p->present_mask |= 1 << o;
-        v.smem_off = off;
-        int elems = v.sz * (v.per_instance ? ipc : 1);
-        off += (elems + 3) / 4 * 4;  // keep every region 16-byte aligned
-    }
-    p->input_elems = off;
-    return 16 + ((size_t)ipc * p->inst_stride + off) * sizeof(T);
-}
 
 template <typename T, int NP, int MR, bool MREG, bool RS>
 int launch_solve_variant(SolveParams p, cudaStream_t stream) {

@@ -29,16 +29,12 @@
 //
 // oracle/pdip_np.py is the NumPy statement of phases B and C, line for line.
 //
-// pdip_core() is written against a minimal set of warp primitives
-// (__syncwarp, __shfl_sync, __shfl_xor_sync, __all_sync) so that the same
-// source also compiles for the host: tests/emu/ runs it lane by lane on
-// fibers (QPMPC_HOST_EMU) and checks it against the NumPy model and the exact
-// oracle without a GPU.
+// The same source also compiles for the host: tests/emu/ runs it thread by
+// thread on fibers (QPMPC_HOST_EMU) and checks it against the NumPy model and
+// the exact oracle without a GPU.
 #pragma once
 
-#ifndef QPMPC_HOST_EMU
 #include "mpc_common.cuh"
-#endif
 
 namespace qpmpc {
 
@@ -451,7 +447,6 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
 
 }  // namespace qpmpc
 
-#ifndef QPMPC_HOST_EMU
 #include "mpc_kernels.cuh"
 
 namespace qpmpc {
@@ -537,4 +532,3 @@ __global__ void __launch_bounds__(256, 1) mpc_pdip_kernel(const SolveParams p, i
 }
 
 }  // namespace qpmpc
-#endif  // QPMPC_HOST_EMU

@@ -1,0 +1,123 @@
+"""Host emulator of the engine's warp kernels.  TEST INFRASTRUCTURE ONLY.
+
+``kernel_emu.cpp`` compiles the DEVICE SOURCE (``qpmpc_b200/csrc/mpc_kernels.cuh``,
+``mpc_pdip.cuh``) for the host against ``warp_emu.h`` (one fiber per CUDA
+thread) and drives it with the product's own host-side parameter code
+(``mpc_host_params.h``, ``layout_smem``).  This module builds the library on
+demand and wraps its entry points; ``tests/test_kernel_emu.py`` and
+``tests/test_pdip_emu.py`` compare the results with the oracle.  Nothing under
+``qpmpc_b200/`` imports this, nothing here is shipped or timed.
+"""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB_PATH = os.path.join(HERE, "libkernel_emu.so")
+_vp = ctypes.c_void_p
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_lib = None
+
+
+def load():
+    """Build (if stale) and load ``libkernel_emu.so``."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    csrc = os.path.join(ROOT, "qpmpc_b200", "csrc")
+    deps = [os.path.join(HERE, "kernel_emu.cpp"), os.path.join(HERE, "warp_emu.h"),
+            os.path.join(ROOT, "include", "qpmpc_b200.h")]
+    deps += [os.path.join(csrc, f) for f in ("mpc_common.cuh", "mpc_kernels.cuh", "mpc_pdip.cuh",
+                                             "mpc_host_params.h")]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DQPMPC_HOST_EMU",
+                        "-Wno-unknown-pragmas", f"-I{ROOT}", "-o", LIB_PATH, deps[0]], check=True)
+    _lib = ctypes.CDLL(LIB_PATH)
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def describe(w, method=0, max_iter=0, tol=0.0, flags=0):
+    """(desc, operands, keep-alive arrays) of a workload dict, host pointers:
+    the structs of include/qpmpc_b200.h filled the way BatchedMPCProblem fills them."""
+    from qpmpc_b200 import _capi
+    from qpmpc_b200.workloads import operand_layout
+
+    d, keep = _capi.Desc(), {}
+    d.batch, d.N, d.nx, d.nu, d.nc = w["batch"], w["N"], w["nx"], w["nu"], w["nc"]
+    d.dtype = 0
+    for name in ("A", "B", "C", "D", "e"):
+        arr, mode = w[name], 0
+        if arr is not None:
+            mode = {(False, False): 1, (False, True): 2, (True, False): 3, (True, True): 4}[operand_layout(w, name)]
+            keep[name] = np.ascontiguousarray(arr, dtype=np.float64)
+        setattr(d, "mode_" + name, mode)
+    for name in ("x0", "goal", "targets"):
+        arr, mode = w[name], 0
+        if arr is not None:
+            mode = 2 if arr.ndim == 2 else 1
+            keep[name] = np.ascontiguousarray(arr, dtype=np.float64)
+        setattr(d, "mode_" + name, mode)
+    d.has_wt, d.has_wx = w["w_t"] is not None, w["w_x"] is not None
+    d.w_t, d.w_x, d.w_u = float(w["w_t"] or 0.0), float(w["w_x"] or 0.0), w["w_u"]
+    d.method, d.max_iter, d.tol, d.flags = method, max_iter, tol, flags
+    ops = _capi.Operands(*[_ptr(keep.get(k)) for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets")])
+    return d, ops, keep
+
+
+def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, descending=False):
+    """qpmpc_b200_solve on the emulator: mpc_solve_kernel / mpc_pdip_kernel."""
+    from qpmpc_b200 import _capi
+
+    lib = load()
+    meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}[method]
+    d, ops, keep = describe(w, meth, max_iter, tol, 0 if polish else _capi.FLAG_NO_POLISH)
+    B, n, m = w["batch"], w["N"] * w["nu"], w["N"] * w["nc"]
+    U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
+    st, it = np.full(B, -1, np.int32), np.zeros(B, np.int32)
+    outs = _capi.Outputs(_ptr(U), _ptr(st), _ptr(it), _ptr(Z))
+    lib.emu_set_lane_order(int(descending))
+    before = lib.emu_smem_overruns()
+    rc = lib.emu_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), wpc)
+    lib.emu_set_lane_order(0)
+    assert lib.emu_smem_overruns() == before, "a CTA wrote past its shared-memory request"
+    return dict(rc=rc, U=U, status=st, iters=it, z=Z[:, :m])
+
+
+def condense(w, fields=("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")):
+    """qpmpc_b200_condense on the emulator: mpc_condense_kernel."""
+    from qpmpc_b200 import _capi
+
+    lib = load()
+    d, ops, keep = describe(w)
+    B, N, nx, n, m = w["batch"], w["N"], w["nx"], w["N"] * w["nu"], w["N"] * w["nc"]
+    shapes = dict(P=(B, n, n), q=(B, n), G=(B, m, n), h=(B, m), Phi=(B, N * nx, nx), Psi=(B, N * nx, n),
+                  phi_last=(B, nx, nx), psi_last=(B, nx, n))
+    out = {k: np.full(shapes[k], np.nan) for k in fields}
+    qf = _capi.QPFields(*[_ptr(out.get(k)) for k in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")])
+    rc = lib.emu_condense(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(qf))
+    assert rc == 0, rc
+    return out
+
+
+def pdip_core(P, q, G, h, np_, mr, dtype=0, max_iter=50, tol=1e-9, polish=True):
+    """pdip_core() on explicit QPs: one emulated warp, up to 32 // np_ QPs side by side."""
+    lib = load()
+    P, q, G, h = (np.ascontiguousarray(a, dtype=np.float64) for a in (P, q, G, h))
+    B, m, n = G.shape
+    U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
+    st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    rc = lib.pdip_emu_solve(dtype, np_, mr, B, n, m, P.ctypes.data_as(_dp), q.ctypes.data_as(_dp),
+                            G.ctypes.data_as(_dp), h.ctypes.data_as(_dp), max_iter, ctypes.c_double(tol),
+                            int(polish), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
+                            st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
+    assert rc == 0, rc
+    return dict(U=U, z=Z[:, :m], status=st, iters=it)

@@ -1,0 +1,261 @@
+// kernel_emu.cpp -- host build of the engine's warp kernels on the fiber
+// emulator (warp_emu.h).  TEST INFRASTRUCTURE ONLY.
+//
+// emu_solve() takes the C ABI's own descriptor / operand / output structs
+// (include/qpmpc_b200.h, HOST pointers) and does what qpmpc_b200_solve does --
+// check_desc, fill_params, pick_variant, layout_smem from the product's headers
+// -- but "launches" mpc_solve_kernel / mpc_pdip_kernel (the device SOURCE,
+// compiled for the host) CTA by CTA on fibers.  emu_condense() does the same
+// for mpc_condense_kernel.  tests/test_kernel_emu.py compares the results with
+// the oracle; nothing here is measured or shipped.
+//
+//   g++ -O1 -std=c++17 -shared -fPIC -DQPMPC_HOST_EMU -Wno-unknown-pragmas \
+//       -I<repo> tests/emu/kernel_emu.cpp -o tests/emu/libkernel_emu.so
+#include "warp_emu.h"
+
+#include <cstdlib>
+
+#include "qpmpc_b200/csrc/mpc_host_params.h"
+#include "qpmpc_b200/csrc/mpc_pdip.cuh"  // brings mpc_common.cuh and mpc_kernels.cuh
+
+namespace qpmpc {
+alignas(16) unsigned char smem_raw[256 * 1024];  // what `extern __shared__` names in the kernels
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+}  // namespace qpmpc
+
+using namespace qpmpc;
+
+namespace {
+
+int g_smem_overrun = 0;  // CTAs that wrote past their dynamic shared-memory request
+
+// one grid: CTAs one after the other, each on a NaN-poisoned shared-memory image
+// followed by a canary (a store past the requested size is an error on the device)
+template <typename K>
+void launch(int grid, int threads, size_t smem, K kernel) {
+    const uint64_t poison = 0x7ff8dead7ff8deadull;  // NaN as double and as two floats
+    const size_t lo = (smem + 7) / 8 * 8;
+    for (int b = 0; b < grid; ++b) {
+        for (size_t i = 0; i + 8 <= sizeof(smem_raw); i += 8) memcpy(smem_raw + i, &poison, 8);
+        emu::run_cta(threads, emu::Idx{(unsigned)b, 0, 0}, emu::Idx{(unsigned)grid, 1, 1}, kernel);
+        for (size_t i = lo; i + 8 <= sizeof(smem_raw); i += 8)
+            if (memcmp(smem_raw + i, &poison, 8) != 0) {
+                ++g_smem_overrun;
+                break;
+            }
+    }
+}
+
+template <typename T, int NP, int MR, bool MREG, bool RS>
+int solve_variant(SolveParams p, int wpc) {
+    using L = Lay<T, NP, MR, MREG, RS>;
+    constexpr int IPW = 32 / NP;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, MREG);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_solve_kernel<T, NP, MR, MREG, RS>(p); });
+    return 0;
+}
+
+// launch_solve (mpc_launch.cuh): the NP = 16 register-resident kernel has two builds
+template <typename T, int NP, int MR, bool MREG>
+int solve(const SolveParams &p, int wpc) {
+    if constexpr (NP == 16 && MREG) {
+        const int rs = env_int("QPMPC_B200_ROWS_SMEM", -1);
+        if (rs > 0 || (rs < 0 && !p.has_wx)) return solve_variant<T, NP, MR, MREG, true>(p, wpc);
+    }
+    return solve_variant<T, NP, MR, MREG, false>(p, wpc);
+}
+
+template <typename T, int NP, int MR>
+int pdip(SolveParams p, int polish, int wpc) {
+    using L = PdipLay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, false, true);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR>(p, polish); });
+    return 0;
+}
+
+template <typename T, int NP, int MR>
+int condense(SolveParams p, int wpc) {
+    using L = Lay<T, NP, MR, false>;
+    constexpr int IPW = 32 / NP;
+    size_t smem = 0;
+    for (;; --wpc) {
+        smem = layout_smem<T>(&p, L::fixed, L::szG, NP, IPW * wpc, false);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc, grid = (p.batch + ipc - 1) / ipc;
+    SolveParams a = p, b = p;
+    a.Phi = a.Psi = a.phi_last = a.psi_last = nullptr;
+    b.P = b.q = b.G = b.h = nullptr;
+    if (p.P || p.q || p.G || p.h) launch(grid, wpc * 32, smem, [&]() { mpc_condense_kernel<T, NP, MR, false>(a); });
+    if (p.Phi || p.Psi || p.phi_last || p.psi_last)
+        launch(grid, wpc * 32, smem, [&]() { mpc_condense_kernel<T, NP, MR, true>(b); });
+    return 0;
+}
+
+
+// ---- pdip_core() on explicit QPs (P, q, G, h given), one emulated warp ------
+// `count` QPs (count <= 32 / NP) side by side, laid out as the kernel lays
+// them out: P, G by columns with the kernel's leading dimensions, padding
+// variables with P = identity.  Lets the tests reach cases the MPC front-end
+// never produces (infeasible rows, m = 0) and the float instantiation.
+template <typename T, int NP, int MR>
+int pdip_core_run(int count, int n, int m, const double *P, const double *q, const double *G, const double *h,
+                  int max_iter, double tol, int polish, double *U, double *Z, int *status, int *iters) {
+    using L = PdipLay<T, NP, MR>;
+    constexpr int IPW = 32 / NP;
+    if (count < 1 || count > IPW || n > NP || m > L::MP) return -1;
+    const int stride = L::fixed + L::szG;
+    std::vector<T> smem((size_t)IPW * stride, std::numeric_limits<T>::quiet_NaN());
+    for (int g = 0; g < IPW; ++g) {
+        const int src = g < count ? g : 0;  // tail slots read instance 0, like the kernel
+        T *wk = smem.data() + (size_t)g * stride;
+        T *hs = wk + L::oH, *Pc = wk + L::oP, *Gc = wk + L::fixed;
+        for (int r = 0; r < m; ++r) hs[r] = (T)h[(size_t)src * m + r];
+        for (int c = 0; c < NP; ++c)
+            for (int r = 0; r < NP; ++r)
+                Pc[c * L::LDL + r] = (r < n && c < n) ? (T)P[((size_t)src * n + r) * n + c] : (r == c ? T(1) : T(0));
+        for (int c = 0; c < NP; ++c)
+            for (int r = 0; r < m; ++r) Gc[c * L::LDG + r] = c < n ? (T)G[((size_t)src * m + r) * n + c] : T(0);
+    }
+    emu::run_cta(32, emu::Idx{0, 0, 0}, emu::Idx{1, 1, 1}, [&]() {
+        const int lane = emu::lane_id();
+        const int sub = lane / NP, l = lane % NP;
+        T *wk = smem.data() + (size_t)sub * stride;
+        T *xs = wk + L::oV, *dv = xs + NP, *wv = wk + L::oW, *tv = wv + L::MP;
+        const bool valid = sub < count;
+        const int src = valid ? sub : 0;
+        const T qj = l < n ? (T)q[(size_t)src * n + l] : T(0);
+        T x, z[MR];
+        int st, it;
+        pdip_core<T, NP, MR>(wk + L::oP, qj, wk + L::fixed, wk + L::oH, wk + L::oL, xs, dv, wv, tv, m, l, valid,
+                             max_iter, (T)tol, polish != 0, x, z, st, it);
+        if (!valid) return;
+        if (l < n) U[(size_t)sub * n + l] = (double)x;
+        for (int s = 0; s < MR; ++s)
+            if (l + s * NP < m) Z[(size_t)sub * m + l + s * NP] = (double)z[s];
+        if (l == 0) {
+            status[sub] = st;
+            iters[sub] = it;
+        }
+    });
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pdip_emu_solve(int dtype, int np, int mr, int count, int n, int m, const double *P, const double *q,
+                   const double *G, const double *h, int max_iter, double tol, int polish, double *U, double *Z,
+                   int *status, int *iters) {
+#define CASE(T, NP, MR)       \
+    if (np == NP && mr == MR) \
+        return pdip_core_run<T, NP, MR>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status, iters);
+    if (dtype == 0) {
+        CASE(double, 8, 2)
+        CASE(double, 8, 4)
+        CASE(double, 16, 2)
+        CASE(double, 16, 4)
+        CASE(double, 32, 2)
+        CASE(double, 32, 4)
+    } else {
+        CASE(float, 8, 2)
+        CASE(float, 16, 2)
+        CASE(float, 32, 2)
+    }
+#undef CASE
+    return -2;
+}
+
+int emu_smem_overruns(void) { return g_smem_overrun; }
+void emu_set_lane_order(int descending) { emu::lane_order() = descending; }
+
+// qpmpc_b200_solve with host pointers.  `wpc`: warps per CTA (<= 0: the launch default).
+int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out, int wpc) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!out || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    if (d->dtype != QPMPC_B200_F64) return QPMPC_B200_EUNSUPPORTED;  // the emulator build instantiates double only
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.U = out->U;
+    p.status = out->status;
+    p.iters = out->iters;
+    p.Z = out->Z;
+    Variant v;
+    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    const int key = v.np * 10 + v.mr;
+    if (d->method == QPMPC_B200_PDIP) {
+        p.max_iter = d->max_iter > 0 ? d->max_iter : 50;
+        const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
+        if (wpc <= 0) wpc = 4;
+        switch (key) {
+            case 82: return pdip<double, 8, 2>(p, polish, wpc);
+            case 84: return pdip<double, 8, 4>(p, polish, wpc);
+            case 162: return pdip<double, 16, 2>(p, polish, wpc);
+            case 164: return pdip<double, 16, 4>(p, polish, wpc);
+            case 322: return pdip<double, 32, 2>(p, polish, wpc);
+            case 324: return pdip<double, 32, 4>(p, polish, wpc);
+        }
+        return QPMPC_B200_ESHAPE;
+    }
+    if (wpc <= 0) wpc = 8;
+    switch (key) {
+        case 82: return solve<double, 8, 2, true>(p, wpc);
+        case 84: return solve<double, 8, 4, true>(p, wpc);
+        case 162: return solve<double, 16, 2, true>(p, wpc);
+        case 164: return solve<double, 16, 4, false>(p, wpc);
+        case 322: return solve<double, 32, 2, false>(p, wpc);
+        case 324: return solve<double, 32, 4, false>(p, wpc);
+    }
+    return QPMPC_B200_ESHAPE;
+}
+
+// qpmpc_b200_condense with host pointers.
+int emu_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_qp_fields *out) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!out || d->dtype != QPMPC_B200_F64) return QPMPC_B200_EINVAL;
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.P = out->P;
+    p.q = out->q;
+    p.G = out->G;
+    p.h = out->h;
+    p.Phi = out->Phi;
+    p.Psi = out->Psi;
+    p.phi_last = out->phi_last;
+    p.psi_last = out->psi_last;
+    Variant v;
+    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    switch (v.np * 10 + v.mr) {
+        case 82: return condense<double, 8, 2>(p, 2);
+        case 84: return condense<double, 8, 4>(p, 2);
+        case 162: return condense<double, 16, 2>(p, 2);
+        case 164: return condense<double, 16, 4>(p, 2);
+        case 322: return condense<double, 32, 2>(p, 2);
+        case 324: return condense<double, 32, 4>(p, 2);
+    }
+    return QPMPC_B200_ESHAPE;
+}
+
+}  // extern "C"

@@ -1,114 +1,203 @@
-// warp_emu.h -- runs warp-synchronous CUDA device code on the host, one fiber
-// per lane.  TEST INFRASTRUCTURE ONLY (no GPU in the development container).
+// warp_emu.h -- runs CUDA kernels written in the warp-synchronous style on the
+// host, one fiber per thread.  TEST INFRASTRUCTURE ONLY (there is no GPU in the
+// development container; this lets the CPU test-suite execute the device
+// SOURCE -- same templates, same indexing, same shared-memory layout -- against
+// the oracle).
 //
-// A warp is 32 ucontext fibers scheduled round-robin; every warp-level
-// synchronisation point (__syncwarp, a shuffle, a vote) yields to the next
-// lane, so that when lane 0 resumes every other lane has reached the same
-// point: a yield IS the barrier.  Shuffles and votes exchange values through a
-// slot array: write own slot, yield, read the source slot(s), yield.  Code
-// whose lanes do not reach the same sequence of synchronisation points
-// (divergent barriers) misbehaves here just as it is undefined on the device.
+// A CTA is blockDim.x ucontext fibers.  The scheduler steps one warp at a time,
+// round-robin over its lanes; every warp-level synchronisation point
+// (__syncwarp, a shuffle, a vote, a redux) yields to the next lane, so when a
+// lane resumes every other running lane of its warp has reached the same
+// point: a yield IS the warp barrier.  Shuffles and votes exchange values
+// through a slot per thread: write own slot, yield, read the source slot(s),
+// yield.  __syncthreads parks the thread until every thread of the CTA is
+// parked or finished.  Warps run one after the other between CTA barriers
+// (a legal schedule: the kernels must not depend on inter-warp timing), and
+// CTAs run one after the other on a fresh, NaN-filled shared-memory image
+// (reads of never-written shared memory poison the result instead of passing
+// by luck).  Bulk-TMA copies complete at issue time and mbarrier waits are
+// no-ops (qpmpc_b200/csrc/mpc_common.cuh, QPMPC_HOST_EMU).
 //
-// Only what the emulated sources use is provided: the *_sync primitives with a
-// full mask, the math helpers of mpc_common.cuh, and the qualifier macros.
+// What it cannot show: data races between lanes (the schedule is sequential),
+// memory-ordering bugs, performance.  Divergent barriers misbehave here just
+// as they are undefined on the device.
 #pragma once
 
+#include <math.h>
+#include <string.h>
 #include <ucontext.h>
 
-#include <cmath>
+#include <algorithm>
 #include <cstdint>
-#include <cstring>
 #include <functional>
 #include <limits>
 #include <vector>
 
 #define __device__
 #define __host__
+#define __global__
 #define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__
+#define __align__(x)
+
+struct double2 {
+    double x, y;
+};
+struct float2 {
+    float x, y;
+};
 
 namespace emu {
 
 constexpr int WARP = 32;
+enum State { RUN, PARKED, DONE };
 
-struct Warp {
-    ucontext_t main_ctx;
-    ucontext_t ctx[WARP];
-    std::vector<char> stack[WARP];
-    bool finished[WARP];
-    int cur = 0;
-    uint64_t slot[WARP];
-    std::function<void(int)> body;
+struct Idx {
+    unsigned x, y, z;
 };
 
-inline Warp *&current() {
-    static thread_local Warp *w = nullptr;
-    return w;
+struct Cta {
+    ucontext_t main_ctx;
+    std::vector<ucontext_t> ctx;
+    std::vector<std::vector<char>> stack;
+    std::vector<State> state;
+    std::vector<uint64_t> slot;
+    int nthreads = 0, cur = 0;
+    Idx block_idx{0, 0, 0}, block_dim{1, 1, 1}, grid_dim{1, 1, 1};
+    std::function<void()> body;
+};
+
+// Lane order inside a scheduling round: 0 ascending, 1 descending.  A result
+// that depends on it reveals a read of another lane's shared-memory write with
+// no synchronisation point in between (a data race on the device).
+inline int &lane_order() {
+    static int order = 0;
+    return order;
 }
 
+inline Cta *&current() {
+    static thread_local Cta *c = nullptr;
+    return c;
+}
 inline void yield() {
-    Warp *w = current();
-    swapcontext(&w->ctx[w->cur], &w->main_ctx);
+    Cta *c = current();
+    swapcontext(&c->ctx[c->cur], &c->main_ctx);
 }
-
 inline void trampoline() {
-    Warp *w = current();
-    const int lane = w->cur;
-    w->body(lane);
-    w->finished[lane] = true;
-    swapcontext(&w->ctx[lane], &w->main_ctx);
+    Cta *c = current();
+    const int t = c->cur;
+    c->body();
+    c->state[t] = DONE;
+    swapcontext(&c->ctx[t], &c->main_ctx);
 }
+inline int tid() { return current()->cur; }
+inline int lane_id() { return current()->cur % WARP; }
+inline int warp_base() { return current()->cur / WARP * WARP; }
 
-// Run body(lane) for the 32 lanes of one warp to completion.
-inline void run_warp(const std::function<void(int)> &body, size_t stack_bytes = 1 << 20) {
-    Warp w;
-    w.body = body;
-    current() = &w;
-    for (int i = 0; i < WARP; ++i) {
-        w.stack[i].resize(stack_bytes);
-        w.finished[i] = false;
-        getcontext(&w.ctx[i]);
-        w.ctx[i].uc_stack.ss_sp = w.stack[i].data();
-        w.ctx[i].uc_stack.ss_size = stack_bytes;
-        w.ctx[i].uc_link = &w.main_ctx;
-        makecontext(&w.ctx[i], trampoline, 0);
+// Run one CTA of `nthreads` threads to completion.
+inline void run_cta(int nthreads, Idx block_idx, Idx grid_dim, const std::function<void()> &body,
+                    size_t stack_bytes = 1 << 20) {
+    Cta c;
+    c.nthreads = nthreads;
+    c.block_idx = block_idx;
+    c.block_dim = Idx{(unsigned)nthreads, 1, 1};
+    c.grid_dim = grid_dim;
+    c.body = body;
+    c.ctx.resize(nthreads);
+    c.stack.resize(nthreads);
+    c.state.assign(nthreads, RUN);
+    c.slot.assign(nthreads, 0);
+    current() = &c;
+    for (int t = 0; t < nthreads; ++t) {
+        c.stack[t].resize(stack_bytes);
+        getcontext(&c.ctx[t]);
+        c.ctx[t].uc_stack.ss_sp = c.stack[t].data();
+        c.ctx[t].uc_stack.ss_size = stack_bytes;
+        c.ctx[t].uc_link = &c.main_ctx;
+        makecontext(&c.ctx[t], trampoline, 0);
     }
-    bool any = true;
-    while (any) {
-        any = false;
-        for (int i = 0; i < WARP; ++i) {
-            if (w.finished[i]) continue;
-            w.cur = i;
-            swapcontext(&w.main_ctx, &w.ctx[i]);
-            any = any || !w.finished[i];
+    const int nwarps = (nthreads + WARP - 1) / WARP;
+    while (true) {
+        for (int w = 0; w < nwarps; ++w) {
+            bool any = true;
+            while (any) {  // step this warp until every lane is parked or done
+                any = false;
+                const int lo = w * WARP, hi = std::min(nthreads, (w + 1) * WARP);
+                for (int k = lo; k < hi; ++k) {
+                    const int t = lane_order() ? hi - 1 - (k - lo) : k;
+                    if (c.state[t] != RUN) continue;
+                    c.cur = t;
+                    swapcontext(&c.main_ctx, &c.ctx[t]);
+                    any = any || c.state[t] == RUN;
+                }
+            }
         }
+        bool parked = false;
+        for (int t = 0; t < nthreads; ++t) parked = parked || c.state[t] == PARKED;
+        if (!parked) break;  // all done
+        for (int t = 0; t < nthreads; ++t)
+            if (c.state[t] == PARKED) c.state[t] = RUN;  // the CTA barrier opens
     }
     current() = nullptr;
 }
 
-inline int lane_id() { return current()->cur; }
-
+template <typename V>
+inline void put(V v) {
+    static_assert(sizeof(V) <= 8, "slot is 8 bytes");
+    Cta *c = current();
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(V));
+    c->slot[c->cur] = raw;
+}
+template <typename V>
+inline V get(int lane) {
+    V out;
+    memcpy(&out, &current()->slot[warp_base() + lane], sizeof(V));
+    return out;
+}
 template <typename V>
 inline V exchange(V v, int src_lane) {
-    static_assert(sizeof(V) <= 8, "slot is 8 bytes");
-    Warp *w = current();
-    uint64_t raw = 0;
-    std::memcpy(&raw, &v, sizeof(V));
-    w->slot[w->cur] = raw;
+    put(v);
     yield();
-    V out;
-    std::memcpy(&out, &w->slot[src_lane], sizeof(V));
+    const V out = get<V>(src_lane);
     yield();
     return out;
+}
+// fold the values of the lanes in `mask` (every lane of the mask calls)
+template <typename V, typename F>
+inline V fold(unsigned mask, V v, F f) {
+    put(v);
+    yield();
+    bool first = true;
+    V acc = v;
+    for (int i = 0; i < WARP; ++i) {
+        if (!((mask >> i) & 1u)) continue;
+        const V o = get<V>(i);
+        acc = first ? o : f(acc, o);
+        first = false;
+    }
+    yield();
+    return acc;
 }
 
 }  // namespace emu
 
 // ---- the CUDA surface the emulated sources use -----------------------------
-namespace qpmpc {
+#define threadIdx (emu::Idx{(unsigned)emu::tid(), 0, 0})
+#define blockIdx (emu::current()->block_idx)
+#define blockDim (emu::current()->block_dim)
+#define gridDim (emu::current()->grid_dim)
 
-constexpr unsigned FULL_MASK = 0xffffffffu;
+using std::max;
+using std::min;
 
-inline void __syncwarp(unsigned = FULL_MASK) { emu::yield(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield(); }
+inline void __syncthreads() {
+    emu::Cta *c = emu::current();
+    c->state[c->cur] = emu::PARKED;
+    emu::yield();
+}
 
 template <typename V>
 inline V __shfl_sync(unsigned, V v, int src, int width = 32) {
@@ -117,33 +206,76 @@ inline V __shfl_sync(unsigned, V v, int src, int width = 32) {
 }
 template <typename V>
 inline V __shfl_xor_sync(unsigned, V v, int mask, int width = 32) {
-    const int lane = emu::lane_id();
-    const int src = lane ^ mask;
-    // a source outside the lane's width-segment returns the lane's own value
+    const int lane = emu::lane_id(), src = lane ^ mask;
     return emu::exchange(v, (src / width == lane / width) ? src : lane);
 }
-inline unsigned __ballot_sync(unsigned, bool pred) {
-    emu::Warp *w = emu::current();
-    w->slot[w->cur] = pred ? 1u : 0u;
+template <typename V>
+inline V __shfl_down_sync(unsigned, V v, unsigned delta, int width = 32) {
+    const int lane = emu::lane_id(), src = lane + (int)delta;
+    return emu::exchange(v, (src / width == lane / width) ? src : lane);
+}
+inline unsigned __ballot_sync(unsigned mask, bool pred) {
+    emu::put<unsigned>(pred ? 1u : 0u);
     emu::yield();
     unsigned out = 0;
-    for (int i = 0; i < emu::WARP; ++i) out |= (w->slot[i] ? 1u : 0u) << i;
+    for (int i = 0; i < emu::WARP; ++i)
+        if (((mask >> i) & 1u) && emu::get<unsigned>(i)) out |= 1u << i;
     emu::yield();
     return out;
 }
-inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == m; }
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+inline unsigned __reduce_max_sync(unsigned m, unsigned v) {
+    return emu::fold(m, v, [](unsigned a, unsigned b) { return a > b ? a : b; });
+}
+inline unsigned __reduce_min_sync(unsigned m, unsigned v) {
+    return emu::fold(m, v, [](unsigned a, unsigned b) { return a < b ? a : b; });
+}
+inline int __reduce_max_sync(unsigned m, int v) {
+    return emu::fold(m, v, [](int a, int b) { return a > b ? a : b; });
+}
+inline int __reduce_min_sync(unsigned m, int v) {
+    return emu::fold(m, v, [](int a, int b) { return a < b ? a : b; });
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __ffs(int v) { return __ffs((unsigned)v); }
 
-inline double abs_(double v) { return std::fabs(v); }
-inline float abs_(float v) { return std::fabs(v); }
-inline double frsqrt_(double v) { return 1.0 / std::sqrt(v); }
-inline float frsqrt_(float v) { return 1.0f / std::sqrt(v); }
-using std::fmax;
-using std::fmin;
-
-template <typename T> struct Num {
-    static T inf() { return std::numeric_limits<T>::infinity(); }
-    static T nan() { return std::numeric_limits<T>::quiet_NaN(); }
-};
-
-}  // namespace qpmpc
+inline int __double2hiint(double v) {
+    uint64_t r;
+    memcpy(&r, &v, 8);
+    return (int)(r >> 32);
+}
+inline int __double2loint(double v) {
+    uint64_t r;
+    memcpy(&r, &v, 8);
+    return (int)(r & 0xffffffffu);
+}
+inline double __hiloint2double(int hi, int lo) {
+    const uint64_t r = ((uint64_t)(unsigned)hi << 32) | (unsigned)lo;
+    double v;
+    memcpy(&v, &r, 8);
+    return v;
+}
+inline double __longlong_as_double(long long r) {
+    double v;
+    memcpy(&v, &r, 8);
+    return v;
+}
+inline float __int_as_float(int r) {
+    float v;
+    memcpy(&v, &r, 4);
+    return v;
+}
+inline float __uint_as_float(unsigned r) {
+    float v;
+    memcpy(&v, &r, 4);
+    return v;
+}
+inline unsigned __float_as_uint(float v) {
+    unsigned r;
+    memcpy(&r, &v, 4);
+    return r;
+}
+inline float __frcp_rn(float v) { return 1.0f / v; }
+inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
+inline double rsqrt(double v) { return 1.0 / sqrt(v); }

@@ -1,0 +1,166 @@
+"""The engine's CUDA kernels, run on the host.
+
+``tests/emu/`` compiles the DEVICE SOURCE of the hot path
+(``qpmpc_b200/csrc/mpc_kernels.cuh``: staging, condensing, Cholesky, the dual
+active-set iteration, outputs; ``mpc_pdip.cuh``: the interior-point kernel) for
+the host -- one fiber per CUDA thread, every warp-level synchronisation a
+scheduling point, shared memory NaN-poisoned, bulk-TMA copies done at issue
+time -- and drives it through the product's own descriptor-to-parameter code.
+The results are held to the GPU bars (``tests/test_gpu_parity.py``): condensing
+within 1e-12 relative of the reference's ``MPCQP`` fields (golden fixtures made
+by ``qpmpc/mpc_qp.py:39-122`` itself), ``|dU|_inf <= 1e-6`` against the exact
+oracle for the solve that replaces ``qpmpc/solve_mpc.py:43``.
+
+What this adds to the GPU tests: it runs in the CPU suite (every commit, no
+device), it catches reads of unwritten shared memory and stores past the
+shared-memory request, and it re-runs the kernels with the lanes scheduled in
+the opposite order -- a result that changes exposes a missing
+``__syncwarp``.  What it cannot replace: the device run (real concurrency,
+TMA, mbarriers, timing).
+"""
+
+import numpy as np
+import pytest
+
+import emu
+import oracle
+from conftest import GOLDEN_NAMES, load_golden
+from qpmpc_b200.workloads import (humanoid_batch, oracle_ops, pendulum_batch, random_batch,
+                                  triple_integrator_batch)
+
+U_TOL = 1e-6  # |du|_inf, fp64 (BASELINE.json north_star)
+
+
+def _oracle(w):
+    return oracle.solve_batch(w["batch"], w["N"], w["nx"], w["nu"], w["nc"], oracle_ops(w),
+                              w["w_t"], w["w_x"], w["w_u"])
+
+
+def _check(w, method="active_set", **kw):
+    got = emu.solve(w, method=method, **kw)
+    assert got["rc"] == 0
+    ref = _oracle(w)
+    ok = ref["status"] == 0
+    assert np.array_equal(got["status"] == 0, ok)
+    assert ok.any()
+    err = np.abs(got["U"][ok] - ref["U"][ok]).max()
+    assert err <= U_TOL, f"|dU|_inf = {err:.3e}"
+    assert np.isnan(got["U"][~ok]).all()
+    return got
+
+
+def _golden_workload(g):
+    """Workload dict (batch of one, shared operands) of a golden fixture."""
+    ltv = tuple(k for k in ("A", "B", "C", "D", "e") if g[k] is not None and bool(g[f"{k}_ltv"]))
+    nc = int(g["e"].shape[-1])
+    return dict(name="golden", batch=1, N=g["N"], nx=int(g["x0"].size), nu=int(g["B"].shape[-1]), nc=nc,
+                A=g["A"], B=g["B"], C=g["C"], D=g["D"], e=g["e"], x0=g["x0"], goal=g["goal"],
+                targets=None if g["targets"] is None else g["targets"].reshape(-1),
+                w_t=g["w_t"], w_x=g["w_x"], w_u=g["w_u"], ltv=ltv)
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if not n.endswith("N64")])
+def test_condense_kernel_matches_reference_fields(name):
+    """mpc_condense_kernel (both builds: fused phase-A code and the Phi / Psi dump)
+    against the fields of the reference's own MPCQP."""
+    g = load_golden(name)
+    out = emu.condense(_golden_workload(g))
+    for field in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last"):
+        ref = g[f"ref_{field}"]
+        got = out[field][0].reshape(ref.shape)
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), field
+
+
+@pytest.mark.parametrize("name", ["triple_integrator", "humanoid", "pendulum", "random_ltv_cd",
+                                  "triple_integrator_stage", "triple_integrator_tiny_wt"])
+def test_solve_kernel_on_the_reference_problems(name):
+    """mpc_solve_kernel on the golden problems vs the exact QP oracle applied to
+    the REFERENCE's condensed matrices; the SURVEY 8(c) known answer for TI."""
+    g = load_golden(name)
+    st, x, _, _ = oracle.qp_gi(g["ref_P"], g["ref_q"], g["ref_G"], g["ref_h"])
+    got = emu.solve(_golden_workload(g))
+    assert got["rc"] == 0 and (got["status"][0] == 0) == (st == 0)
+    if st == 0:
+        assert np.abs(got["U"][0] - x).max() <= U_TOL
+    if name == "triple_integrator":
+        expect = {0: 48.0, 7: -27.51976087031062, 8: -54.819558402499155, 9: -13.660680727190227,
+                  15: 47.92404503861714}
+        assert max(abs(got["U"][0, i] - expect.get(i, 0.0)) for i in range(16)) <= U_TOL
+
+
+@pytest.mark.parametrize("rows_smem", ["0", "1"])
+def test_solve_kernel_config2_both_builds(rows_smem, monkeypatch):
+    """BASELINE config 2 shape (NP = 16 register-resident kernel, Toeplitz G):
+    per-row constants in registers / in shared memory; ragged last CTA."""
+    monkeypatch.setenv("QPMPC_B200_ROWS_SMEM", rows_smem)
+    _check(triple_integrator_batch(37, N=16, seed=3))
+
+
+def test_solve_kernel_dense_g_and_shared_model(monkeypatch):
+    _check(triple_integrator_batch(11, per_instance_model=False, seed=12))
+    monkeypatch.setenv("QPMPC_B200_NO_TOEPLITZ", "1")
+    _check(triple_integrator_batch(11, N=16, seed=13))
+
+
+@pytest.mark.parametrize("N,batch,wpc", [(8, 21, 8), (8, 5, 1), (32, 5, 2)])
+def test_solve_kernel_lane_group_widths(N, batch, wpc):
+    """NP = 8 (four instances per warp) and NP = 32 (J kept in registers)."""
+    _check(triple_integrator_batch(batch, N=N, seed=N), wpc=wpc)
+
+
+@pytest.mark.parametrize("kind", ["pendulum", "pendulum_ltv", "humanoid", "infeasible"])
+def test_solve_kernel_workloads(kind):
+    """Configs 3 and 4 data (stage cost from Toeplitz prefix sums, D-only rows,
+    per-step e_k) and a batch with infeasible instances (status 2, NaN rows)."""
+    if kind == "humanoid":
+        w = humanoid_batch(10)
+    elif kind == "infeasible":
+        w = triple_integrator_batch(12, seed=11)
+        w["x0"][::4, 2] = 5.0
+    else:
+        w = pendulum_batch(10, ltv_model=kind.endswith("ltv"))
+    _check(w)
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 2, 4), (7, 5, 1, 4), (5, 2, 2, 5), (6, 3, 2, 7), (9, 4, 3, 5), (3, 6, 2, 0)])
+@pytest.mark.parametrize("ltv", [False, True])
+def test_solve_kernel_random_shapes(shape, ltv):
+    """Every compiled (NP, MR) variant, register and generic-nx condensing, C and D."""
+    N, nx, nu, nc = shape
+    _check(random_batch(7, N, nx, nu, nc, seed=sum(shape), ltv=ltv))
+
+
+@pytest.mark.parametrize("kind", ["ti16", "ti8", "pendulum", "humanoid", "random", "random_generic_nx"])
+def test_pdip_kernel_matches_the_exact_solution(kind):
+    """mpc_pdip_kernel end to end (staging, dense-G condensing, interior point,
+    polish, outputs): the north star's |dU| <= 1e-6 with the method it names."""
+    w = {"ti16": lambda: triple_integrator_batch(19, N=16, seed=5),
+         "ti8": lambda: triple_integrator_batch(9, N=8, seed=6),
+         "pendulum": lambda: pendulum_batch(9),
+         "humanoid": lambda: humanoid_batch(9),
+         "random": lambda: random_batch(9, 6, 3, 2, 7, seed=5),
+         "random_generic_nx": lambda: random_batch(9, 7, 5, 1, 4, seed=6)}[kind]()
+    got = _check(w, method="pdip")
+    assert got["iters"].max() <= 50
+    assert got["z"].min() >= -1e-9 * max(1.0, got["z"].max())
+
+
+@pytest.mark.parametrize("method", ["active_set", "pdip"])
+def test_results_do_not_depend_on_the_lane_schedule(method):
+    """Ascending and descending lane order between synchronisation points give
+    bit-identical results: no lane reads another lane's shared-memory write
+    without a synchronisation point in between."""
+    for w in (triple_integrator_batch(9, N=16, seed=21), pendulum_batch(5), random_batch(5, 6, 3, 2, 7, seed=9),
+              random_batch(5, 7, 5, 1, 4, seed=10)):
+        a = emu.solve(w, method=method)
+        b = emu.solve(w, method=method, descending=True)
+        assert np.array_equal(a["U"], b["U"], equal_nan=True)
+        assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["status"], b["status"])
+
+
+def test_unsupported_requests_are_refused():
+    w = triple_integrator_batch(2, N=64)
+    assert emu.solve(w)["rc"] != 0  # n = 64: the CTA kernel's territory, not emulated
+    bad = triple_integrator_batch(2)
+    bad["w_u"] = 0.0
+    assert emu.solve(bad)["rc"] == -3  # QPMPC_B200_EWEIGHT, as check_desc says on the device path

@@ -2,63 +2,38 @@
 
 ``qpmpc_b200/csrc/mpc_pdip.cuh:pdip_core`` (the device source behind
 ``desc.method = QPMPC_B200_PDIP``) is compiled for the host against
-``tests/emu/warp_emu.h`` -- 32 fibers per warp, every ``__syncwarp`` / shuffle /
-vote a scheduling point -- and checked against the NumPy statement of the same
-iteration (``oracle/pdip_np.py``) and the exact active-set oracle.  This is the
-CPU-side evidence for the kernel's arithmetic, indexing and lock-step logic;
-``tests/test_gpu_parity.py`` repeats the comparison on the device through the
-C ABI.  (It replaces the third-party solve at ``qpmpc/solve_mpc.py:43`` of the
+``tests/emu/warp_emu.h`` -- one fiber per CUDA thread, every ``__syncwarp`` /
+shuffle / vote a scheduling point -- and run on explicit QPs ``(P, q, G, h)``,
+checked against the NumPy statement of the same iteration
+(``oracle/pdip_np.py``) and the exact active-set oracle.  This is the CPU-side
+evidence for the arithmetic, indexing and lock-step logic of the
+interior-point phases; ``tests/test_kernel_emu.py`` runs the whole kernels
+(staging, condensing, outputs) the same way and ``tests/test_gpu_pdip.py``
+repeats the comparison on the device through the C ABI.  (It replaces the third-party solve at ``qpmpc/solve_mpc.py:43`` of the
 reference, like every other solver test here.)
 """
-
-import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
 import oracle
+from emu import pdip_core
 from oracle.pdip_np import pdip_batch
 from qpmpc_b200.workloads import (humanoid_batch, oracle_ops, pendulum_batch, random_batch,
                                   triple_integrator_batch)
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-EMU_DIR = os.path.join(HERE, "emu")
-EMU_LIB = os.path.join(EMU_DIR, "libpdip_emu.so")
-_dp = ctypes.POINTER(ctypes.c_double)
-_ip = ctypes.POINTER(ctypes.c_int)
-
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [os.path.join(EMU_DIR, "pdip_emu.cpp"), os.path.join(EMU_DIR, "warp_emu.h"),
-            os.path.join(ROOT, "qpmpc_b200", "csrc", "mpc_pdip.cuh")]
-    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DQPMPC_HOST_EMU", f"-I{ROOT}",
-                        "-o", EMU_LIB, deps[0]], check=True)
-    lib = ctypes.CDLL(EMU_LIB)
-    lib.pdip_emu_solve.restype = ctypes.c_int
-
-    def solve(P, q, G, h, np_, mr, dtype=0, max_iter=50, tol=1e-9, polish=True):
-        """One emulated warp: up to 32 // np_ QPs side by side."""
-        P, q, G, h = (np.ascontiguousarray(a, dtype=np.float64) for a in (P, q, G, h))
-        B, m, n = G.shape
-        U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
-        st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
-        rc = lib.pdip_emu_solve(dtype, np_, mr, B, n, m, P.ctypes.data_as(_dp), q.ctypes.data_as(_dp),
-                                G.ctypes.data_as(_dp), h.ctypes.data_as(_dp), max_iter, ctypes.c_double(tol),
-                                int(polish), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
-                                st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
-        assert rc == 0, rc
-        return dict(U=U, z=Z[:, :m], status=st, iters=it)
-
+    """``emu(P, q, G, h, NP, MR, ...)``: one emulated warp; ``emu.all`` splits a batch into warps."""
     def solve_all(P, q, G, h, np_, mr, **kw):
         per = 32 // np_
-        parts = [solve(P[b:b + per], q[b:b + per], G[b:b + per], h[b:b + per], np_, mr, **kw)
+        parts = [pdip_core(P[b:b + per], q[b:b + per], G[b:b + per], h[b:b + per], np_, mr, **kw)
                  for b in range(0, len(q), per)]
         return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+    def solve(*a, **kw):
+        return pdip_core(*a, **kw)
 
     solve.all = solve_all
     return solve
