@@ -422,11 +422,14 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
                     zmax = fmax(zmax, abs_(lam[s]));
                 }
             }
+            // (every reduction is a shuffle sequence the whole warp must enter: evaluate
+            // them all before combining -- inside a short-circuited `&&` the groups of a
+            // warp would leave the chain at different links and the device deadlocks)
             const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
-            const bool ok = spd && pdip_max<T, NP>(worst_viol) <= eps * hscale &&
-                            pdip_max<T, NP>(worst_act) <= eps * hscale &&
-                            pdip_max<T, NP>(worst_neg) <= eps * zscale &&
-                            pdip_max<T, NP>(abs_(rd)) <= eps * qscale;
+            const T g_viol = pdip_max<T, NP>(worst_viol), g_act = pdip_max<T, NP>(worst_act);
+            const T g_neg = pdip_max<T, NP>(worst_neg), g_rd = pdip_max<T, NP>(abs_(rd));
+            const bool ok = spd && g_viol <= eps * hscale && g_act <= eps * hscale && g_neg <= eps * zscale &&
+                            g_rd <= eps * qscale;
             if (need && ok) {
                 accepted = true;
                 x = up;

@@ -38,7 +38,28 @@ def load():
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DQPMPC_HOST_EMU",
                         "-Wno-unknown-pragmas", f"-I{ROOT}", "-o", LIB_PATH, deps[0]], check=True)
     _lib = ctypes.CDLL(LIB_PATH)
+    _lib.emu_divergent_collectives.restype = ctypes.c_long
+    _lib.emu_selftest.restype = ctypes.c_long
     return _lib
+
+
+class _Checked:
+    """Fails the test if the emulated launch stored past its shared-memory request
+    or entered a warp-level collective with only part of the lanes it names."""
+
+    def __enter__(self):
+        lib = load()
+        self.before = (lib.emu_smem_overruns(), lib.emu_divergent_collectives())
+        return lib
+
+    def __exit__(self, *exc):
+        lib = load()
+        lib.emu_set_lane_order(0)
+        if exc[0] is None:
+            assert lib.emu_smem_overruns() == self.before[0], "a CTA wrote past its shared-memory request"
+            assert lib.emu_divergent_collectives() == self.before[1], \
+                "a shuffle / vote / reduction was entered by only part of the lanes it names (deadlock on the device)"
+        return False
 
 
 def _ptr(a):
@@ -84,11 +105,9 @@ def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, desce
     U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
     st, it = np.full(B, -1, np.int32), np.zeros(B, np.int32)
     outs = _capi.Outputs(_ptr(U), _ptr(st), _ptr(it), _ptr(Z))
-    lib.emu_set_lane_order(int(descending))
-    before = lib.emu_smem_overruns()
-    rc = lib.emu_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), wpc)
-    lib.emu_set_lane_order(0)
-    assert lib.emu_smem_overruns() == before, "a CTA wrote past its shared-memory request"
+    with _Checked() as lib:
+        lib.emu_set_lane_order(int(descending))
+        rc = lib.emu_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), wpc)
     return dict(rc=rc, U=U, status=st, iters=it, z=Z[:, :m])
 
 
@@ -103,7 +122,8 @@ def condense(w, fields=("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last"
                   phi_last=(B, nx, nx), psi_last=(B, nx, n))
     out = {k: np.full(shapes[k], np.nan) for k in fields}
     qf = _capi.QPFields(*[_ptr(out.get(k)) for k in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")])
-    rc = lib.emu_condense(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(qf))
+    with _Checked() as lib:
+        rc = lib.emu_condense(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(qf))
     assert rc == 0, rc
     return out
 
@@ -115,9 +135,10 @@ def pdip_core(P, q, G, h, np_, mr, dtype=0, max_iter=50, tol=1e-9, polish=True):
     B, m, n = G.shape
     U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
     st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
-    rc = lib.pdip_emu_solve(dtype, np_, mr, B, n, m, P.ctypes.data_as(_dp), q.ctypes.data_as(_dp),
-                            G.ctypes.data_as(_dp), h.ctypes.data_as(_dp), max_iter, ctypes.c_double(tol),
-                            int(polish), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
-                            st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
+    with _Checked() as lib:
+        rc = lib.pdip_emu_solve(dtype, np_, mr, B, n, m, P.ctypes.data_as(_dp), q.ctypes.data_as(_dp),
+                                G.ctypes.data_as(_dp), h.ctypes.data_as(_dp), max_iter, ctypes.c_double(tol),
+                                int(polish), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
+                                st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
     assert rc == 0, rc
     return dict(U=U, z=Z[:, :m], status=st, iters=it)

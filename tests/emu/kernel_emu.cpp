@@ -184,8 +184,32 @@ int pdip_emu_solve(int dtype, int np, int mr, int count, int n, int m, const dou
     return -2;
 }
 
+// Self-test of the emulator's convergence check: a group-wise reduction entered
+// by all lanes (which = 0), or hidden behind a short-circuited `&&` whose left
+// side differs between the two 16-lane groups of the warp (which = 1: the bug
+// class that hangs a device).  Returns the number of divergent collectives seen.
+long emu_selftest(int which) {
+    const long before = emu::divergent_collectives();
+    emu::run_cta(32, emu::Idx{0, 0, 0}, emu::Idx{1, 1, 1}, [&]() {
+        const int lane = emu::lane_id();
+        const bool flag = lane < 16;  // uniform inside a group, different across groups
+        const double v = (double)lane;
+        bool ok;
+        if (which == 0) {
+            const double r = pdip_max<double, 16>(v);
+            ok = flag && r > 3.0;
+        } else {
+            ok = flag && pdip_max<double, 16>(v) > 3.0;
+        }
+        __syncwarp();
+        (void)ok;
+    });
+    return emu::divergent_collectives() - before;
+}
+
 int emu_smem_overruns(void) { return g_smem_overrun; }
 void emu_set_lane_order(int descending) { emu::lane_order() = descending; }
+long emu_divergent_collectives(void) { return emu::divergent_collectives(); }
 
 // qpmpc_b200_solve with host pointers.  `wpc`: warps per CTA (<= 0: the launch default).
 int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out, int wpc) {

@@ -18,12 +18,18 @@
 // by luck).  Bulk-TMA copies complete at issue time and mbarrier waits are
 // no-ops (qpmpc_b200/csrc/mpc_common.cuh, QPMPC_HOST_EMU).
 //
-// What it cannot show: data races between lanes (the schedule is sequential),
-// memory-ordering bugs, performance.  Divergent barriers misbehave here just
-// as they are undefined on the device.
+// Checks it makes besides the results: every warp-level synchronisation point
+// must be entered by all the lanes it names (divergent_collectives(): on the
+// device such a point deadlocks -- this is how the round-1 hang of the
+// interior-point kernel, a shuffle inside a short-circuited `&&`, was found);
+// running the lanes in descending order as well exposes reads of another
+// lane's shared-memory write that have no synchronisation point in between.
+// What it cannot show: memory-ordering bugs, inter-warp races, performance.
 #pragma once
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
 
@@ -63,6 +69,8 @@ struct Cta {
     std::vector<std::vector<char>> stack;
     std::vector<State> state;
     std::vector<uint64_t> slot;
+    std::vector<uint64_t> nsync;     // warp-level synchronisation points entered, per thread
+    std::vector<int> site;           // source line of the last one entered
     int nthreads = 0, cur = 0;
     Idx block_idx{0, 0, 0}, block_dim{1, 1, 1}, grid_dim{1, 1, 1};
     std::function<void()> body;
@@ -76,6 +84,14 @@ inline int &lane_order() {
     return order;
 }
 
+// Collectives entered by only part of the lanes they name (e.g. a shuffle inside
+// a short-circuited `a && reduce(b)`, or behind a lane-dependent branch): the
+// device deadlocks or returns garbage there, the emulator counts them.
+inline long &divergent_collectives() {
+    static long count = 0;
+    return count;
+}
+
 inline Cta *&current() {
     static thread_local Cta *c = nullptr;
     return c;
@@ -83,6 +99,34 @@ inline Cta *&current() {
 inline void yield() {
     Cta *c = current();
     swapcontext(&c->ctx[c->cur], &c->main_ctx);
+}
+// Called by every warp-level synchronisation point after its first yield.  The
+// lanes scheduled after this one have not run since: each of them that the
+// mask names must be waiting at this very point -- same source line, same
+// number of points entered.  (Lanes scheduled before may already have left.)
+inline void check_convergence(unsigned mask) {
+    Cta *c = current();
+    const int base = c->cur / WARP * WARP, me = c->cur - base;
+    for (int i = 0; i < WARP && base + i < c->nthreads; ++i) {
+        const bool later = lane_order() ? i < me : i > me;
+        if (!later || !((mask >> i) & 1u) || c->state[base + i] != RUN) continue;
+        // __syncwarp (negative line) pairs with a __syncwarp anywhere: bar.warp.sync matches across code
+        // addresses; shuffles, votes and reductions exchange data and must be the same instruction
+        const bool same_site = c->site[base + i] == c->site[c->cur] || (c->site[base + i] < 0 && c->site[c->cur] < 0);
+        if (c->nsync[base + i] != c->nsync[c->cur] || !same_site) {
+            if (getenv("EMU_DEBUG") && divergent_collectives() < 12)
+                fprintf(stderr, "divergent: lane %d (point %lu, line %d) vs lane %d (point %lu, line %d)\n", me,
+                        (unsigned long)c->nsync[c->cur], c->site[c->cur], i, (unsigned long)c->nsync[base + i],
+                        c->site[base + i]);
+            ++divergent_collectives();
+            return;
+        }
+    }
+}
+inline void enter_sync(int line) {
+    Cta *c = current();
+    ++c->nsync[c->cur];
+    c->site[c->cur] = line;
 }
 inline void trampoline() {
     Cta *c = current();
@@ -108,6 +152,8 @@ inline void run_cta(int nthreads, Idx block_idx, Idx grid_dim, const std::functi
     c.stack.resize(nthreads);
     c.state.assign(nthreads, RUN);
     c.slot.assign(nthreads, 0);
+    c.nsync.assign(nthreads, 0);
+    c.site.assign(nthreads, 0);
     current() = &c;
     for (int t = 0; t < nthreads; ++t) {
         c.stack[t].resize(stack_bytes);
@@ -157,18 +203,22 @@ inline V get(int lane) {
     return out;
 }
 template <typename V>
-inline V exchange(V v, int src_lane) {
+inline V exchange(int line, V v, int src_lane, unsigned mask = 0xffffffffu) {
+    enter_sync(line);
     put(v);
     yield();
+    check_convergence(mask);
     const V out = get<V>(src_lane);
     yield();
     return out;
 }
 // fold the values of the lanes in `mask` (every lane of the mask calls)
 template <typename V, typename F>
-inline V fold(unsigned mask, V v, F f) {
+inline V fold(int line, unsigned mask, V v, F f) {
+    enter_sync(line);
     put(v);
     yield();
+    check_convergence(mask);
     bool first = true;
     V acc = v;
     for (int i = 0; i < WARP; ++i) {
@@ -192,51 +242,67 @@ inline V fold(unsigned mask, V v, F f) {
 using std::max;
 using std::min;
 
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::yield(); }
+// The warp-level primitives are macros over emu_*(__LINE__, ...): the source
+// line of the call identifies the synchronisation point (check_convergence).
+inline void emu_syncwarp(int line, unsigned mask = 0xffffffffu) {
+    emu::enter_sync(-line);
+    emu::yield();
+    emu::check_convergence(mask);
+}
 inline void __syncthreads() {
     emu::Cta *c = emu::current();
     c->state[c->cur] = emu::PARKED;
     emu::yield();
 }
-
 template <typename V>
-inline V __shfl_sync(unsigned, V v, int src, int width = 32) {
+inline V emu_shfl_sync(int line, unsigned m, V v, int src, int width = 32) {
     const int lane = emu::lane_id();
-    return emu::exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
+    return emu::exchange(line, v, (lane & ~(width - 1)) | (src & (width - 1)), m);
 }
 template <typename V>
-inline V __shfl_xor_sync(unsigned, V v, int mask, int width = 32) {
+inline V emu_shfl_xor_sync(int line, unsigned m, V v, int mask, int width = 32) {
     const int lane = emu::lane_id(), src = lane ^ mask;
-    return emu::exchange(v, (src / width == lane / width) ? src : lane);
+    return emu::exchange(line, v, (src / width == lane / width) ? src : lane, m);
 }
 template <typename V>
-inline V __shfl_down_sync(unsigned, V v, unsigned delta, int width = 32) {
+inline V emu_shfl_down_sync(int line, unsigned m, V v, unsigned delta, int width = 32) {
     const int lane = emu::lane_id(), src = lane + (int)delta;
-    return emu::exchange(v, (src / width == lane / width) ? src : lane);
+    return emu::exchange(line, v, (src / width == lane / width) ? src : lane, m);
 }
-inline unsigned __ballot_sync(unsigned mask, bool pred) {
+inline unsigned emu_ballot_sync(int line, unsigned mask, bool pred) {
+    emu::enter_sync(line);
     emu::put<unsigned>(pred ? 1u : 0u);
     emu::yield();
+    emu::check_convergence(mask);
     unsigned out = 0;
     for (int i = 0; i < emu::WARP; ++i)
         if (((mask >> i) & 1u) && emu::get<unsigned>(i)) out |= 1u << i;
     emu::yield();
     return out;
 }
-inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == m; }
-inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
-inline unsigned __reduce_max_sync(unsigned m, unsigned v) {
-    return emu::fold(m, v, [](unsigned a, unsigned b) { return a > b ? a : b; });
+inline bool emu_all_sync(int line, unsigned m, bool pred) { return emu_ballot_sync(line, m, pred) == m; }
+inline bool emu_any_sync(int line, unsigned m, bool pred) { return emu_ballot_sync(line, m, pred) != 0u; }
+inline unsigned emu_reduce_max_sync(int line, unsigned m, unsigned v) {
+    return emu::fold(line, m, v, [](unsigned a, unsigned b) { return a > b ? a : b; });
 }
-inline unsigned __reduce_min_sync(unsigned m, unsigned v) {
-    return emu::fold(m, v, [](unsigned a, unsigned b) { return a < b ? a : b; });
+inline unsigned emu_reduce_min_sync(int line, unsigned m, unsigned v) {
+    return emu::fold(line, m, v, [](unsigned a, unsigned b) { return a < b ? a : b; });
 }
-inline int __reduce_max_sync(unsigned m, int v) {
-    return emu::fold(m, v, [](int a, int b) { return a > b ? a : b; });
+inline int emu_reduce_max_sync(int line, unsigned m, int v) {
+    return emu::fold(line, m, v, [](int a, int b) { return a > b ? a : b; });
 }
-inline int __reduce_min_sync(unsigned m, int v) {
-    return emu::fold(m, v, [](int a, int b) { return a < b ? a : b; });
+inline int emu_reduce_min_sync(int line, unsigned m, int v) {
+    return emu::fold(line, m, v, [](int a, int b) { return a < b ? a : b; });
 }
+#define __syncwarp() emu_syncwarp(__LINE__)
+#define __shfl_sync(...) emu_shfl_sync(__LINE__, __VA_ARGS__)
+#define __shfl_xor_sync(...) emu_shfl_xor_sync(__LINE__, __VA_ARGS__)
+#define __shfl_down_sync(...) emu_shfl_down_sync(__LINE__, __VA_ARGS__)
+#define __ballot_sync(...) emu_ballot_sync(__LINE__, __VA_ARGS__)
+#define __all_sync(...) emu_all_sync(__LINE__, __VA_ARGS__)
+#define __any_sync(...) emu_any_sync(__LINE__, __VA_ARGS__)
+#define __reduce_max_sync(...) emu_reduce_max_sync(__LINE__, __VA_ARGS__)
+#define __reduce_min_sync(...) emu_reduce_min_sync(__LINE__, __VA_ARGS__)
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __ffs(int v) { return __ffs((unsigned)v); }
 

@@ -158,6 +158,14 @@ def test_results_do_not_depend_on_the_lane_schedule(method):
         assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["status"], b["status"])
 
 
+def test_emulator_flags_collectives_entered_by_part_of_a_warp():
+    """The check that found the interior-point kernel's device hang: a shuffle
+    sequence behind a short-circuited `&&` is entered by one lane group only."""
+    lib = emu.load()
+    assert lib.emu_selftest(0) == 0
+    assert lib.emu_selftest(1) > 0
+
+
 def test_unsupported_requests_are_refused():
     w = triple_integrator_batch(2, N=64)
     assert emu.solve(w)["rc"] != 0  # n = 64: the CTA kernel's territory, not emulated
