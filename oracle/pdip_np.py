@@ -52,16 +52,24 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
     status = np.full(B, 1, dtype=np.int32)
     iters = np.zeros(B, dtype=np.int32)
     active = np.ones(B, dtype=bool)
-    hscale = np.maximum(1.0, np.abs(h).max(axis=1))
+    hscale = np.maximum(1.0, np.abs(h).max(axis=1, initial=0.0))
     qscale = np.maximum(1.0, np.abs(q).max(axis=1))
     for it in range(max_iter):
-        r_d = np.einsum("bij,bj->bi", P, u) + q + np.einsum("bmn,bm->bn", G, z)
-        r_p = np.einsum("bmn,bn->bm", G, u) + s - h
-        mu = (s * z).sum(axis=1) / m
+        Pu = np.einsum("bij,bj->bi", P, u)
+        Gtz = np.einsum("bmn,bm->bn", G, z)
+        Gu = np.einsum("bmn,bn->bm", G, u)
+        r_d = Pu + q + Gtz
+        r_p = Gu + s - h
+        mu = (s * z).sum(axis=1) / max(m, 1)
+        # relative criteria: each residual against the size of the terms it is the sum of
+        # (their rounding noise is the floor it can reach), the gap against the objective
+        dscale = np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtz)).max(axis=1))
+        pscale = np.maximum(hscale, np.maximum(np.abs(Gu), s).max(axis=1, initial=0.0))
+        obj = np.abs(np.einsum("bi,bi->b", u, 0.5 * Pu + q))
         done = (
-            (np.abs(r_d).max(axis=1) <= tol * qscale)
-            & (np.abs(r_p).max(axis=1) <= tol * hscale)
-            & (mu <= tol)
+            (np.abs(r_d).max(axis=1) <= tol * dscale)
+            & (np.abs(r_p).max(axis=1, initial=0.0) <= tol * pscale)
+            & (mu <= tol * (1.0 + obj))
         )
         newly = active & done
         status[newly] = 0
@@ -134,14 +142,19 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9):
             du = _solve(L, -(r1 + np.einsum("bmn,bm->bn", G, r2 / delta)))
             lam = lam + np.where(act, (r2 + np.einsum("bmn,bn->bm", G, du)) / delta, 0.0)
             up = up + du
-        viol = np.einsum("bmn,bn->bm", G, up) - h
+        Pu = np.einsum("bij,bj->bi", P, up)
+        Gtl = np.einsum("bmn,bm->bn", G, lam)
+        Gu = np.einsum("bmn,bn->bm", G, up)
+        viol = Gu - h
         zscale = np.maximum(1.0, np.abs(lam).max(axis=1, initial=0.0))[:, None]
-        r_d = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
+        dscale = np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1))
+        pscale = np.maximum(hscale[:, 0], np.abs(Gu).max(axis=1, initial=0.0))[:, None]
+        r_d = Pu + q + Gtl
         ok = (
-            (viol <= eps * hscale).all(axis=1)
-            & (np.abs(np.where(act, viol, 0.0)) <= eps * hscale).all(axis=1)
+            (viol <= eps * pscale).all(axis=1)
+            & (np.abs(np.where(act, viol, 0.0)) <= eps * pscale).all(axis=1)
             & (lam >= -eps * zscale).all(axis=1)
-            & (np.abs(r_d).max(axis=1) <= eps * qscale)
+            & (np.abs(r_d).max(axis=1) <= eps * dscale)
         )
         new = ok & ~accepted
         u_out[new], z_out[new] = up[new], lam[new]

@@ -254,19 +254,29 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             px0 += Pc[c * LDL + l] * xs[c];
             px1 += Pc[(c + 1) * LDL + l] * xs[c + 1];
         }
-        const T rd = (px0 + px1) + qj + pdip_gt_dot<T, LDG>(Gc, tv, m, l);
+        const T px = px0 + px1, gz = pdip_gt_dot<T, LDG>(Gc, tv, m, l);
+        const T rd = px + qj + gz;
         pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
-        T comp = T(0), rpabs = T(0);
+        T comp = T(0), rpabs = T(0), pabs = T(0);
 #pragma unroll
         for (int s = 0; s < MR; ++s) {
             rp[s] = rowvalid[s] ? gx[s] + sl[s] - hrow[s] : T(0);
             rpabs = fmax(rpabs, abs_(rp[s]));
-            if (rowvalid[s]) comp += sl[s] * z[s];
+            if (rowvalid[s]) {
+                comp += sl[s] * z[s];
+                pabs = fmax(pabs, fmax(abs_(gx[s]), sl[s]));
+            }
         }
         const T mu = pdip_sum<T, NP>(comp) * minv;
         const T rdmax = pdip_max<T, NP>(abs_(rd));
         const T rpmax = pdip_max<T, NP>(rpabs);
-        const bool conv = rdmax <= tol * qscale && rpmax <= tol * hscale && mu <= tol;
+        // relative criteria (pdip_np.py): each residual against the size of the terms it is
+        // the sum of -- their rounding noise is the floor it can reach -- and the gap
+        // against the objective.  All reductions first, then the (short-circuiting) test.
+        const T dscale = fmax(qscale, pdip_max<T, NP>(fmax(abs_(px), abs_(gz))));
+        const T pscale = fmax(hscale, pdip_max<T, NP>(pabs));
+        const T obj = abs_(pdip_sum<T, NP>(x * (T(0.5) * px + qj)));
+        const bool conv = rdmax <= tol * dscale && rpmax <= tol * pscale && mu <= tol * (T(1) + obj);
         if (!done && conv) {
             st = 0;
             done = true;
@@ -373,7 +383,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             pdip_build<T, NP, LDG, LDL>(Hrow, Pc, Gc, wv, tv, m, l);
             const bool spd = pdip_cholesky<T, NP, LDL>(Hrow, Lc, dv, l);
             __syncwarp();
-            T rd = T(0);
+            T rd = T(0), pxp = T(0), gtl = T(0);
             // steps 0 .. 2 move (up, lam); the last pass only evaluates the residuals
             for (int step = 0; step <= 3; ++step) {
                 xs[l] = up;
@@ -387,7 +397,9 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
                     px0 += Pc[c * LDL + l] * xs[c];
                     px1 += Pc[(c + 1) * LDL + l] * xs[c + 1];
                 }
-                rd = (px0 + px1) + qj + pdip_gt_dot<T, LDG>(Gc, tv, m, l);  // r1
+                pxp = px0 + px1;
+                gtl = pdip_gt_dot<T, LDG>(Gc, tv, m, l);
+                rd = pxp + qj + gtl;  // r1
                 pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
 #pragma unroll
                 for (int s = 0; s < MR; ++s) gx[s] = rowvalid[s] ? gx[s] - hrow[s] : T(0);  // G up - h
@@ -412,7 +424,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             }
             // accept a primal feasible point with non-negative multipliers, zero
             // residual on A and a small stationarity residual
-            T worst_viol = T(0), worst_act = T(0), worst_neg = T(0), zmax = T(0);
+            T worst_viol = T(0), worst_act = T(0), worst_neg = T(0), zmax = T(0), gumax = T(0);
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
                 if (rowvalid[s]) {
@@ -420,6 +432,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
                     if (act[s]) worst_act = fmax(worst_act, abs_(gx[s]));
                     worst_neg = fmax(worst_neg, -lam[s]);
                     zmax = fmax(zmax, abs_(lam[s]));
+                    gumax = fmax(gumax, abs_(gx[s] + hrow[s]));  // |G up|
                 }
             }
             // (every reduction is a shuffle sequence the whole warp must enter: evaluate
@@ -428,8 +441,10 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
             const T g_viol = pdip_max<T, NP>(worst_viol), g_act = pdip_max<T, NP>(worst_act);
             const T g_neg = pdip_max<T, NP>(worst_neg), g_rd = pdip_max<T, NP>(abs_(rd));
-            const bool ok = spd && g_viol <= eps * hscale && g_act <= eps * hscale && g_neg <= eps * zscale &&
-                            g_rd <= eps * qscale;
+            const T dscale = fmax(qscale, pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl))));
+            const T pscale = fmax(hscale, pdip_max<T, NP>(gumax));
+            const bool ok = spd && g_viol <= eps * pscale && g_act <= eps * pscale && g_neg <= eps * zscale &&
+                            g_rd <= eps * dscale;
             if (need && ok) {
                 accepted = true;
                 x = up;

@@ -82,12 +82,12 @@ def test_triple_integrator_objective_and_model(N, batch):
     from qpmpc_b200.workloads import triple_integrator_batch
 
     w = triple_integrator_batch(batch, N=N, seed=N)
-    got = _solve(w, tol=1e-10, polish=False)
+    got = _solve(w, tol=1e-11, polish=False)
     assert (got["status"] == 0).all()
     assert got["iters"].max() <= 30
     k = 48
     P, q, G, h = _condensed(w, k)
-    model = pdip_batch(P, q, G, h, tol=1e-10, polish=False, max_iter=50)
+    model = pdip_batch(P, q, G, h, tol=1e-11, polish=False, max_iter=50)
     assert (np.abs(got["iters"][:k] - model["iters"]) <= 1).all()
     same = got["iters"][:k] == model["iters"]
     assert same.mean() >= 0.9
