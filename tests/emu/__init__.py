@@ -142,3 +142,36 @@ def pdip_core(P, q, G, h, np_, mr, dtype=0, max_iter=50, tol=1e-9, polish=True):
                                 st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
     assert rc == 0, rc
     return dict(U=U, z=Z[:, :m], status=st, iters=it)
+
+
+def integrate(w, U):
+    """qpmpc_b200_integrate on the emulator (mpc_integrate_kernel): X [B, N+1, nx]."""
+    d, ops, keep = describe(w)
+    U = np.ascontiguousarray(U, dtype=np.float64).reshape(w["batch"], -1)
+    X = np.full((w["batch"], w["N"] + 1, w["nx"]), np.nan)
+    with _Checked() as lib:
+        rc = lib.emu_integrate(ctypes.byref(d), ctypes.byref(ops), _ptr(U), _ptr(X))
+    assert rc == 0, rc
+    return X
+
+
+def pendulum_closed_loop(w, cycles, substeps=15, length=0.6, gravity=9.81, method="active_set"):
+    """qpmpc_b200_pendulum_closed_loop on the emulator: pendulum_step_kernel and the
+    fused solve alternate; returns (trajectory [cycles+1, B, 4], unsolved count)."""
+    from qpmpc_b200 import _capi
+
+    B, N = w["batch"], w["N"]
+    w = dict(w, goal=np.zeros((B, 4)), targets=np.zeros((B, N * 4)), x0=w["x0"].copy())
+    meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}[method]
+    d, ops, keep = describe(w, meth)
+    U, st, it = np.zeros((B, N)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    outs = _capi.Outputs(_ptr(U), _ptr(st), _ptr(it), None)
+    v = np.ascontiguousarray(w["v_target"], dtype=np.float64)
+    traj = np.full((cycles + 1, B, 4), np.nan)
+    unsolved = np.zeros(1, np.int32)
+    loop = _capi.ClosedLoop(int(cycles), int(substeps), w["T"] / substeps, w["T"], length, gravity,
+                            _ptr(v), _ptr(traj), _ptr(unsolved))
+    with _Checked() as lib:
+        rc = lib.emu_pendulum_closed_loop(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), ctypes.byref(loop))
+    assert rc == 0, rc
+    return traj, int(unsolved[0])

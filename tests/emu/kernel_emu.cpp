@@ -17,6 +17,9 @@
 
 #include "qpmpc_b200/csrc/mpc_host_params.h"
 #include "qpmpc_b200/csrc/mpc_pdip.cuh"  // brings mpc_common.cuh and mpc_kernels.cuh
+#include "qpmpc_b200/csrc/mpc_cta_kernel.cuh"
+#include "qpmpc_b200/csrc/mpc_integrate.cuh"
+#include "qpmpc_b200/csrc/mpc_plant.cuh"
 
 namespace qpmpc {
 alignas(16) unsigned char smem_raw[256 * 1024];  // what `extern __shared__` names in the kernels
@@ -109,6 +112,23 @@ int condense(SolveParams p, int wpc) {
     return 0;
 }
 
+
+// launch_solve_cta / launch_condense_cta (qpmpc_b200.cu): one CTA per instance
+template <typename T>
+int solve_cta(SolveParams p, int threads) {
+    p.toeplitz = env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0;
+    const size_t smem = (size_t)cta_layout(p.n, p.m, p.nx, (int)sizeof(T)).total * sizeof(T);
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    launch(p.batch, threads, smem, [&]() { mpc_solve_cta_kernel<T>(p); });
+    return 0;
+}
+template <typename T>
+int condense_cta(const SolveParams &p) {
+    const size_t smem = (size_t)cta_layout(p.n, p.m, p.nx, (int)sizeof(T)).total * sizeof(T);
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    launch(p.batch, 256, smem, [&]() { mpc_condense_cta_kernel<T>(p); });
+    return 0;
+}
 
 // ---- pdip_core() on explicit QPs (P, q, G, h given), one emulated warp ------
 // `count` QPs (count <= 32 / NP) side by side, laid out as the kernel lays
@@ -225,7 +245,13 @@ int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpm
     p.iters = out->iters;
     p.Z = out->Z;
     Variant v;
-    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    const bool warp_ok = pick_variant(p.n, p.m, &v);
+    if (d->method != QPMPC_B200_PDIP && (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0)) {
+        int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
+        threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
+        return solve_cta<double>(p, threads);
+    }
+    if (!warp_ok) return QPMPC_B200_EUNSUPPORTED;
     const int key = v.np * 10 + v.mr;
     if (d->method == QPMPC_B200_PDIP) {
         p.max_iter = d->max_iter > 0 ? d->max_iter : 50;
@@ -270,7 +296,7 @@ int emu_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const 
     p.phi_last = out->phi_last;
     p.psi_last = out->psi_last;
     Variant v;
-    if (!pick_variant(p.n, p.m, &v)) return QPMPC_B200_ESHAPE;
+    if (!pick_variant(p.n, p.m, &v) || env_int("QPMPC_B200_FORCE_CTA", 0) != 0) return condense_cta<double>(p);
     switch (v.np * 10 + v.mr) {
         case 82: return condense<double, 8, 2>(p, 2);
         case 84: return condense<double, 8, 4>(p, 2);
@@ -280,6 +306,66 @@ int emu_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const 
         case 324: return condense<double, 32, 4>(p, 2);
     }
     return QPMPC_B200_ESHAPE;
+}
+
+// qpmpc_b200_integrate with host pointers (mpc_integrate_kernel).
+int emu_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *U, void *X) {
+    if (!d || !in || !U || !X || !in->A || !in->B || !in->x0 || d->dtype != QPMPC_B200_F64) return QPMPC_B200_EINVAL;
+    IntegrateParams p;
+    p.batch = d->batch;
+    p.N = d->N;
+    p.nx = d->nx;
+    p.nu = d->nu;
+    p.A = in->A;
+    p.B = in->B;
+    p.x0 = in->x0;
+    p.U = U;
+    p.X = X;
+    auto ltv = [](int mode) { return mode == QPMPC_B200_SHARED_LTV || mode == QPMPC_B200_BATCH_LTV; };
+    auto per = [](int mode) { return mode == QPMPC_B200_BATCH_LTI || mode == QPMPC_B200_BATCH_LTV; };
+    p.sA = ltv(d->mode_A) ? d->nx * d->nx : 0;
+    p.sB = ltv(d->mode_B) ? d->nx * d->nu : 0;
+    p.bA = per(d->mode_A) ? (long long)d->nx * d->nx * (ltv(d->mode_A) ? d->N : 1) : 0;
+    p.bB = per(d->mode_B) ? (long long)d->nx * d->nu * (ltv(d->mode_B) ? d->N : 1) : 0;
+    p.bx0 = d->mode_x0 == QPMPC_B200_VEC_BATCH ? d->nx : 0;
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    launch(grid, threads, 0, [&]() { mpc_integrate_kernel<double>(p); });
+    return 0;
+}
+
+// qpmpc_b200_pendulum_closed_loop with host pointers: pendulum_step_kernel and the
+// fused solve alternate exactly as in qpmpc_b200.cu.
+int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                             const qpmpc_b200_closed_loop *loop) {
+    if (!d || !in || !out || !loop || d->nx != 4 || d->nu != 1 || d->dtype != QPMPC_B200_F64) return QPMPC_B200_EINVAL;
+    PendulumStepParams pp;
+    pp.batch = d->batch;
+    pp.N = d->N;
+    pp.n = d->N * d->nu;
+    pp.dt = loop->dt;
+    pp.T = loop->sampling_period;
+    pp.g = loop->gravity;
+    pp.omega2 = loop->gravity / loop->length;
+    pp.state = const_cast<void *>(in->x0);
+    pp.U = out->U;
+    pp.status = out->status;
+    pp.v_target = loop->v_target;
+    pp.goal = const_cast<void *>(in->goal);
+    pp.targets = const_cast<void *>(in->targets);
+    pp.unsolved = loop->unsolved;
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    auto step = [&](int substeps, int slot) {
+        pp.substeps = substeps;
+        pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 4 * 8 : nullptr;
+        launch(grid, threads, 0, [&]() { pendulum_step_kernel<double>(pp); });
+    };
+    step(0, 0);
+    for (int c = 0; c < loop->cycles; ++c) {
+        const int rc = emu_solve(d, in, out, 0);
+        if (rc) return rc;
+        step(loop->substeps, c + 1);
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -254,6 +254,27 @@ inline void __syncthreads() {
     c->state[c->cur] = emu::PARKED;
     emu::yield();
 }
+// __syncthreads_or: park, combine, park again (nobody may overwrite its slot
+// before everybody has read it).  Every thread of the CTA must call it.
+inline int __syncthreads_or(int pred) {
+    emu::Cta *c = emu::current();
+    emu::put<int>(pred != 0);
+    __syncthreads();
+    int any = 0;
+    for (int t = 0; t < c->nthreads; ++t) {
+        int v;
+        memcpy(&v, &c->slot[t], sizeof(int));
+        any |= v;
+    }
+    __syncthreads();
+    return any;
+}
+template <typename V>
+inline V atomicAdd(V *addr, V v) {  // the schedule is sequential
+    const V old = *addr;
+    *addr = old + v;
+    return old;
+}
 template <typename V>
 inline V emu_shfl_sync(int line, unsigned m, V v, int src, int width = 32) {
     const int lane = emu::lane_id();
@@ -326,6 +347,16 @@ inline double __longlong_as_double(long long r) {
     double v;
     memcpy(&v, &r, 8);
     return v;
+}
+inline long long __double_as_longlong(double v) {
+    long long r;
+    memcpy(&r, &v, 8);
+    return r;
+}
+inline int __float_as_int(float v) {
+    int r;
+    memcpy(&r, &v, 4);
+    return r;
 }
 inline float __int_as_float(int r) {
     float v;

@@ -2,8 +2,9 @@
 
 ``tests/emu/`` compiles the DEVICE SOURCE of the hot path
 (``qpmpc_b200/csrc/mpc_kernels.cuh``: staging, condensing, Cholesky, the dual
-active-set iteration, outputs; ``mpc_pdip.cuh``: the interior-point kernel) for
-the host -- one fiber per CUDA thread, every warp-level synchronisation a
+active-set iteration, outputs; ``mpc_cta_kernel.cuh``: the CTA-per-instance
+kernels; ``mpc_pdip.cuh``: the interior-point kernel; ``mpc_integrate.cuh``,
+``mpc_plant.cuh``) for the host -- one fiber per CUDA thread, every warp-level synchronisation a
 scheduling point, shared memory NaN-poisoned, bulk-TMA copies done at issue
 time -- and drives it through the product's own descriptor-to-parameter code.
 The results are held to the GPU bars (``tests/test_gpu_parity.py``): condensing
@@ -158,6 +159,74 @@ def test_results_do_not_depend_on_the_lane_schedule(method):
         assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["status"], b["status"])
 
 
+def test_cta_kernel_long_horizon_and_forced_small_shapes(monkeypatch):
+    """mpc_solve_cta_kernel (one CTA per instance): the N = 64 sweep point, and the
+    same kernel forced onto small shapes (block-wide reductions, __syncthreads_or)."""
+    _check(triple_integrator_batch(2, N=64, seed=64))
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    for w in (triple_integrator_batch(3, seed=21), pendulum_batch(3), humanoid_batch(3),
+              random_batch(3, 7, 5, 2, 3, seed=23, ltv=True)):
+        _check(w)
+    inf = triple_integrator_batch(4, seed=11)
+    inf["x0"][::2, 2] = 5.0
+    _check(inf)
+
+
+def test_cta_condense_kernel_matches_reference_fields(monkeypatch):
+    """mpc_condense_cta_kernel against the reference's MPCQP fields (N = 64 golden
+    fixture natively, two more through QPMPC_B200_FORCE_CTA)."""
+    for name, force in (("triple_integrator_N64", "0"), ("pendulum", "1"), ("random_ltv_cd", "1")):
+        monkeypatch.setenv("QPMPC_B200_FORCE_CTA", force)
+        g = load_golden(name)
+        out = emu.condense(_golden_workload(g))
+        for field in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last"):
+            ref = g[f"ref_{field}"]
+            got = out[field][0].reshape(ref.shape)
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (name, field)
+
+
+def test_integrate_kernel_matches_the_host_mirror():
+    """mpc_integrate_kernel == MPCProblem.integrate (qpmpc/mpc_problem.py:316-335)."""
+    w = random_batch(5, 6, 3, 2, 2, seed=3, ltv=True)
+    U = np.random.default_rng(0).standard_normal((5, 6, 2))
+    X = emu.integrate(w, U)
+    for b in range(5):
+        x = w["x0"][b].copy()
+        for k in range(6):
+            assert np.abs(X[b, k] - x).max() <= 1e-12
+            x = w["A"][b, k] @ x + w["B"][b, k] @ U[b, k]
+        assert np.abs(X[b, -1] - x).max() <= 1e-12
+
+
+@pytest.mark.parametrize("method", ["active_set", "pdip"])
+def test_pendulum_closed_loop_matches_the_cpu_loop(method):
+    """BASELINE config 3 pattern (examples/wheeled_inverted_pendulum.py:99-118):
+    pendulum_step_kernel + fused solve, 12 cycles, against oracle + host plant."""
+    from qpmpc_b200.systems import WheeledInvertedPendulum
+    from qpmpc_b200.workloads import pendulum_targets
+
+    w = pendulum_batch(6, seed=1)
+    cycles, substeps = 12, 15
+    got, unsolved = emu.pendulum_closed_loop(w, cycles, substeps, method=method)
+    pend, state, ref = WheeledInvertedPendulum(), w["x0"].copy(), [w["x0"].copy()]
+    wc = dict(w)
+    for _ in range(cycles):
+        wc["x0"] = state
+        wc["targets"], wc["goal"] = pendulum_targets(state, w["v_target"], w["N"], w["T"])
+        sol = _oracle(wc)
+        assert (sol["status"] == 0).all()
+        state = np.stack([_advance(pend, state[b], sol["U"][b, 0], w["T"], substeps) for b in range(6)])
+        ref.append(state.copy())
+    assert unsolved == 0
+    assert np.abs(got - np.stack(ref)).max() <= 1e-6
+
+
+def _advance(pend, x, u, T, substeps):
+    for _ in range(substeps):
+        x = pend.integrate(x, u, T / substeps)
+    return x
+
+
 def test_emulator_flags_collectives_entered_by_part_of_a_warp():
     """The check that found the interior-point kernel's device hang: a shuffle
     sequence behind a short-circuited `&&` is entered by one lane group only."""
@@ -168,7 +237,7 @@ def test_emulator_flags_collectives_entered_by_part_of_a_warp():
 
 def test_unsupported_requests_are_refused():
     w = triple_integrator_batch(2, N=64)
-    assert emu.solve(w)["rc"] != 0  # n = 64: the CTA kernel's territory, not emulated
+    assert emu.solve(w, method="pdip")["rc"] == -5  # n = 64: QPMPC_B200_EUNSUPPORTED for the interior point
     bad = triple_integrator_batch(2)
     bad["w_u"] = 0.0
     assert emu.solve(bad)["rc"] == -3  # QPMPC_B200_EWEIGHT, as check_desc says on the device path
