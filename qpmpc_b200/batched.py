@@ -18,6 +18,7 @@ shared by the batch or per instance, and either time-invariant or per step:
 """
 
 import ctypes
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -401,6 +402,10 @@ def solve_mpc_batch(
     meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}.get(method)
     if meth is None:
         raise ProblemDefinitionError(f"unknown method {method!r}")
+    if meth == _capi.PDIP and os.environ.get("QPMPC_B200_ENABLE_PDIP", "0") in ("", "0"):
+        raise BackendError(
+            'method="pdip" is experimental (validated on the host emulator, not yet on a device: '
+            "DESIGN.md section 2b); set QPMPC_B200_ENABLE_PDIP=1 to use it")
     desc = problem.desc(meth, max_iter, tol, polish)
     B, n, m = problem.batch_size, problem.nb_vars, problem.nb_rows
     with torch.cuda.device(problem.device):

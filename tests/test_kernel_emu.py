@@ -20,6 +20,8 @@ the opposite order -- a result that changes exposes a missing
 TMA, mbarriers, timing).
 """
 
+import os
+
 import numpy as np
 import pytest
 
@@ -241,3 +243,53 @@ def test_unsupported_requests_are_refused():
     bad = triple_integrator_batch(2)
     bad["w_u"] = 0.0
     assert emu.solve(bad)["rc"] == -3  # QPMPC_B200_EWEIGHT, as check_desc says on the device path
+
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+# QPMPC_EMU_EXAMPLES=<n> turns the fixed 25-example run into a randomised search
+_N_EX = int(os.environ.get("QPMPC_EMU_EXAMPLES", "25"))
+
+
+@settings(max_examples=_N_EX, deadline=None, derandomize=(_N_EX == 25))
+@given(N=st.integers(1, 12), nx=st.integers(1, 6), nu=st.integers(1, 3), nc=st.integers(1, 4),
+       ltv=st.booleans(), with_C=st.booleans(), with_D=st.booleans(),
+       cost=st.sampled_from(["terminal", "stage", "both"]), shared=st.booleans(),
+       hard=st.booleans(), seed=st.integers(0, 99999))
+def test_random_problems_both_methods(N, nx, nu, nc, ltv, with_C, with_D, cost, shared, hard, seed):
+    """The GPU property test (tests/test_properties.py) on the emulator, for both
+    methods: random shapes and operand patterns, optionally badly scaled (large
+    states against tight bounds: infeasible and nearly infeasible instances).
+    Same solved set as the oracle for the active-set kernel; the interior point
+    never reports an infeasible instance solved, may give up on a feasible one
+    only if it is numerically degenerate, and agrees wherever both solve --
+    errors relative to |U|, which reaches 1e4 on the hard instances."""
+    if not (with_C or with_D):
+        with_D = True
+    w = random_batch(4, N, nx, nu, nc, seed=seed, with_C=with_C, with_D=with_D,
+                     w_t=None if cost == "stage" else 0.7, w_x=None if cost == "terminal" else 0.3, ltv=ltv)
+    if hard:
+        w["x0"] = w["x0"] * 20.0
+        w["e"] = w["e"] * 0.2
+    if shared and not ltv:
+        for k in ("A", "B", "C", "D", "e"):
+            if w[k] is not None:
+                w[k] = w[k][0]
+    ref = oracle.solve_batch(4, N, nx, nu, nc, oracle_ops(w), w["w_t"], w["w_x"], w["w_u"], want_kkt=True)
+    # instances the oracle itself cannot certify (|U| ~ 1e12 on numerically infeasible data) are not a reference
+    sane = (ref["status"] != 0) | (np.nan_to_num(ref["kkt"], nan=np.inf).max(axis=1) <= 1e-6)
+    feas = (ref["status"] == 0) & sane
+    scale = np.maximum(1.0, np.abs(np.nan_to_num(ref["U"])).max(axis=1))
+    a = emu.solve(w)
+    assert np.array_equal((a["status"] == 0)[sane], (ref["status"] == 0)[sane])
+    if feas.any():
+        assert (np.abs(a["U"][feas] - ref["U"][feas]).max(axis=1) / scale[feas]).max() <= U_TOL
+    b = emu.solve(w, method="pdip")
+    assert not (b["status"][ref["status"] != 0] == 0).any()
+    both = feas & (b["status"] == 0)
+    if not hard:
+        assert np.array_equal(both, feas)
+    if both.any():
+        assert (np.abs(b["U"][both] - ref["U"][both]).max(axis=1) / scale[both]).max() <= U_TOL
