@@ -40,6 +40,7 @@ def load():
     _lib = ctypes.CDLL(LIB_PATH)
     _lib.emu_divergent_collectives.restype = ctypes.c_long
     _lib.emu_selftest.restype = ctypes.c_long
+    _lib.emu_sync_points.restype = ctypes.c_long
     return _lib
 
 

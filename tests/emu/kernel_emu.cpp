@@ -230,6 +230,7 @@ long emu_selftest(int which) {
 int emu_smem_overruns(void) { return g_smem_overrun; }
 void emu_set_lane_order(int descending) { emu::lane_order() = descending; }
 long emu_divergent_collectives(void) { return emu::divergent_collectives(); }
+long emu_sync_points(void) { return emu::sync_points(); }
 
 // qpmpc_b200_solve with host pointers.  `wpc`: warps per CTA (<= 0: the launch default).
 int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out, int wpc) {

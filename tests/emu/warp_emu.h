@@ -123,8 +123,15 @@ inline void check_convergence(unsigned mask) {
         }
     }
 }
+// warp-level synchronisation points entered, summed over all threads (a proxy
+// for the length of the dependent chain: tools/emu_sync_profile.py)
+inline long &sync_points() {
+    static long count = 0;
+    return count;
+}
 inline void enter_sync(int line) {
     Cta *c = current();
+    ++sync_points();
     ++c->nsync[c->cur];
     c->site[c->cur] = line;
 }

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Warp-level synchronisation points per warp (shuffles, votes, reductions,
+__syncwarp) of the two solver kernels on samples of the BASELINE workloads,
+counted on the host emulator (tests/emu).  No GPU needed.  The kernels are
+latency-bound chains of such points, so the ratio is a first, hardware-free
+estimate of the interior-point kernel's cost relative to the active-set kernel
+(it ignores the arithmetic between the points, which is heavier for the
+interior point: m rank-one updates of H per iteration)."""
+
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import emu  # noqa: E402
+from qpmpc_b200.workloads import humanoid_batch, pendulum_batch, triple_integrator_batch  # noqa: E402
+
+lib = emu.load()
+B = 64
+for name, w, np_ in (("config 2: triple integrator N=16", triple_integrator_batch(B, seed=0), 16),
+                     ("config 3: pendulum N=12", pendulum_batch(B, seed=1), 16),
+                     ("config 4: humanoid N=16", humanoid_batch(B, seed=2), 16),
+                     ("config 5: triple integrator N=8", triple_integrator_batch(B, N=8, seed=3), 8),
+                     ("config 5: triple integrator N=32", triple_integrator_batch(16, N=32, seed=3), 32)):
+    row = {"workload": name, "instances": w["batch"]}
+    for method, kw in (("active_set", {}), ("pdip", {"tol": 1e-9}), ("pdip_tol1e-6", {"method": "pdip", "tol": 1e-6})):
+        before = lib.emu_sync_points()
+        got = emu.solve(w, **{"method": method, **kw})
+        warps = w["batch"] * np_ / 32.0
+        row[method] = {"sync_points_per_warp": round((lib.emu_sync_points() - before) / 32.0 / warps, 1),
+                       "iters_mean": round(float(got["iters"].mean()), 2),
+                       "solved": float((got["status"] == 0).mean())}
+    row["pdip_over_active_set"] = round(row["pdip"]["sync_points_per_warp"] / row["active_set"]["sync_points_per_warp"], 2)
+    print(json.dumps(row), flush=True)
