@@ -66,7 +66,7 @@ struct Idx {
 struct Cta {
     ucontext_t main_ctx;
     std::vector<ucontext_t> ctx;
-    std::vector<std::vector<char>> stack;
+    std::vector<char *> stack;  // from a pool that lives as long as the process (never zero-filled)
     std::vector<State> state;
     std::vector<uint64_t> slot;
     std::vector<uint64_t> nsync;     // warp-level synchronisation points entered, per thread
@@ -148,7 +148,7 @@ inline int warp_base() { return current()->cur / WARP * WARP; }
 
 // Run one CTA of `nthreads` threads to completion.
 inline void run_cta(int nthreads, Idx block_idx, Idx grid_dim, const std::function<void()> &body,
-                    size_t stack_bytes = 1 << 20) {
+                    size_t stack_bytes = 256 << 10) {
     Cta c;
     c.nthreads = nthreads;
     c.block_idx = block_idx;
@@ -162,10 +162,18 @@ inline void run_cta(int nthreads, Idx block_idx, Idx grid_dim, const std::functi
     c.nsync.assign(nthreads, 0);
     c.site.assign(nthreads, 0);
     current() = &c;
+    static std::vector<char *> pool;
+    static size_t pool_bytes = 0;
+    if (pool_bytes != stack_bytes) {
+        for (char *b : pool) free(b);
+        pool.clear();
+        pool_bytes = stack_bytes;
+    }
+    while ((int)pool.size() < nthreads) pool.push_back(static_cast<char *>(malloc(stack_bytes)));
     for (int t = 0; t < nthreads; ++t) {
-        c.stack[t].resize(stack_bytes);
+        c.stack[t] = pool[t];
         getcontext(&c.ctx[t]);
-        c.ctx[t].uc_stack.ss_sp = c.stack[t].data();
+        c.ctx[t].uc_stack.ss_sp = c.stack[t];
         c.ctx[t].uc_stack.ss_size = stack_bytes;
         c.ctx[t].uc_link = &c.main_ctx;
         makecontext(&c.ctx[t], trampoline, 0);

@@ -254,3 +254,18 @@ def test_gather_plans_world_size_two(batch):
         out = mgr.dict()
         mp.spawn(_gloo_worker, args=(2, port, batch, out), nprocs=2, join=True)
         assert out[0] and out[1]
+
+
+def test_product_library_is_not_a_host_emulation_build():
+    """QPMPC_HOST_EMU (host bodies for the inline-PTX helpers, used by tests/emu
+    only) never reaches the product: the build has no such flag, the library
+    exports nothing of the emulator and still contains sm_100a device code."""
+    import subprocess
+
+    from qpmpc_b200 import build
+
+    assert not any("HOST_EMU" in f for f in build.NVCC_FLAGS)
+    syms = subprocess.run(["nm", "-D", "--defined-only", build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "emu_" not in syms and "pdip_emu" not in syms
+    elf = subprocess.run(["cuobjdump", "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
