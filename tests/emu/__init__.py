@@ -29,6 +29,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get("QPMPC_EMU_LIB"):  # another build of kernel_emu.cpp, e.g. -march=native -ffp-contract=fast
+        _lib = ctypes.CDLL(os.environ["QPMPC_EMU_LIB"])
+        _lib.emu_divergent_collectives.restype = ctypes.c_long
+        _lib.emu_selftest.restype = ctypes.c_long
+        _lib.emu_sync_points.restype = ctypes.c_long
+        return _lib
     csrc = os.path.join(ROOT, "qpmpc_b200", "csrc")
     deps = [os.path.join(HERE, "kernel_emu.cpp"), os.path.join(HERE, "warp_emu.h"),
             os.path.join(ROOT, "include", "qpmpc_b200.h")]
