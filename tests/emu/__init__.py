@@ -73,7 +73,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
 
-def describe(w, method=0, max_iter=0, tol=0.0, flags=0):
+def describe(w, method=0, max_iter=0, tol=0.0, flags=0, dtype=np.float64):
     """(desc, operands, keep-alive arrays) of a workload dict, host pointers:
     the structs of include/qpmpc_b200.h filled the way BatchedMPCProblem fills them."""
     from qpmpc_b200 import _capi
@@ -81,18 +81,18 @@ def describe(w, method=0, max_iter=0, tol=0.0, flags=0):
 
     d, keep = _capi.Desc(), {}
     d.batch, d.N, d.nx, d.nu, d.nc = w["batch"], w["N"], w["nx"], w["nu"], w["nc"]
-    d.dtype = 0
+    d.dtype = 0 if dtype == np.float64 else 1
     for name in ("A", "B", "C", "D", "e"):
         arr, mode = w[name], 0
         if arr is not None:
             mode = {(False, False): 1, (False, True): 2, (True, False): 3, (True, True): 4}[operand_layout(w, name)]
-            keep[name] = np.ascontiguousarray(arr, dtype=np.float64)
+            keep[name] = np.ascontiguousarray(arr, dtype=dtype)
         setattr(d, "mode_" + name, mode)
     for name in ("x0", "goal", "targets"):
         arr, mode = w[name], 0
         if arr is not None:
             mode = 2 if arr.ndim == 2 else 1
-            keep[name] = np.ascontiguousarray(arr, dtype=np.float64)
+            keep[name] = np.ascontiguousarray(arr, dtype=dtype)
         setattr(d, "mode_" + name, mode)
     d.has_wt, d.has_wx = w["w_t"] is not None, w["w_x"] is not None
     d.w_t, d.w_x, d.w_u = float(w["w_t"] or 0.0), float(w["w_x"] or 0.0), w["w_u"]
@@ -101,21 +101,22 @@ def describe(w, method=0, max_iter=0, tol=0.0, flags=0):
     return d, ops, keep
 
 
-def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, descending=False):
-    """qpmpc_b200_solve on the emulator: mpc_solve_kernel / mpc_pdip_kernel."""
+def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, descending=False, dtype=np.float64):
+    """qpmpc_b200_solve on the emulator: mpc_solve_kernel / mpc_solve_cta_kernel /
+    mpc_pdip_kernel, in ``dtype`` (float64 or float32; U and z come back as float64)."""
     from qpmpc_b200 import _capi
 
     lib = load()
     meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}[method]
-    d, ops, keep = describe(w, meth, max_iter, tol, 0 if polish else _capi.FLAG_NO_POLISH)
+    d, ops, keep = describe(w, meth, max_iter, tol, 0 if polish else _capi.FLAG_NO_POLISH, dtype)
     B, n, m = w["batch"], w["N"] * w["nu"], w["N"] * w["nc"]
-    U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
+    U, Z = np.zeros((B, n), dtype=dtype), np.zeros((B, max(m, 1)), dtype=dtype)
     st, it = np.full(B, -1, np.int32), np.zeros(B, np.int32)
     outs = _capi.Outputs(_ptr(U), _ptr(st), _ptr(it), _ptr(Z))
     with _Checked() as lib:
         lib.emu_set_lane_order(int(descending))
         rc = lib.emu_solve(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), wpc)
-    return dict(rc=rc, U=U, status=st, iters=it, z=Z[:, :m])
+    return dict(rc=rc, U=U.astype(np.float64), status=st, iters=it, z=Z[:, :m].astype(np.float64))
 
 
 def condense(w, fields=("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")):

@@ -178,6 +178,28 @@ int pdip_core_run(int count, int n, int m, const double *P, const double *q, con
     return 0;
 }
 
+// the active-set kernels of one dtype: warp kernel variants, or the CTA kernel
+template <typename T>
+int emu_solve_t(const qpmpc_b200_desc *d, SolveParams &p, int wpc) {
+    Variant v;
+    const bool warp_ok = pick_variant(p.n, p.m, &v);
+    if (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0) {
+        int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
+        threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
+        return solve_cta<T>(p, threads);
+    }
+    if (wpc <= 0) wpc = 8;
+    switch (v.np * 10 + v.mr) {
+        case 82: return solve<T, 8, 2, true>(p, wpc);
+        case 84: return solve<T, 8, 4, true>(p, wpc);
+        case 162: return solve<T, 16, 2, true>(p, wpc);
+        case 164: return solve<T, 16, 4, false>(p, wpc);
+        case 322: return solve<T, 32, 2, false>(p, wpc);
+        case 324: return solve<T, 32, 4, false>(p, wpc);
+    }
+    return QPMPC_B200_ESHAPE;
+}
+
 }  // namespace
 
 extern "C" {
@@ -237,7 +259,6 @@ int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpm
     int rc = check_desc(d, in);
     if (rc) return rc;
     if (!out || !out->U || !out->status) return QPMPC_B200_EINVAL;
-    if (d->dtype != QPMPC_B200_F64) return QPMPC_B200_EUNSUPPORTED;  // the emulator build instantiates double only
     if (d->batch == 0) return 0;
     SolveParams p;
     fill_params(d, in, &p);
@@ -245,20 +266,14 @@ int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpm
     p.status = out->status;
     p.iters = out->iters;
     p.Z = out->Z;
-    Variant v;
-    const bool warp_ok = pick_variant(p.n, p.m, &v);
-    if (d->method != QPMPC_B200_PDIP && (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0)) {
-        int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
-        threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
-        return solve_cta<double>(p, threads);
-    }
-    if (!warp_ok) return QPMPC_B200_EUNSUPPORTED;
-    const int key = v.np * 10 + v.mr;
     if (d->method == QPMPC_B200_PDIP) {
+        // as solve_impl: double precision, warp kernel shapes only
+        Variant v;
+        if (d->dtype != QPMPC_B200_F64 || !pick_variant(p.n, p.m, &v)) return QPMPC_B200_EUNSUPPORTED;
         p.max_iter = d->max_iter > 0 ? d->max_iter : 50;
         const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
         if (wpc <= 0) wpc = 4;
-        switch (key) {
+        switch (v.np * 10 + v.mr) {
             case 82: return pdip<double, 8, 2>(p, polish, wpc);
             case 84: return pdip<double, 8, 4>(p, polish, wpc);
             case 162: return pdip<double, 16, 2>(p, polish, wpc);
@@ -268,16 +283,7 @@ int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpm
         }
         return QPMPC_B200_ESHAPE;
     }
-    if (wpc <= 0) wpc = 8;
-    switch (key) {
-        case 82: return solve<double, 8, 2, true>(p, wpc);
-        case 84: return solve<double, 8, 4, true>(p, wpc);
-        case 162: return solve<double, 16, 2, true>(p, wpc);
-        case 164: return solve<double, 16, 4, false>(p, wpc);
-        case 322: return solve<double, 32, 2, false>(p, wpc);
-        case 324: return solve<double, 32, 4, false>(p, wpc);
-    }
-    return QPMPC_B200_ESHAPE;
+    return d->dtype == QPMPC_B200_F64 ? emu_solve_t<double>(d, p, wpc) : emu_solve_t<float>(d, p, wpc);
 }
 
 // qpmpc_b200_condense with host pointers.
