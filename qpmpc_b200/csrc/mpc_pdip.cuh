@@ -34,7 +34,7 @@
 // the exact oracle without a GPU.
 #pragma once
 
-#include "mpc_common.cuh"
+#include "mpc_kernels.cuh"  // stage_inputs, condense_dispatch, fsolve
 
 namespace qpmpc {
 
@@ -135,6 +135,46 @@ __device__ __forceinline__ T pdip_solve(const T *Lc, const T *dv, T w, int l) {
     return x;
 }
 
+// LS variant of the two substitutions: L is replaced once per factorisation by
+// its inverse (column l of L^-1 is a lane-local forward substitution with
+// L y = e_l, as the active-set kernel builds J), after which a solve is two
+// matrix-vector products through shared memory -- 4 __syncwarp instead of 2 NP
+// dependent shuffles.  On exit Lc holds L^-1 by columns: Lc[k*LDL + r] = Linv[r][k].
+template <typename T, int NP, int LDL>
+__device__ __forceinline__ void pdip_invert(T *Lc, const T *dv, int l) {
+    T jr[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) jr[c] = (c == l) ? T(1) : T(0);
+    fsolve<T, NP, LDL, 1>(Lc, dv, jr, jr, jr);
+    __syncwarp();  // every lane has read L
+#pragma unroll
+    for (int c = 0; c < NP; ++c) Lc[l * LDL + c] = jr[c];
+    __syncwarp();
+}
+// Component l of H^-1 w = L^-T (L^-1 w); xs [NP] is the exchange vector (free on entry and on exit).
+template <typename T, int NP, int LDL>
+__device__ __forceinline__ T pdip_solve_inv(const T *Li, T *xs, T w, int l) {
+    xs[l] = w;
+    __syncwarp();
+    T y0 = T(0), y1 = T(0);
+#pragma unroll
+    for (int k = 0; k < NP; k += 2) {
+        y0 += Li[k * LDL + l] * xs[k];
+        y1 += Li[(k + 1) * LDL + l] * xs[k + 1];
+    }
+    __syncwarp();
+    xs[l] = y0 + y1;
+    __syncwarp();
+    T x0 = T(0), x1 = T(0);
+#pragma unroll
+    for (int c = 0; c < NP; c += 2) {
+        x0 += Li[l * LDL + c] * xs[c];
+        x1 += Li[l * LDL + c + 1] * xs[c + 1];
+    }
+    __syncwarp();
+    return x0 + x1;
+}
+
 // Row l of H = P + G' diag(wv) G into Hrow and, in the same pass over the
 // rows, g = sum_row G[row, l] tv[row].
 template <typename T, int NP, int LDG, int LDL>
@@ -212,7 +252,7 @@ __device__ __forceinline__ T pdip_step(const T (&sl)[MR], const T (&z)[MR], cons
 //        iterations
 // Scratch: Lc [NP*LDL], xs [NP], dv [NP], wv [MP], tv [MP].
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR>
+template <typename T, int NP, int MR, bool LS = false>
 __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const T *hs, T *Lc, T *xs, T *dv, T *wv,
                                           T *tv, int m, int l, bool valid, int max_iter, T tol, bool polish,
                                           T &x_out, T (&z_out)[MR], int &st_out, int &it_out) {
@@ -303,7 +343,8 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             st = 3;  // numerical failure: H lost positive definiteness
             done = true;
         }
-        T du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+        if (LS) pdip_invert<T, NP, LDL>(Lc, dv, l);
+        T du = LS ? pdip_solve_inv<T, NP, LDL>(Lc, xs, rhs, l) : pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
         xs[l] = du;
         __syncwarp();
         pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
@@ -329,7 +370,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
         }
         __syncwarp();
         rhs = -rd - pdip_gt_dot<T, LDG>(Gc, tv, m, l);
-        du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+        du = LS ? pdip_solve_inv<T, NP, LDL>(Lc, xs, rhs, l) : pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
         xs[l] = du;
         __syncwarp();
         pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
@@ -383,6 +424,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             pdip_build<T, NP, LDG, LDL>(Hrow, Pc, Gc, wv, tv, m, l);
             const bool spd = pdip_cholesky<T, NP, LDL>(Hrow, Lc, dv, l);
             __syncwarp();
+            if (LS) pdip_invert<T, NP, LDL>(Lc, dv, l);
             T rd = T(0), pxp = T(0), gtl = T(0);
             // steps 0 .. 2 move (up, lam); the last pass only evaluates the residuals
             for (int step = 0; step <= 3; ++step) {
@@ -412,7 +454,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
                 }
                 __syncwarp();
                 const T rhs = -(rd + pdip_gt_dot<T, LDG>(Gc, tv, m, l));
-                const T du = pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
+                const T du = LS ? pdip_solve_inv<T, NP, LDL>(Lc, xs, rhs, l) : pdip_solve<T, NP, LDL>(Lc, dv, rhs, l);
                 __syncwarp();
                 xs[l] = du;
                 __syncwarp();
@@ -463,16 +505,10 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
     it_out = it;
 }
 
-}  // namespace qpmpc
-
-#include "mpc_kernels.cuh"
-
-namespace qpmpc {
-
 // ---------------------------------------------------------------------------
 // The fused kernel: stage, condense, interior point, outputs.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR>  // @phase pdip kernel
+template <typename T, int NP, int MR, bool LS>  // @phase pdip kernel
 __global__ void __launch_bounds__(256, 1) mpc_pdip_kernel(const SolveParams p, int polish) {
     using L = PdipLay<T, NP, MR>;
     constexpr int IPW = 32 / NP;
@@ -524,8 +560,8 @@ __global__ void __launch_bounds__(256, 1) mpc_pdip_kernel(const SolveParams p, i
 
     T x, z[MR];
     int st, it;
-    pdip_core<T, NP, MR>(Pc, qj, Gc, hs, Lc, xs, dv, wv, tv, m, l, valid, p.max_iter, (T)p.tol, polish != 0, x, z, st,
-                         it);
+    pdip_core<T, NP, MR, LS>(Pc, qj, Gc, hs, Lc, xs, dv, wv, tv, m, l, valid, p.max_iter, (T)p.tol, polish != 0, x, z,
+                             st, it);
 
     // phase D: outputs
     {

@@ -88,7 +88,10 @@ int pdip(SolveParams p, int polish, int wpc) {
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     const int ipc = IPW * wpc;
-    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR>(p, polish); });
+    if (env_int("QPMPC_B200_PDIP_SOLVE", 1) != 0)
+        launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR, true>(p, polish); });
+    else
+        launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR, false>(p, polish); });
     return 0;
 }
 
@@ -135,7 +138,7 @@ int condense_cta(const SolveParams &p) {
 // them out: P, G by columns with the kernel's leading dimensions, padding
 // variables with P = identity.  Lets the tests reach cases the MPC front-end
 // never produces (infeasible rows, m = 0) and the float instantiation.
-template <typename T, int NP, int MR>
+template <typename T, int NP, int MR, bool LS>
 int pdip_core_run(int count, int n, int m, const double *P, const double *q, const double *G, const double *h,
                   int max_iter, double tol, int polish, double *U, double *Z, int *status, int *iters) {
     using L = PdipLay<T, NP, MR>;
@@ -164,8 +167,8 @@ int pdip_core_run(int count, int n, int m, const double *P, const double *q, con
         const T qj = l < n ? (T)q[(size_t)src * n + l] : T(0);
         T x, z[MR];
         int st, it;
-        pdip_core<T, NP, MR>(wk + L::oP, qj, wk + L::fixed, wk + L::oH, wk + L::oL, xs, dv, wv, tv, m, l, valid,
-                             max_iter, (T)tol, polish != 0, x, z, st, it);
+        pdip_core<T, NP, MR, LS>(wk + L::oP, qj, wk + L::fixed, wk + L::oH, wk + L::oL, xs, dv, wv, tv, m, l, valid,
+                                 max_iter, (T)tol, polish != 0, x, z, st, it);
         if (!valid) return;
         if (l < n) U[(size_t)sub * n + l] = (double)x;
         for (int s = 0; s < MR; ++s)
@@ -207,9 +210,15 @@ extern "C" {
 int pdip_emu_solve(int dtype, int np, int mr, int count, int n, int m, const double *P, const double *q,
                    const double *G, const double *h, int max_iter, double tol, int polish, double *U, double *Z,
                    int *status, int *iters) {
-#define CASE(T, NP, MR)       \
-    if (np == NP && mr == MR) \
-        return pdip_core_run<T, NP, MR>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status, iters);
+    // as launch_pdip; the float instantiation (not offered through the ABI) only works with the
+    // substitutions: an explicit L^-1 of the late, ill-conditioned H is beyond single precision
+    const bool ls = dtype == 0 && env_int("QPMPC_B200_PDIP_SOLVE", 1) != 0;
+#define CASE(T, NP, MR)                                                                                             \
+    if (np == NP && mr == MR)                                                                                       \
+        return ls ? pdip_core_run<T, NP, MR, true>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status,    \
+                                                   iters)                                                           \
+                  : pdip_core_run<T, NP, MR, false>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status,   \
+                                                    iters);
     if (dtype == 0) {
         CASE(double, 8, 2)
         CASE(double, 8, 4)
