@@ -124,9 +124,10 @@ int launch_pdip(SolveParams p, int polish, cudaStream_t stream) {
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     const int ipc = IPW * wpc;
-    // The two substitutions per solve: through L^-1 and shared memory (LS, 4 __syncwarp) or by
-    // 2 NP dependent shuffles.  Default LS; QPMPC_B200_PDIP_SOLVE=0 selects the shuffles (A/B).
-    const bool ls = env_int("QPMPC_B200_PDIP_SOLVE", 1) != 0;
+    // The two substitutions per solve: by 2 NP dependent shuffles (default: backward stable), or
+    // through L^-1 and shared memory (LS, QPMPC_B200_PDIP_SOLVE=1: 4 __syncwarp per solve, but
+    // the explicit inverse of the late, ill-conditioned H costs robustness at tight tolerances).
+    const bool ls = env_int("QPMPC_B200_PDIP_SOLVE", 0) != 0;
     auto kern = ls ? mpc_pdip_kernel<T, NP, MR, true> : mpc_pdip_kernel<T, NP, MR, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;

@@ -88,7 +88,7 @@ int pdip(SolveParams p, int polish, int wpc) {
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     const int ipc = IPW * wpc;
-    if (env_int("QPMPC_B200_PDIP_SOLVE", 1) != 0)
+    if (env_int("QPMPC_B200_PDIP_SOLVE", 0) != 0)
         launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR, true>(p, polish); });
     else
         launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_pdip_kernel<T, NP, MR, false>(p, polish); });
@@ -212,7 +212,7 @@ int pdip_emu_solve(int dtype, int np, int mr, int count, int n, int m, const dou
                    int *status, int *iters) {
     // as launch_pdip; the float instantiation (not offered through the ABI) only works with the
     // substitutions: an explicit L^-1 of the late, ill-conditioned H is beyond single precision
-    const bool ls = dtype == 0 && env_int("QPMPC_B200_PDIP_SOLVE", 1) != 0;
+    const bool ls = dtype == 0 && env_int("QPMPC_B200_PDIP_SOLVE", 0) != 0;
 #define CASE(T, NP, MR)                                                                                             \
     if (np == NP && mr == MR)                                                                                       \
         return ls ? pdip_core_run<T, NP, MR, true>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status,    \

@@ -26,7 +26,10 @@ for name, w, np_ in (("config 2: triple integrator N=16", triple_integrator_batc
                      ("config 5: triple integrator N=8", triple_integrator_batch(B, N=8, seed=3), 8),
                      ("config 5: triple integrator N=32", triple_integrator_batch(16, N=32, seed=3), 32)):
     row = {"workload": name, "instances": w["batch"]}
-    for method, kw in (("active_set", {}), ("pdip", {"tol": 1e-9}), ("pdip_tol1e-6", {"method": "pdip", "tol": 1e-6})):
+    for method, kw, ls in (("active_set", {}, "0"), ("pdip", {"tol": 1e-9}, "0"),
+                           ("pdip_tol1e-6", {"method": "pdip", "tol": 1e-6}, "0"),
+                           ("pdip_LS", {"method": "pdip", "tol": 1e-9}, "1")):
+        os.environ["QPMPC_B200_PDIP_SOLVE"] = ls  # 1: solves through L^-1
         before = lib.emu_sync_points()
         got = emu.solve(w, **{"method": method, **kw})
         warps = w["batch"] * np_ / 32.0

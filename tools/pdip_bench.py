@@ -45,10 +45,11 @@ ref = oracle.solve_batch(w0["batch"], w0["N"], w0["nx"], w0["nu"], w0["nc"], ora
 
 variants = [
     ("active_set", dict(method="active_set"), {}),
-    ("pdip tol=1e-9 polish wpc=4", dict(method="pdip", tol=1e-9), {"QPMPC_B200_PDIP_WPC": "4"}),
-    ("pdip tol=1e-9 polish wpc=4 shuffle solves", dict(method="pdip", tol=1e-9),
+    ("pdip tol=1e-9 polish wpc=4", dict(method="pdip", tol=1e-9),
      {"QPMPC_B200_PDIP_WPC": "4", "QPMPC_B200_PDIP_SOLVE": "0"}),
-    ("pdip tol=1e-9 polish wpc=8", dict(method="pdip", tol=1e-9), {"QPMPC_B200_PDIP_WPC": "8", "QPMPC_B200_PDIP_SOLVE": "1"}),
+    ("pdip tol=1e-9 polish wpc=4 solves through L^-1", dict(method="pdip", tol=1e-9),
+     {"QPMPC_B200_PDIP_WPC": "4", "QPMPC_B200_PDIP_SOLVE": "1"}),
+    ("pdip tol=1e-9 polish wpc=8", dict(method="pdip", tol=1e-9), {"QPMPC_B200_PDIP_WPC": "8", "QPMPC_B200_PDIP_SOLVE": "0"}),
     ("pdip tol=1e-9 polish wpc=2", dict(method="pdip", tol=1e-9), {"QPMPC_B200_PDIP_WPC": "2"}),
     ("pdip tol=1e-6 polish wpc=4", dict(method="pdip", tol=1e-6), {"QPMPC_B200_PDIP_WPC": "4"}),
     ("pdip tol=1e-9 no polish wpc=4", dict(method="pdip", tol=1e-9, polish=False), {"QPMPC_B200_PDIP_WPC": "4"}),
