@@ -183,6 +183,21 @@ def test_single_precision_kernels_within_the_stated_tolerance(kind, monkeypatch)
     assert rel <= (2e-2 if kind in ("pendulum", "ti8") else 1e-4), rel
 
 
+@pytest.mark.parametrize("wpc", [1, 3, 5])
+def test_launch_geometry_knobs(wpc, monkeypatch):
+    """Other warps-per-CTA counts (QPMPC_B200_WPC / _PDIP_WPC: odd CTA sizes, ragged
+    last CTAs with unaligned bulk copies -> the cooperative staging fallback), a
+    smaller CTA for the CTA kernel, and the interior point's solves through L^-1."""
+    for w in (triple_integrator_batch(7, seed=31), pendulum_batch(5), random_batch(5, 5, 2, 2, 5, seed=8)):
+        _check(w, wpc=wpc)
+        _check(w, method="pdip", wpc=wpc)
+    monkeypatch.setenv("QPMPC_B200_PDIP_SOLVE", "1")
+    _check(triple_integrator_batch(7, seed=32), method="pdip", wpc=wpc)
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    monkeypatch.setenv("QPMPC_B200_CTA_THREADS", str(32 * wpc))
+    _check(humanoid_batch(2))
+
+
 def test_cta_kernel_long_horizon_and_forced_small_shapes(monkeypatch):
     """mpc_solve_cta_kernel (one CTA per instance): the N = 64 sweep point, and the
     same kernel forced onto small shapes (block-wide reductions, __syncthreads_or)."""
