@@ -79,10 +79,11 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
         iters[active] += 1
         W = z / s
         H = P + np.einsum("bmi,bm,bmj->bij", G, W, G)
-        try:
-            L = np.linalg.cholesky(H)
-        except np.linalg.LinAlgError:
-            status[active] = 2
+        L, spd = _cholesky_each(H)
+        lost = active & ~spd
+        status[lost] = 3  # H lost positive definiteness (numerically): the polish may still rescue it
+        active &= spd
+        if not active.any():
             break
         # predictor
         rhs = -r_d - np.einsum("bmn,bm->bn", G, W * r_p - z)
@@ -104,8 +105,11 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
         s = s + alpha * ds
         z = z + alpha * dz
     if polish:
-        up, zp, ok = _polish(P, q, G, h, u, s, z, polish_steps, delta, polish_rounds)
-        ok &= status == 0
+        # instances the iteration gave up on (cap, lost definiteness) are polished too: an accepted
+        # point is a KKT-certified solution wherever the iterate came from; they are held to the
+        # absolute form of the acceptance test (their iterate may be huge)
+        up, zp, ok = _polish(P, q, G, h, u, s, z, polish_steps, delta, polish_rounds, strict=status != 0)
+        status[ok] = 0
         u = np.where(ok[:, None], up, u)
         z = np.where(ok[:, None], zp, z)
     else:
@@ -121,8 +125,23 @@ def _step(s, z, ds, dz, frac):
     return np.minimum(1.0, frac * np.minimum(a_s, a_z))
 
 
-def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9):
+def _cholesky_each(H):
+    """Batched Cholesky that survives a failing member: (L, ok [B])."""
+    try:
+        return np.linalg.cholesky(H), np.ones(H.shape[0], dtype=bool)
+    except np.linalg.LinAlgError:
+        L, ok = np.zeros_like(H), np.zeros(H.shape[0], dtype=bool)
+        for b in range(H.shape[0]):
+            try:
+                L[b], ok[b] = np.linalg.cholesky(H[b]), True
+            except np.linalg.LinAlgError:
+                L[b] = np.eye(H.shape[1])
+        return L, ok
+
+
+def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9, strict=None):
     B = q.shape[0]
+    strict = np.zeros(B, dtype=bool) if strict is None else strict
     act = z > s
     lam = np.where(act, z, 0.0)
     up = u.copy()
@@ -134,7 +153,7 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9):
         if accepted.all():
             break
         H = P + np.einsum("bmi,bm,bmj->bij", G, act / delta, G)
-        L = np.linalg.cholesky(H)
+        L, spd = _cholesky_each(H)
         lam = np.where(act, lam, 0.0)
         for _ in range(steps):
             r1 = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
@@ -147,11 +166,15 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9):
         Gu = np.einsum("bmn,bn->bm", G, up)
         viol = Gu - h
         zscale = np.maximum(1.0, np.abs(lam).max(axis=1, initial=0.0))[:, None]
-        dscale = np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1))
-        pscale = np.maximum(hscale[:, 0], np.abs(Gu).max(axis=1, initial=0.0))[:, None]
+        dscale = np.where(strict, qscale, np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1)))
+        pscale = np.where(strict, hscale[:, 0],
+                          np.maximum(hscale[:, 0], np.abs(Gu).max(axis=1, initial=0.0)))[:, None]
         r_d = Pu + q + Gtl
+        with np.errstate(invalid="ignore"):
+            finite = np.isfinite(up).all(axis=1) & np.isfinite(lam).all(axis=1)
         ok = (
-            (viol <= eps * pscale).all(axis=1)
+            spd & finite
+            & (viol <= eps * pscale).all(axis=1)
             & (np.abs(np.where(act, viol, 0.0)) <= eps * pscale).all(axis=1)
             & (lam >= -eps * zscale).all(axis=1)
             & (np.abs(r_d).max(axis=1) <= eps * dscale)

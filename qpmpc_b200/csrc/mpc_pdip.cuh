@@ -396,8 +396,12 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
     // guessed active set A; an accepted point is the exact solution on A.  A
     // rejected guess is corrected (negative multipliers leave, violated rows
     // enter) and the polish repeated.
-    if (__any_sync(FULL_MASK, polish && st == 0 && m > 0)) {
+    // Instances the iteration gave up on (cap, lost definiteness) are polished too: an
+    // accepted point is a KKT-certified solution wherever the iterate came from.  They are
+    // held to the absolute form of the acceptance test (`strict`: their iterate may be huge).
+    if (__any_sync(FULL_MASK, polish && valid && m > 0)) {
         const T delta = PdipNum<T>::delta, dinv = T(1) / delta, eps = PdipNum<T>::polish_eps;
+        const bool strict = st != 0;
         bool act[MR];
         T lam[MR], r2[MR];
         bool accepted = false;
@@ -409,7 +413,7 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             r2[s] = T(0);
         }
         for (int round = 0; round < PdipNum<T>::polish_rounds; ++round) {
-            const bool need = polish && st == 0 && m > 0 && !accepted;
+            const bool need = polish && valid && m > 0 && !accepted;
             if (!__any_sync(FULL_MASK, need)) break;
             __syncwarp();
 #pragma unroll
@@ -467,9 +471,11 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             // accept a primal feasible point with non-negative multipliers, zero
             // residual on A and a small stationarity residual
             T worst_viol = T(0), worst_act = T(0), worst_neg = T(0), zmax = T(0), gumax = T(0);
+            bool finite = abs_(up) < Num<T>::inf();  // fmax / fmin drop NaNs: test for them explicitly
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
                 if (rowvalid[s]) {
+                    finite = finite && abs_(lam[s]) < Num<T>::inf() && abs_(gx[s]) < Num<T>::inf();
                     worst_viol = fmax(worst_viol, gx[s]);
                     if (act[s]) worst_act = fmax(worst_act, abs_(gx[s]));
                     worst_neg = fmax(worst_neg, -lam[s]);
@@ -483,12 +489,15 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
             const T g_viol = pdip_max<T, NP>(worst_viol), g_act = pdip_max<T, NP>(worst_act);
             const T g_neg = pdip_max<T, NP>(worst_neg), g_rd = pdip_max<T, NP>(abs_(rd));
-            const T dscale = fmax(qscale, pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl))));
-            const T pscale = fmax(hscale, pdip_max<T, NP>(gumax));
-            const bool ok = spd && g_viol <= eps * pscale && g_act <= eps * pscale && g_neg <= eps * zscale &&
-                            g_rd <= eps * dscale;
+            const T g_ds = pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl))), g_ps = pdip_max<T, NP>(gumax);
+            const T g_bad = pdip_max<T, NP>((finite && abs_(rd) < Num<T>::inf()) ? T(0) : T(1));
+            const T dscale = strict ? qscale : fmax(qscale, g_ds);
+            const T pscale = strict ? hscale : fmax(hscale, g_ps);
+            const bool ok = spd && g_bad == T(0) && g_viol <= eps * pscale && g_act <= eps * pscale &&
+                            g_neg <= eps * zscale && g_rd <= eps * dscale;
             if (need && ok) {
                 accepted = true;
+                st = 0;
                 x = up;
 #pragma unroll
                 for (int s = 0; s < MR; ++s) z[s] = lam[s];
