@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--method", default="active_set", choices=["active_set", "pdip"],
+                    help="solver kernel; the headline and the default is the exact active set "
+                         "(pdip: experimental, needs QPMPC_B200_ENABLE_PDIP=1, DESIGN.md 2b)")
     return ap.parse_args()
 
 
@@ -66,7 +69,9 @@ def config_dict(args, world):
         "workload": f"triple_integrator fp64 nx=3 nu=1 nc=2 N={args.horizon} "
                     f"batch={args.batch}/GPU per-instance A,B,C,e,x0,goal (BASELINE configs[1])",
         "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-        "horizon": args.horizon, "method": "dual active set (Goldfarb-Idnani), exact",
+        "horizon": args.horizon,
+        "method": "dual active set (Goldfarb-Idnani), exact" if args.method == "active_set"
+        else "interior point (Mehrotra) + primal-dual active-set polish, tol 1e-9",
         "l2": f"inputs rotate over {ROTATE} distinct sets ({ROTATE}x{args.batch * 208 / 1e6:.1f} MB > L2)",
         "parallelism": f"batch-sharded x{world}, U gathered on every rank each step" if world > 1 else "single GPU",
     }
@@ -221,10 +226,12 @@ def run_b200(args, rank, local_rank, world):
     # N > 1: the kernel's epilogue stores every U row into all ranks' buffers
     # over NVLink (fused gather); NCCL all-gather only if symmetric memory is
     # unavailable on the box.
+    mkw = {} if args.method == "active_set" else {"method": args.method}
     gather, gather_kind = None, "none"
     if world > 1:
         gather_kind = "nccl all_gather_into_tensor"
-        if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer":
+        # (the fused gather exists for the active-set kernel only)
+        if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer" and args.method == "active_set":
             try:
                 from qpmpc_b200.distributed import PeerGather
 
@@ -237,7 +244,7 @@ def run_b200(args, rank, local_rank, world):
         if gather is not None:
             _, status, iters = gather.solve(problems[i % ROTATE])
             return _StepResult(status[rank * B:(rank + 1) * B], iters)
-        plan = solve_mpc_batch(problems[i % ROTATE], out=U_out)
+        plan = solve_mpc_batch(problems[i % ROTATE], out=U_out, **mkw)
         if world > 1:
             dist.all_gather_into_tensor(U_all, U_out)
         return plan
@@ -277,7 +284,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
     for i in range(args.steps):
         kev[2 * i].record()
-        solve_mpc_batch(problems[i % ROTATE], out=U_out)
+        solve_mpc_batch(problems[i % ROTATE], out=U_out, **mkw)
         kev[2 * i + 1].record()
     torch.cuda.synchronize()
     kernel_ms = float(np.mean([kev[2 * i].elapsed_time(kev[2 * i + 1]) for i in range(args.steps)]))
@@ -291,7 +298,7 @@ def run_b200(args, rank, local_rank, world):
         host_sets.append(hs)
     U_host = torch.empty((B, n), dtype=torch.float64).pin_memory()
     st_host = torch.empty(B, dtype=torch.int32).pin_memory()
-    desc = problems[0].desc()
+    desc = problems[0].desc() if args.method == "active_set" else problems[0].desc(_capi.PDIP)
     h2d = sum(t.numel() * 8 for t in host_sets[0].values())
     d2h = U_host.numel() * 8 + st_host.numel() * 4
     vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
@@ -375,6 +382,11 @@ def run_b200(args, rank, local_rank, world):
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }
+    if args.method != "active_set":
+        # the flop model and the ncu traffic figure above belong to the active-set kernel
+        line["roofline"]["kernel"] = line["roofline"]["kernel"].replace("mpc_solve_kernel", "mpc_pdip_kernel")
+        line["roofline"]["traffic"] = None
+        line["fp64"] = None
     if not args.no_cpu_baseline:
         v, threads, sample = cpu_arm(sets[0], args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -34,6 +34,10 @@ echo "== 3. throughput next to the active-set kernel, config 2 (90 s)"
 timeout 90 python tools/pdip_bench.py > $OUT/${TAG}_pdip_bench.jsonl 2> $OUT/${TAG}_pdip_bench.err
 echo "rc=$?"; cat $OUT/${TAG}_pdip_bench.jsonl
 
+echo "== 3b. the bench contract with the interior-point kernel (120 s)"
+timeout 120 python bench.py --method pdip --steps 64 --warmup 4 --cpu-seconds 2 > $OUT/${TAG}_bench_pdip.json 2> $OUT/${TAG}_bench_pdip.err
+echo "rc=$?"; cat $OUT/${TAG}_pdip_bench.jsonl
+
 echo "== 4. compute-sanitizer synccheck + memcheck on a small launch (90 s)"
 for tool in synccheck memcheck; do
   timeout 90 compute-sanitizer --tool $tool python - > $OUT/${TAG}_pdip_${tool}.txt 2>&1 <<'PY'
