@@ -36,7 +36,7 @@ echo "rc=$?"; cat $OUT/${TAG}_pdip_bench.jsonl
 
 echo "== 3b. the bench contract with the interior-point kernel (120 s)"
 timeout 120 python bench.py --method pdip --steps 64 --warmup 4 --cpu-seconds 2 > $OUT/${TAG}_bench_pdip.json 2> $OUT/${TAG}_bench_pdip.err
-echo "rc=$?"; cat $OUT/${TAG}_pdip_bench.jsonl
+echo "rc=$?"; cat $OUT/${TAG}_bench_pdip.json
 
 echo "== 4. compute-sanitizer synccheck + memcheck on a small launch (90 s)"
 for tool in synccheck memcheck; do
