@@ -76,9 +76,10 @@ struct Cta {
     std::function<void()> body;
 };
 
-// Lane order inside a scheduling round: 0 ascending, 1 descending.  A result
-// that depends on it reveals a read of another lane's shared-memory write with
-// no synchronisation point in between (a data race on the device).
+// Lane order inside a scheduling round (and warp order inside a CTA round):
+// 0 ascending, 1 descending.  A result that depends on it reveals a read of
+// another thread's shared-memory write with no synchronisation point in
+// between (a data race on the device).
 inline int &lane_order() {
     static int order = 0;
     return order;
@@ -180,7 +181,8 @@ inline void run_cta(int nthreads, Idx block_idx, Idx grid_dim, const std::functi
     }
     const int nwarps = (nthreads + WARP - 1) / WARP;
     while (true) {
-        for (int w = 0; w < nwarps; ++w) {
+        for (int wi = 0; wi < nwarps; ++wi) {
+            const int w = lane_order() ? nwarps - 1 - wi : wi;  // warps too: a missing __syncthreads shows the same way
             bool any = true;
             while (any) {  // step this warp until every lane is parked or done
                 any = false;

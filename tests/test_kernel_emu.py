@@ -161,6 +161,18 @@ def test_results_do_not_depend_on_the_lane_schedule(method):
         assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["status"], b["status"])
 
 
+def test_cta_kernel_results_do_not_depend_on_the_schedule(monkeypatch):
+    """The same for the CTA-per-instance kernel, whose threads talk through shared
+    memory across warps: warps (and lanes) in the opposite order, same bits."""
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    for w in (triple_integrator_batch(2, seed=41), pendulum_batch(2), random_batch(2, 7, 5, 2, 3, seed=23, ltv=True),
+              triple_integrator_batch(1, N=64, seed=64)):
+        a = emu.solve(w)
+        b = emu.solve(w, descending=True)
+        assert np.array_equal(a["U"], b["U"], equal_nan=True)
+        assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["status"], b["status"])
+
+
 @pytest.mark.parametrize("kind", ["humanoid", "pendulum", "ti8", "random", "humanoid_cta"])
 def test_single_precision_kernels_within_the_stated_tolerance(kind, monkeypatch):
     """The float instantiations (BASELINE config 4 runs in fp32): the GPU bar,
