@@ -24,29 +24,30 @@ _ip = ctypes.POINTER(ctypes.c_int)
 _lib = None
 
 
+def _declare(lib):
+    for name in ("emu_divergent_collectives", "emu_selftest", "emu_sync_points", "emu_sync_points_at"):
+        getattr(lib, name).restype = ctypes.c_long
+    return lib
+
+
 def load():
     """Build (if stale) and load ``libkernel_emu.so``."""
     global _lib
     if _lib is not None:
         return _lib
     if os.environ.get("QPMPC_EMU_LIB"):  # another build of kernel_emu.cpp, e.g. -march=native -ffp-contract=fast
-        _lib = ctypes.CDLL(os.environ["QPMPC_EMU_LIB"])
-        _lib.emu_divergent_collectives.restype = ctypes.c_long
-        _lib.emu_selftest.restype = ctypes.c_long
-        _lib.emu_sync_points.restype = ctypes.c_long
+        _lib = _declare(ctypes.CDLL(os.environ["QPMPC_EMU_LIB"]))
         return _lib
     csrc = os.path.join(ROOT, "qpmpc_b200", "csrc")
     deps = [os.path.join(HERE, "kernel_emu.cpp"), os.path.join(HERE, "warp_emu.h"),
             os.path.join(ROOT, "include", "qpmpc_b200.h")]
     deps += [os.path.join(csrc, f) for f in ("mpc_common.cuh", "mpc_kernels.cuh", "mpc_pdip.cuh",
+                                             "mpc_cta_kernel.cuh", "mpc_integrate.cuh", "mpc_plant.cuh",
                                              "mpc_host_params.h")]
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DQPMPC_HOST_EMU",
                         "-Wno-unknown-pragmas", f"-I{ROOT}", "-o", LIB_PATH, deps[0]], check=True)
-    _lib = ctypes.CDLL(LIB_PATH)
-    _lib.emu_divergent_collectives.restype = ctypes.c_long
-    _lib.emu_selftest.restype = ctypes.c_long
-    _lib.emu_sync_points.restype = ctypes.c_long
+    _lib = _declare(ctypes.CDLL(LIB_PATH))
     return _lib
 
 

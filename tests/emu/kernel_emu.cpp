@@ -262,6 +262,13 @@ int emu_smem_overruns(void) { return g_smem_overrun; }
 void emu_set_lane_order(int descending) { emu::lane_order() = descending; }
 long emu_divergent_collectives(void) { return emu::divergent_collectives(); }
 long emu_sync_points(void) { return emu::sync_points(); }
+// per-source-line histogram of synchronisation points (line numbers of the kernel headers; the
+// files overlap in line numbers, the caller knows which kernel it ran); reset = 1 clears it
+long emu_sync_points_at(int line, int reset) {
+    auto &h = emu::sync_points_by_line();
+    if (reset) std::fill(h.begin(), h.end(), 0L);
+    return (line >= 0 && line < (int)h.size()) ? h[line] : 0;
+}
 
 // qpmpc_b200_solve with host pointers.  `wpc`: warps per CTA (<= 0: the launch default).
 int emu_solve(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out, int wpc) {

@@ -130,9 +130,16 @@ inline long &sync_points() {
     static long count = 0;
     return count;
 }
+// the same, per source line (|line|: __syncwarp is recorded negative), for tools/emu_sync_profile.py --lines
+inline std::vector<long> &sync_points_by_line() {
+    static std::vector<long> hist(4096, 0);
+    return hist;
+}
 inline void enter_sync(int line) {
     Cta *c = current();
     ++sync_points();
+    const int key = line < 0 ? -line : line;
+    if (key < (int)sync_points_by_line().size()) ++sync_points_by_line()[key];
     ++c->nsync[c->cur];
     c->site[c->cur] = line;
 }

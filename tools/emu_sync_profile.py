@@ -20,6 +20,25 @@ from qpmpc_b200.workloads import humanoid_batch, pendulum_batch, triple_integrat
 
 lib = emu.load()
 B = 64
+
+if "--lines" in sys.argv:
+    # where the synchronisation points of one kernel are: per source line, config 2
+    method = "pdip" if "pdip" in sys.argv else "active_set"
+    src = os.path.join(ROOT, "qpmpc_b200", "csrc", "mpc_pdip.cuh" if method == "pdip" else "mpc_kernels.cuh")
+    text = open(src).read().splitlines()
+    w = triple_integrator_batch(B, seed=0)
+    lib.emu_sync_points_at(0, 1)
+    emu.solve(w, method=method)
+    hist = sorted(((lib.emu_sync_points_at(i, 0), i) for i in range(1, 4096)), reverse=True)
+    total = sum(c for c, _ in hist)
+    warps = B * 16 / 32.0
+    print(f"{method}: {total / 32.0 / warps:.1f} synchronisation points per warp; by source line of "
+          f"{os.path.basename(src)} (helpers in other headers are listed by their own line numbers):")
+    for c, i in hist[:18]:
+        if c:
+            print(f"  {c / 32.0 / warps:7.1f}  {100.0 * c / total:5.1f} %  line {i:4d}: {text[i - 1].strip()[:90] if i <= len(text) else ''}")
+    sys.exit(0)
+
 for name, w, np_ in (("config 2: triple integrator N=16", triple_integrator_batch(B, seed=0), 16),
                      ("config 3: pendulum N=12", pendulum_batch(B, seed=1), 16),
                      ("config 4: humanoid N=16", humanoid_batch(B, seed=2), 16),
