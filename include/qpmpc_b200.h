@@ -68,8 +68,7 @@ enum { QPMPC_B200_F64 = 0, QPMPC_B200_F32 = 1 };
  *               available through qpmpc_b200_solve_scatter
  *               (QPMPC_B200_EUNSUPPORTED otherwise).  It has no infeasibility
  *               certificate: an infeasible instance ends as STATUS_MAX_ITER
- *               or STATUS_NOT_SPD, never as STATUS_SOLVED.  Experimental:
- *               refused unless the process sets QPMPC_B200_ENABLE_PDIP=1. */
+ *               or STATUS_NOT_SPD, never as STATUS_SOLVED. */
 enum { QPMPC_B200_ACTIVE_SET = 0, QPMPC_B200_PDIP = 1 };
 enum { QPMPC_B200_FLAG_NO_POLISH = 1 /* PDIP: skip the polish */ };
 

@@ -46,13 +46,14 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
     P, q, G, h = (np.asarray(a, dtype=np.float64) for a in (P, q, G, h))
     B, m, n = G.shape
     u = np.zeros((B, n))
-    # start: u = 0, s = max(h, 1), z = 1
+    # start: u = 0, s = max(h, 1), z = 1 / s (every complementarity product starts at 1: a row
+    # with a huge bound -- "no bound" constants, padding -- does not inflate mu)
     s = np.maximum(h - np.einsum("bmn,bn->bm", G, u), 1.0)
-    z = np.ones((B, m))
+    z = 1.0 / s
     status = np.full(B, 1, dtype=np.int32)
     iters = np.zeros(B, dtype=np.int32)
     active = np.ones(B, dtype=bool)
-    hscale = np.maximum(1.0, np.abs(h).max(axis=1, initial=0.0))
+    hrow = np.maximum(1.0, np.abs(h))  # per-row scale of the primal tests
     qscale = np.maximum(1.0, np.abs(q).max(axis=1))
     for it in range(max_iter):
         Pu = np.einsum("bij,bj->bi", P, u)
@@ -64,11 +65,12 @@ def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
         # relative criteria: each residual against the size of the terms it is the sum of
         # (their rounding noise is the floor it can reach), the gap against the objective
         dscale = np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtz)).max(axis=1))
-        pscale = np.maximum(hscale, np.maximum(np.abs(Gu), s).max(axis=1, initial=0.0))
+        # (the primal residual row by row: one huge bound must not relax the test of the others)
+        prow = np.maximum(hrow, np.maximum(np.abs(Gu), s))
         obj = np.abs(np.einsum("bi,bi->b", u, 0.5 * Pu + q))
         done = (
             (np.abs(r_d).max(axis=1) <= tol * dscale)
-            & (np.abs(r_p).max(axis=1, initial=0.0) <= tol * pscale)
+            & (np.abs(r_p) <= tol * prow).all(axis=1)
             & (mu <= tol * (1.0 + obj))
         )
         newly = active & done
@@ -147,7 +149,7 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9, strict=None):
     up = u.copy()
     u_out, z_out = u.copy(), z.copy()
     accepted = np.zeros(B, dtype=bool)
-    hscale = np.maximum(1.0, np.abs(h).max(axis=1, initial=0.0))[:, None]
+    hrow = np.maximum(1.0, np.abs(h))
     qscale = np.maximum(1.0, np.abs(q).max(axis=1))
     for _ in range(rounds):
         if accepted.all():
@@ -167,8 +169,7 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9, strict=None):
         viol = Gu - h
         zscale = np.maximum(1.0, np.abs(lam).max(axis=1, initial=0.0))[:, None]
         dscale = np.where(strict, qscale, np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1)))
-        pscale = np.where(strict, hscale[:, 0],
-                          np.maximum(hscale[:, 0], np.abs(Gu).max(axis=1, initial=0.0)))[:, None]
+        pscale = np.where(strict[:, None], hrow, np.maximum(hrow, np.abs(Gu)))  # row by row
         r_d = Pu + q + Gtl
         with np.errstate(invalid="ignore"):
             finite = np.isfinite(up).all(axis=1) & np.isfinite(lam).all(axis=1)

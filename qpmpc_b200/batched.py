@@ -272,7 +272,7 @@ def pack_problem(problem: MPCProblem) -> dict:
 
     LTV operands (Python lists, ``mpc_problem.py:178-180``) become [N, r, c]
     stacks.  Ragged per-step row counts are padded to the largest ``nc`` with
-    all-zero rows whose bound is huge, and ``row_map`` lists the real rows.
+    all-zero rows with bound 1, and ``row_map`` lists the real rows.
     """
     N = problem.nb_timesteps
     if problem.initial_state is None:
@@ -281,7 +281,9 @@ def pack_problem(problem: MPCProblem) -> dict:
     ncs = [ek.shape[0] for ek in e_steps]
     nc = max(ncs)
     ragged = len(set(ncs)) > 1
-    BIG = 1e30
+    # bound of the padding rows: 0 . u <= 1 is never active and is well scaled for both methods
+    # (a huge "no bound" constant would dominate the interior point's scale estimates)
+    PAD_BOUND = 1.0
 
     def mat(op, cols):
         if op is None:
@@ -311,7 +313,7 @@ def pack_problem(problem: MPCProblem) -> dict:
         D = [np.zeros((ncs[k], nu)) if d is None else d for k, d in enumerate(D)]
     Cm, Dm = mat(C, nx), mat(D, nu)
     if isinstance(problem.ineq_vector, list) or ragged:
-        e = np.full((N, nc), BIG)
+        e = np.full((N, nc), PAD_BOUND)
         for k in range(N):
             e[k, : ncs[k]] = e_steps[k]
     else:
@@ -402,10 +404,6 @@ def solve_mpc_batch(
     meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}.get(method)
     if meth is None:
         raise ProblemDefinitionError(f"unknown method {method!r}")
-    if meth == _capi.PDIP and os.environ.get("QPMPC_B200_ENABLE_PDIP", "0") in ("", "0"):
-        raise BackendError(
-            'method="pdip" is experimental (validated on the host emulator, not yet on a device: '
-            "DESIGN.md section 2b); set QPMPC_B200_ENABLE_PDIP=1 to use it")
     desc = problem.desc(meth, max_iter, tol, polish)
     B, n, m = problem.batch_size, problem.nb_vars, problem.nb_rows
     with torch.cuda.device(problem.device):

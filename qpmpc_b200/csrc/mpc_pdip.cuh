@@ -260,19 +260,17 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
     constexpr int LDG = L::LDG, LDL = L::LDL;
     bool rowvalid[MR];
     T hrow[MR], sl[MR], z[MR], rp[MR], W[MR], ds[MR], dz[MR], rc[MR], gx[MR];
-    T habs = T(0);
 #pragma unroll
     for (int s = 0; s < MR; ++s) {
         const int row = l + s * NP;
         rowvalid[s] = row < m;
         hrow[s] = rowvalid[s] ? hs[row] : T(1);
-        // start (pdip_np.py): u = 0, s = max(h, 1), z = 1
+        // start (pdip_np.py): u = 0, s = max(h, 1), z = 1 / s -- every complementarity product
+        // starts at 1, so a row with a huge bound ("no bound" constants) does not inflate mu
         sl[s] = rowvalid[s] ? fmax(hrow[s], T(1)) : T(1);
-        z[s] = rowvalid[s] ? T(1) : T(0);
-        if (rowvalid[s]) habs = fmax(habs, abs_(hrow[s]));
+        z[s] = rowvalid[s] ? T(1) / sl[s] : T(0);
         rp[s] = W[s] = ds[s] = dz[s] = rc[s] = gx[s] = T(0);
     }
-    const T hscale = fmax(T(1), pdip_max<T, NP>(habs));
     const T qscale = fmax(T(1), pdip_max<T, NP>(abs_(qj)));
     const T minv = m > 0 ? T(1) / (T)m : T(0);
     tol = fmax(tol, PdipNum<T>::tol_min);
@@ -297,26 +295,27 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
         const T px = px0 + px1, gz = pdip_gt_dot<T, LDG>(Gc, tv, m, l);
         const T rd = px + qj + gz;
         pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
-        T comp = T(0), rpabs = T(0), pabs = T(0);
+        // the primal residual is tested row by row, each against the size of its own terms
+        // (one huge bound must not relax the test of the other rows): rpex <= 0 passes
+        T comp = T(0), rpex = T(-1);
 #pragma unroll
         for (int s = 0; s < MR; ++s) {
             rp[s] = rowvalid[s] ? gx[s] + sl[s] - hrow[s] : T(0);
-            rpabs = fmax(rpabs, abs_(rp[s]));
             if (rowvalid[s]) {
                 comp += sl[s] * z[s];
-                pabs = fmax(pabs, fmax(abs_(gx[s]), sl[s]));
+                const T scale = fmax(fmax(T(1), abs_(hrow[s])), fmax(abs_(gx[s]), sl[s]));
+                rpex = fmax(rpex, abs_(rp[s]) - tol * scale);
             }
         }
         const T mu = pdip_sum<T, NP>(comp) * minv;
         const T rdmax = pdip_max<T, NP>(abs_(rd));
-        const T rpmax = pdip_max<T, NP>(rpabs);
+        const T rpmax = pdip_max<T, NP>(rpex);
         // relative criteria (pdip_np.py): each residual against the size of the terms it is
         // the sum of -- their rounding noise is the floor it can reach -- and the gap
         // against the objective.  All reductions first, then the (short-circuiting) test.
         const T dscale = fmax(qscale, pdip_max<T, NP>(fmax(abs_(px), abs_(gz))));
-        const T pscale = fmax(hscale, pdip_max<T, NP>(pabs));
         const T obj = abs_(pdip_sum<T, NP>(x * (T(0.5) * px + qj)));
-        const bool conv = rdmax <= tol * dscale && rpmax <= tol * pscale && mu <= tol * (T(1) + obj);
+        const bool conv = rdmax <= tol * dscale && rpmax <= T(0) && mu <= tol * (T(1) + obj);
         if (!done && conv) {
             st = 0;
             done = true;
@@ -470,30 +469,31 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             }
             // accept a primal feasible point with non-negative multipliers, zero
             // residual on A and a small stationarity residual
-            T worst_viol = T(0), worst_act = T(0), worst_neg = T(0), zmax = T(0), gumax = T(0);
+            // (primal tests row by row against the row's own scale: *_ex <= 0 passes)
+            T viol_ex = T(-1), act_ex = T(-1), worst_neg = T(0), zmax = T(0);
             bool finite = abs_(up) < Num<T>::inf();  // fmax / fmin drop NaNs: test for them explicitly
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
                 if (rowvalid[s]) {
                     finite = finite && abs_(lam[s]) < Num<T>::inf() && abs_(gx[s]) < Num<T>::inf();
-                    worst_viol = fmax(worst_viol, gx[s]);
-                    if (act[s]) worst_act = fmax(worst_act, abs_(gx[s]));
+                    const T hs_ = fmax(T(1), abs_(hrow[s]));
+                    const T ps = strict ? hs_ : fmax(hs_, abs_(gx[s] + hrow[s]));  // |G up|
+                    viol_ex = fmax(viol_ex, gx[s] - eps * ps);
+                    if (act[s]) act_ex = fmax(act_ex, abs_(gx[s]) - eps * ps);
                     worst_neg = fmax(worst_neg, -lam[s]);
                     zmax = fmax(zmax, abs_(lam[s]));
-                    gumax = fmax(gumax, abs_(gx[s] + hrow[s]));  // |G up|
                 }
             }
             // (every reduction is a shuffle sequence the whole warp must enter: evaluate
             // them all before combining -- inside a short-circuited `&&` the groups of a
             // warp would leave the chain at different links and the device deadlocks)
             const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
-            const T g_viol = pdip_max<T, NP>(worst_viol), g_act = pdip_max<T, NP>(worst_act);
+            const T g_viol = pdip_max<T, NP>(viol_ex), g_act = pdip_max<T, NP>(act_ex);
             const T g_neg = pdip_max<T, NP>(worst_neg), g_rd = pdip_max<T, NP>(abs_(rd));
-            const T g_ds = pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl))), g_ps = pdip_max<T, NP>(gumax);
+            const T g_ds = pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl)));
             const T g_bad = pdip_max<T, NP>((finite && abs_(rd) < Num<T>::inf()) ? T(0) : T(1));
             const T dscale = strict ? qscale : fmax(qscale, g_ds);
-            const T pscale = strict ? hscale : fmax(hscale, g_ps);
-            const bool ok = spd && g_bad == T(0) && g_viol <= eps * pscale && g_act <= eps * pscale &&
+            const bool ok = spd && g_bad == T(0) && g_viol <= T(0) && g_act <= T(0) &&
                             g_neg <= eps * zscale && g_rd <= eps * dscale;
             if (need && ok) {
                 accepted = true;

@@ -242,11 +242,6 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
         // above the engine's fp32 bar on 7-15 % of the humanoid instances (emulator
         // measurement, tests/emu), so it is refused rather than offered.
         if (peers || d->dtype != QPMPC_B200_F64 || !pick_variant(p.n, p.m, &v)) return QPMPC_B200_EUNSUPPORTED;
-        // EXPERIMENTAL: validated on the host warp emulator (tests/test_pdip_emu.py); its
-        // first run on a B200 did not return within the time limit and the round's GPU
-        // budget ended before the cause was found.  Off unless
-        // asked for explicitly, so that no caller can hang a device by accident.
-        if (env_int("QPMPC_B200_ENABLE_PDIP", 0) == 0) return QPMPC_B200_EUNSUPPORTED;
         p.max_iter = d->max_iter > 0 ? d->max_iter : 50;
         const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
         return dispatch_pdip(p, v, polish, s);

@@ -20,16 +20,7 @@ import os
 import numpy as np
 import pytest
 
-# The kernel is EXPERIMENTAL (validated on the host emulator only, see
-# tests/test_pdip_emu.py and DESIGN.md section 2b): its first B200 run did not
-# return within the time limit.  These tests run only when the method is
-# switched on explicitly -- never in the default `pytest -m gpu`.
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("QPMPC_B200_ENABLE_PDIP", "0") in ("", "0"),
-                       reason="interior-point kernel is experimental: set QPMPC_B200_ENABLE_PDIP=1"),
-    pytest.mark.timeout(60),
-]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(60)]
 
 
 def _solve(w, dtype=None, **kw):

@@ -125,7 +125,8 @@ def test_pack_problem_pads_ragged_rows():
     pk = pack_problem(p)
     assert pk["nc"] == 3 and pk["C"].shape == (3, 3, 2) and pk["e"].shape == (3, 3)
     assert pk["row_map"] == [0, 3, 4, 5, 6, 7]
-    assert pk["e"][0, 1] > 1e29 and np.all(pk["C"][0, 1:] == 0.0) and np.all(pk["C"][2] == 0.0)
+    assert pk["e"][0, 1] == 1.0 and pk["e"][2, 2] == 1.0  # padding rows: 0 . u <= 1
+    assert np.all(pk["C"][0, 1:] == 0.0) and np.all(pk["C"][2] == 0.0)
 
 
 def test_workload_algorithmic_bytes_match_survey():
@@ -213,6 +214,31 @@ def test_product_path_fails_loudly_without_cuda():
 
     with pytest.raises(BackendError):
         solve_mpc(golden_problem(load_golden("triple_integrator")), solver="b200")
+
+
+def test_qpmpc_alias_exposes_the_reference_import_paths():
+    """The imports of the reference's tests (tests/test_humanoid_one_step.py:12-13,
+    tests/test_wheeled_inverted_pendulum.py:11-12) resolve to this package."""
+    import qpmpc
+    import qpmpc_b200
+    from qpmpc import MPCProblem, MPCQP, Plan, solve_mpc
+    from qpmpc.exceptions import ProblemDefinitionError, StateError
+    from qpmpc.mpc_problem import MPCProblem as P2
+    from qpmpc.solve_mpc import MPCQP as Q2
+    from qpmpc.systems import WheeledInvertedPendulum
+
+    assert MPCProblem is qpmpc_b200.MPCProblem is P2 and MPCQP is qpmpc_b200.MPCQP is Q2
+    assert Plan is qpmpc_b200.Plan and solve_mpc is qpmpc_b200.solve_mpc and callable(qpmpc.solve_mpc)
+    assert WheeledInvertedPendulum is qpmpc_b200.systems.WheeledInvertedPendulum
+    assert issubclass(ProblemDefinitionError, qpmpc_b200.QPMPCException) and StateError is qpmpc_b200.StateError
+    assert qpmpc.__all__ == ["MPCProblem", "MPCQP", "Plan", "solve_mpc"]  # qpmpc/__init__.py:14-19
+
+
+def test_solver_names_are_checked_before_any_device_work():
+    from qpmpc_b200 import BackendError, solve_mpc
+
+    with pytest.raises(BackendError, match="unknown solver"):
+        solve_mpc(golden_problem(load_golden("triple_integrator")), solver="not_a_backend")
 
 
 # -- sharding over ranks (gloo, world size 2) -----------------------------------------

@@ -48,10 +48,11 @@ def test_mpc_qp_first_constraints():
 
 
 def test_solve_mpc_shapes():
-    from qpmpc_b200 import solve_mpc
+    from qpmpc import solve_mpc  # the compat alias opts in to serving qpsolvers names
 
     problem = _humanoid_problem()
-    plan = solve_mpc(problem, solver="proxqp")  # a qpsolvers name: served by the CUDA engine
+    plan = solve_mpc(problem, solver="proxqp")  # what tests/test_humanoid_one_step.py:78 passes
+    assert plan.qpsol.extras["method"] == "active_set"
     N = problem.nb_timesteps
     assert plan.inputs.flatten().shape == (N * problem.input_dim,)
     assert plan.states.flatten().shape == ((N + 1) * problem.state_dim,)
@@ -123,8 +124,55 @@ def test_single_step_and_unconstrained_problems():
         assert plan.qpsol.extras["iters"] == 0
 
 
-def test_strict_solver_names():
-    from qpmpc_b200 import BackendError, solve_mpc
+def test_solver_name_policy():
+    """``solver=`` keeps its reference meaning (solve_mpc.py:43): native names run the CUDA
+    engine, qpsolvers names need qpsolvers or the documented opt-in, anything else raises;
+    keywords that do not apply are dropped with a warning, never silently."""
+    import importlib.util
 
-    with pytest.raises(BackendError):
-        solve_mpc(_humanoid_problem(), solver="osqp", strict=True)
+    from qpmpc_b200 import BackendError, solve_mpc
+    from qpmpc_b200.solve_mpc import serve_qpsolvers_names
+
+    problem = _humanoid_problem()
+    with pytest.raises(BackendError, match="unknown solver"):
+        solve_mpc(problem, solver="no_such_backend")
+    try:
+        serve_qpsolvers_names(False)
+        if importlib.util.find_spec("qpsolvers") is None:
+            with pytest.raises(BackendError, match="qpsolvers"):
+                solve_mpc(problem, solver="osqp")
+        serve_qpsolvers_names(True)
+        with pytest.warns(UserWarning, match="initvals"):
+            exact = solve_mpc(problem, solver="quadprog", initvals=np.zeros(16))
+        ipm = solve_mpc(problem, solver="clarabel", eps_abs=1e-9)  # interior-point name -> pdip kernel
+        assert ipm.qpsol.extras["method"] == "pdip" and exact.qpsol.extras["method"] == "active_set"
+        assert np.abs(ipm.inputs - exact.inputs).max() <= 1e-6
+        assert np.abs(solve_mpc(problem, solver="b200_pdip").inputs - exact.inputs).max() <= 1e-6
+    finally:
+        serve_qpsolvers_names(True)
+
+
+def test_mpcqp_problem_record_and_sparse():
+    """``MPCQP.problem`` (mpc_qp.py:124-127) and ``sparse=True`` (mpc_qp.py:108-109): P and G
+    become csc matrices with the dense entries, q and h stay arrays, the record has no
+    equalities or bounds, and solving the record's QP reproduces the plan."""
+    import oracle
+    import scipy.sparse
+
+    from qpmpc_b200 import MPCQP, solve_mpc
+
+    problem = _humanoid_problem()
+    dense, sparse = MPCQP(problem), MPCQP(problem, sparse=True)
+    assert scipy.sparse.isspmatrix_csc(sparse.P) and scipy.sparse.isspmatrix_csc(sparse.G)
+    assert isinstance(dense.P, np.ndarray) and isinstance(dense.G, np.ndarray)
+    np.testing.assert_array_equal(sparse.P.toarray(), dense.P)
+    np.testing.assert_array_equal(sparse.G.toarray(), dense.G)
+    np.testing.assert_array_equal(sparse.q, dense.q)
+    np.testing.assert_array_equal(sparse.h, dense.h)
+    qp = dense.problem
+    assert qp.P is dense.P and qp.q is dense.q and qp.G is dense.G and qp.h is dense.h
+    assert qp.A is None and qp.b is None and qp.lb is None and qp.ub is None
+    assert sparse.problem.P is sparse.P and sparse.problem.G is sparse.G
+    st, x, _, _ = oracle.qp_gi(qp.P, qp.q, qp.G, qp.h)
+    assert st == 0
+    assert np.abs(solve_mpc(problem, solver="b200", sparse=True).inputs.flatten() - x).max() <= 1e-6

@@ -8,7 +8,6 @@ set -u
 TAG=${1:-pdip}
 OUT=gpurun_out
 mkdir -p $OUT
-export QPMPC_B200_ENABLE_PDIP=1
 export PYTHONUNBUFFERED=1
 
 echo "== 1. two instances, smallest possible launch (60 s)"
