@@ -1,34 +1,45 @@
 #!/usr/bin/env python3
 """bench.py -- MPC solves/sec (batched), the BASELINE.json metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): triple integrator (nx=3, nu=1, nc=2, N=16),
-fp64, 65 536 instances per GPU, per-instance A, B, C, e, x0, goal records
-(seed 0).  A "step" condenses and solves the whole batch once.
-Weak scaling: every rank owns its own 65 536 instances; for N > 1 every rank
-ends each step with the stacked U of ALL ranks -- the all-gather the north star
-names, fused into the solve kernel (its epilogue stores each row into every
-rank's symmetric buffer over NVLink; NCCL all-gather is the fallback).
+Workloads (BASELINE.json configs; SURVEY.md 8(d) for shapes, distributions, seeds):
+  --config 2 (default, the configuration the metric is quoted on): triple integrator
+             (nx=3, nu=1, nc=2, N=16), fp64, 65 536 instances per GPU, per-instance
+             A, B, C, e, x0, goal records.  A step condenses and solves the batch once.
+  --config 3 wheeled inverted pendulum (nx=4, nu=1, N=12), 16 384 instances, a step is one
+             200-cycle receding-horizon closed loop (targets -> solve -> 15 plant substeps).
+  --config 4 humanoid / LIPM with per-instance per-step ZMP bounds e_k, fp32, 8 192 instances.
+  --config 5 one point of the horizon sweep: triple integrator with T = 1/N,
+             --horizon N in {8,16,32,64}, --batch B (default N=64, B=262 144).
+Weak scaling: every rank owns its own batch; for N > 1 (config 2) every rank ends each step
+with the stacked U of ALL ranks -- the all-gather the north star names, fused into the solve
+kernel (its epilogue stores each row into every rank's symmetric buffer over NVLink; NCCL
+all-gather is the fallback) -- and the gathered buffer is checked, after the timed region,
+against a local re-solve of the other ranks' shards.
 
-`value`     device-resident throughput (inputs already in HBM), CUDA events.
-`e2e`       the same batch through qpmpc_b200_solve_host with pinned HOST
-            buffers: H2D of every operand + kernel + D2H of U/status per step
-            (pipelined over three streams in chunks, one sync per step).
-`roofline`  algorithmic bytes per launch / measured kernel time vs the HBM
-            peak -- by construction tiny: the path is FP64-issue bound, so the
-            FP64 fraction is reported next to it (`fp64`).
-`cpu_baseline`  the C oracle (oracle/mpc_oracle.c: condensing + Goldfarb-Idnani,
-            OpenMP) on the same instances, all host threads.
+`value`     device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
+`e2e`       the same batch through qpmpc_b200_solve_host with pinned HOST buffers: H2D of
+            every operand + kernel + D2H of U/status per step; at N > 1 the ranks write their
+            rows into ONE host array shared by the ranks (the gather), barrier per step.
+`roofline`  algorithmic bytes per launch / measured kernel time vs the HBM peak -- by
+            construction tiny: the path is FP64-issue bound, so two FP64 fractions are
+            reported next to it (`fp64`): SURVEY 8(d)'s structure-agnostic flop count F and
+            the flops this algorithm executes, both against a measured DFMA peak.
+`cpu_baseline`  the C oracle (oracle/mpc_oracle.c: condensing + Goldfarb-Idnani, OpenMP)
+            on a bounded sample of the same instances, all host threads.
 
-`--impl reference` times that CPU port alone (the reference itself is pure
-Python over qpsolvers wheels that cannot be installed offline).
+`--impl reference` times that CPU port alone on all host threads, on the whole job's
+batch (world x batch) -- the reference itself is pure Python over qpsolvers wheels that
+cannot be installed offline; see DESIGN.md.
 """
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -40,41 +51,79 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-BATCH_PER_GPU = 65536
-HORIZON = 16
-ROTATE = 12  # distinct input sets: 12 x 13.6 MB = 164 MB > 126 MB of L2
+ROTATE_BYTES = 160e6  # distinct input sets must exceed the 126 MB L2
 METRIC = "MPC solves/sec (batched)"
 UNIT = "solves/s"
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+DEFAULTS = {2: (65536, 16), 3: (16384, 12), 4: (8192, 16), 5: (262144, 64)}  # config -> (batch/GPU, N)
+CYCLES = 200  # config 3
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1024)
-    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--horizon", type=int, default=HORIZON)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--horizon", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--method", default="active_set", choices=["active_set", "pdip"],
-                    help="solver kernel; the headline and the default is the exact active set "
-                         "(pdip: experimental, needs QPMPC_B200_ENABLE_PDIP=1, DESIGN.md 2b)")
-    return ap.parse_args()
+                    help="solver kernel; the headline and the default is the exact active set")
+    args = ap.parse_args()
+    b, n = DEFAULTS[args.config]
+    args.batch = args.batch or b
+    args.horizon = args.horizon or n
+    if args.steps is None:
+        args.steps = {2: 1024, 3: 8, 4: 1024, 5: 64}[args.config] if args.impl == "b200" else 8
+    if args.warmup is None:
+        args.warmup = {2: 16, 3: 3, 4: 16, 5: 4}[args.config] if args.impl == "b200" else 3
+    return args
 
 
-def config_dict(args, world):
-    return {
-        "workload": f"triple_integrator fp64 nx=3 nu=1 nc=2 N={args.horizon} "
-                    f"batch={args.batch}/GPU per-instance A,B,C,e,x0,goal (BASELINE configs[1])",
-        "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-        "horizon": args.horizon,
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+def make_workload(args, seed):
+    from qpmpc_b200.workloads import humanoid_batch, pendulum_batch, triple_integrator_batch
+
+    if args.config == 3:
+        return pendulum_batch(args.batch, N=args.horizon, seed=1 + seed)
+    if args.config == 4:
+        return humanoid_batch(args.batch, N=args.horizon, seed=2 + seed)
+    return triple_integrator_batch(args.batch, N=args.horizon, seed=(0 if args.config == 2 else 3) + seed)
+
+
+def dtype_of(args):
+    return "f32" if args.config == 4 else "f64"
+
+
+def solves_per_step(args):
+    return args.batch * (CYCLES if args.config == 3 else 1)
+
+
+def config_dict(args, world, rotate=None):
+    B, N = args.batch, args.horizon
+    names = {
+        2: f"triple_integrator fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU per-instance A,B,C,e,x0,goal "
+           "(BASELINE configs[1])",
+        3: f"wheeled_inverted_pendulum fp64 nx=4 nu=1 nc=2 N={N} batch={B}/GPU, {CYCLES}-cycle receding horizon "
+           "(targets -> condense+solve -> 15 plant substeps per cycle), shared model (BASELINE configs[2])",
+        4: f"humanoid/LIPM fp32 nx=3 nu=1 nc=2 N={N} batch={B}/GPU per-instance per-step e_k (BASELINE configs[3])",
+        5: f"triple_integrator T=1/N fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU (BASELINE configs[4], one sweep point)",
+    }
+    cfg = {
+        "workload": names[args.config],
+        "batch_per_gpu": B, "global_batch": B * world, "horizon": N,
         "method": "dual active set (Goldfarb-Idnani), exact" if args.method == "active_set"
         else "interior point (Mehrotra) + primal-dual active-set polish, tol 1e-9",
-        "l2": f"inputs rotate over {ROTATE} distinct sets ({ROTATE}x{args.batch * 208 / 1e6:.1f} MB > L2)",
         "parallelism": f"batch-sharded x{world}, U gathered on every rank each step" if world > 1 else "single GPU",
     }
+    if rotate is not None:
+        cfg["l2"] = rotate
+    return cfg
 
 
 # ---------------------------------------------------------------------------
@@ -133,67 +182,189 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------
-def cpu_arm(workload, seconds, min_reps=1):
-    """Time oracle.solve_batch (C, OpenMP, all threads) on the workload for
-    about `seconds`; returns (solves/s, threads, sample description)."""
+def host_threads():
+    """Every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers; the CPU arm ignores it and asks the oracle for this many threads."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_solve(workload, threads):
     import oracle
     from qpmpc_b200.workloads import oracle_ops
 
-    threads = oracle.num_threads()
-    ops = oracle_ops(workload)
-    B = workload["batch"]
-    args = (B, workload["N"], workload["nx"], workload["nu"], workload["nc"], ops,
-            workload["w_t"], workload["w_x"], workload["w_u"])
-    oracle.solve_batch(*args)  # warm-up (page in, thread pool)
+    return oracle.solve_batch(workload["batch"], workload["N"], workload["nx"], workload["nu"], workload["nc"],
+                              oracle_ops(workload), workload["w_t"], workload["w_x"], workload["w_u"],
+                              nthreads=threads)
+
+
+def cpu_closed_loop(workload, cycles, threads, substeps=15):
+    """Config 3 on the host: the closed loop of examples/wheeled_inverted_pendulum.py:99-118
+    with the oracle as the solver and the host mirror of the plant."""
+    from qpmpc_b200.systems import WheeledInvertedPendulum
+    from qpmpc_b200.workloads import pendulum_targets
+
+    pend = WheeledInvertedPendulum()
+    w = dict(workload)
+    x = w["x0"].copy()
+    T = w["T"]
+    for _ in range(cycles):
+        w["targets"], w["goal"] = pendulum_targets(x, w["v_target"], w["N"], T)
+        w["x0"] = x
+        ref = cpu_solve(w, threads)
+        u0 = np.where(ref["status"] == 0, ref["U"][:, 0], 0.0)
+        # WheeledInvertedPendulum.integrate (systems/wheeled_inverted_pendulum.py:127-160 of the
+        # reference), vectorised over the instances
+        dt = T / substeps
+        for _ in range(substeps):
+            pa = pend.omega**2 * (np.sin(x[:, 1]) - (u0 / pend.GRAVITY) * np.cos(x[:, 1]))
+            x = np.stack([x[:, 0] + dt * x[:, 2] + 0.5 * dt * dt * u0, x[:, 1] + dt * x[:, 3] + 0.5 * dt * dt * pa,
+                          x[:, 2] + dt * u0, x[:, 3] + dt * pa], axis=1)
+    return x
+
+
+def cpu_arm(args, workload, seconds):
+    """Time the oracle on a bounded sample of the workload for about `seconds`;
+    returns (solves/s, threads, sample description)."""
+    from qpmpc_b200.workloads import slice_workload
+
+    threads = host_threads()
+    if args.config == 3:
+        # the closed loop is sequential over cycles: a slice of the batch, fewer cycles
+        k, cyc = min(workload["batch"], 16384), 20
+        ws = slice_workload(workload, 0, k)
+        t0 = time.perf_counter()
+        cpu_closed_loop(ws, cyc, threads)
+        dt = time.perf_counter() - t0
+        return k * cyc / dt, threads, (f"{k} instances x {cyc} closed-loop cycles (C oracle solve on {threads} "
+                                       f"threads + NumPy plant step) in {dt:.1f} s")
+    k = min(workload["batch"], 65536 if workload["N"] <= 16 else 16384 if workload["N"] <= 32 else 4096)
+    ws = slice_workload(workload, 0, k)
+    cpu_solve(ws, threads)  # warm-up (page in, thread pool)
     reps, t0 = 0, time.perf_counter()
     while True:
-        oracle.solve_batch(*args)
+        cpu_solve(ws, threads)
         reps += 1
         dt = time.perf_counter() - t0
-        if reps >= min_reps and dt >= seconds:
+        if dt >= seconds:
             break
-    return B * reps / dt, threads, f"{reps} x {B} instances of the bench workload in {dt:.1f} s"
-
-
-class _StepResult:
-    def __init__(self, status, iters):
-        self.status, self.iters = status, iters
+    return k * reps / dt, threads, f"{reps} x {k} instances of the bench workload (fp64) in {dt:.1f} s"
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the C port of the path on ALL host threads, on the whole job's
+    batch (world x batch instances per step), rank 0 only."""
     if rank != 0:
         return
-    from qpmpc_b200.workloads import triple_integrator_batch
+    from qpmpc_b200.workloads import slice_workload
 
-    import oracle
-
-    w = triple_integrator_batch(args.batch, N=args.horizon, seed=0)
-    ops_args = None
-    from qpmpc_b200.workloads import oracle_ops
-
-    ops_args = (args.batch, w["N"], 3, 1, 2, oracle_ops(w), w["w_t"], w["w_x"], w["w_u"])
-    threads = oracle.num_threads()
-    for _ in range(max(args.warmup, 1)):
-        oracle.solve_batch(*ops_args)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.solve_batch(*ops_args)
-    dt = time.perf_counter() - t0
-    value = args.batch * args.steps / dt
+    threads = host_threads()
+    if args.config == 3:
+        w = make_workload(args, 0)
+        k, cyc = min(args.batch, 16384), 20
+        ws = slice_workload(w, 0, k)
+        for _ in range(min(args.warmup, 1)):
+            cpu_closed_loop(ws, 1, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_closed_loop(ws, cyc, threads)
+        dt = time.perf_counter() - t0
+        value, per_step = k * cyc * args.steps / dt, k * cyc
+        sample = f"{args.steps} steps x ({k} instances x {cyc} closed-loop cycles): C oracle + NumPy plant"
+    else:
+        total = args.batch * world
+        cap = 1 << 20 if args.horizon <= 16 else 1 << 17 if args.horizon <= 32 else 1 << 14
+        k = min(total, cap)
+        saved, args.batch = args.batch, k
+        w = make_workload(args, 0)
+        args.batch = saved
+        for _ in range(max(args.warmup, 1)):
+            cpu_solve(w, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_solve(w, threads)
+        dt = time.perf_counter() - t0
+        value, per_step = k * args.steps / dt, k
+        sample = (f"{args.steps} steps x {k} instances" + ("" if k == total else f" (of the job's {total})")
+                  + ", C oracle (condense + Goldfarb-Idnani), OpenMP")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {args.batch} instances, C oracle "
-                                   "(condense + Goldfarb-Idnani), OpenMP"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(args),
+        "data": "synthetic", "config": config_dict(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "instances_per_step": per_step,
         "note": "reference is pure Python over qpsolvers/proxqp wheels that are not installable "
-                "offline; this arm is the C port of its algorithm (oracle/), on all host threads",
+                f"offline; this arm is the C port of its algorithm (oracle/), on {threads} host threads "
+                "(OMP_NUM_THREADS exported by torchrun is ignored)",
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# roofline helpers
+# ---------------------------------------------------------------------------
+def kernel_name(args):
+    n = args.horizon  # nu = 1 in every config
+    t = "float" if args.config == 4 else "double"
+    if args.method == "pdip":
+        return f"mpc_pdip_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
+    if n > 32:
+        return f"mpc_solve_cta_kernel<{t}>"
+    return f"mpc_solve_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
+
+
+def measured_traffic(args):
+    """dram bytes (read + write) of one launch from the newest committed ncu summary of this
+    kernel and shape (profiles/*.txt written by tools/ncu_summary.py), with its file name;
+    (None, None) when there is none -- never a constant."""
+    want = "mpc_pdip_kernel" if args.method == "pdip" else ("mpc_solve_cta_kernel" if args.horizon > 32
+                                                           else "mpc_solve_kernel")
+    tag = {2: "ti16", 3: "pend", 4: "hum", 5: f"ti{args.horizon}"}[args.config]
+    best = (None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_*.txt"))):
+        base = os.path.basename(path)
+        if tag not in base:
+            continue
+        try:
+            text = open(path).read()
+        except OSError:
+            continue
+        m = re.search(r"== kernel: void (?:qpmpc::)?(\w+)<[^\n]*grid \((\d+)", text)
+        if not m or m.group(1) != want:
+            continue
+        vals = {}
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mm = re.search(re.escape(key) + r"\s+([0-9.]+)\s+(\w?byte)", text)
+            if mm:
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[mm.group(2)]
+                vals[key] = float(mm.group(1)) * mult
+        if len(vals) == 2:
+            best = (sum(vals.values()), base)
+    return best
+
+
+def flop_models(args, iters_mean):
+    """(F of SURVEY 8(d), executed flops of the active-set algorithm) per solve."""
+    N, nu = args.horizon, 1
+    nx = 4 if args.config == 3 else 3
+    nc, n, m = 2, N * nu, 2 * N
+    has_C = args.config != 3
+    has_wx = args.config == 3
+    # SURVEY 8(d): dense, structure-agnostic condensing + K = 10 interior-point iterations
+    f_cond = N * (2 * nx**3 + 2 * nx * nx * n + (2 * nc * nx * n + 2 * nc * nx * nx + 2 * nc * nx if has_C else 0)) \
+        + 2 * nx * n * n + (2 * N * nx * n * n if has_wx else 0)
+    f_iter = 2 * m * n * n + n**3 / 3 + 6 * n * n + 12 * m * n
+    survey = f_cond + 10 * f_iter
+    # executed by the active-set kernel: condensing recursions, Cholesky, forward substitutions for
+    # t and the m rows of M, the final two triangular solves, and per iteration one matrix-vector
+    # product with M plus one Householder update of M
+    f_setup = N * (4 * nx * nx + 2 * nc * nx) * n + n**3 / 3 + (m + 1) * n * n + 2 * n * n
+    executed = f_setup + iters_mean * 6 * m * n
+    return survey, executed
 
 
 # ---------------------------------------------------------------------------
@@ -204,9 +375,8 @@ def run_b200(args, rank, local_rank, world):
 
     import torch
 
-    from qpmpc_b200 import _capi, solve_mpc_batch
-    from qpmpc_b200.workloads import (algorithmic_bytes_per_solve, to_batched,
-                                      triple_integrator_batch)
+    from qpmpc_b200 import _capi, pendulum_closed_loop, solve_mpc_batch
+    from qpmpc_b200.workloads import algorithmic_bytes_per_solve, to_batched
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -219,19 +389,23 @@ def run_b200(args, rank, local_rank, world):
 
     B, N = args.batch, args.horizon
     n = N  # nu = 1
-    sets = [triple_integrator_batch(B, N=N, seed=1000 * rank + s) for s in range(ROTATE)]
-    problems = [to_batched(w, device=dev) for w in sets]
-    U_out = torch.empty((B, n), dtype=torch.float64, device=dev)
-    U_all = torch.empty((world * B, n), dtype=torch.float64, device=dev) if world > 1 else None
-    # N > 1: the kernel's epilogue stores every U row into all ranks' buffers
-    # over NVLink (fused gather); NCCL all-gather only if symmetric memory is
-    # unavailable on the box.
+    tdtype = torch.float32 if args.config == 4 else torch.float64
+    es = 4 if args.config == 4 else 8
+    w0 = make_workload(args, 1000 * rank)
+    bytes_per_solve = algorithmic_bytes_per_solve(w0, es)
+    in_bytes = (bytes_per_solve - es * n - 4) * B
+    rotate = 1 if args.config == 3 else max(2, min(16, int(np.ceil(ROTATE_BYTES / max(in_bytes, 1)))))
+    sets = [w0] + [make_workload(args, 1000 * rank + s) for s in range(1, rotate)]
+    problems = [to_batched(w, dtype=tdtype, device=dev) for w in sets]
+    U_out = torch.empty((B, n), dtype=tdtype, device=dev)
+    U_all = torch.empty((world * B, n), dtype=tdtype, device=dev) if world > 1 else None
     mkw = {} if args.method == "active_set" else {"method": args.method}
     gather, gather_kind = None, "none"
-    if world > 1:
+    if world > 1 and args.config != 3:
         gather_kind = "nccl all_gather_into_tensor"
         # (the fused gather exists for the active-set kernel only)
-        if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer" and args.method == "active_set":
+        if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer" and args.method == "active_set" \
+                and tdtype == torch.float64:
             try:
                 from qpmpc_b200.distributed import PeerGather
 
@@ -240,13 +414,23 @@ def run_b200(args, rank, local_rank, world):
             except Exception as exc:  # noqa: BLE001
                 gather_kind += f" (symmetric memory unavailable: {type(exc).__name__})"
 
+    x0_init = torch.as_tensor(w0["x0"]).to(dev) if args.config == 3 else None
+    v_dev = torch.as_tensor(w0["v_target"]).to(dev) if args.config == 3 else None
+    loop_info = {}
+
     def step(i):
+        if args.config == 3:
+            problems[0].x0.copy_(x0_init)
+            plan, _, unsolved = pendulum_closed_loop(problems[0], v_dev, CYCLES)
+            loop_info["unsolved"] = unsolved
+            return plan
         if gather is not None:
-            _, status, iters = gather.solve(problems[i % ROTATE])
-            return _StepResult(status[rank * B:(rank + 1) * B], iters)
-        plan = solve_mpc_batch(problems[i % ROTATE], out=U_out, **mkw)
+            U, status, iters = gather.solve(problems[i % rotate])
+            return _StepResult(status[rank * B:(rank + 1) * B], iters, U)
+        plan = solve_mpc_batch(problems[i % rotate], out=U_out, **mkw)
         if world > 1:
             dist.all_gather_into_tensor(U_all, U_out)
+            plan.gathered = U_all
         return plan
 
     def barrier():
@@ -257,7 +441,8 @@ def run_b200(args, rank, local_rank, world):
     for i in range(args.warmup):
         plan = step(i)
     barrier()
-    assert int((plan.status != 0).sum().item()) == 0, "warm-up batch has unsolved instances"
+    if args.config != 3:
+        assert int((plan.status != 0).sum().item()) == 0, "warm-up batch has unsolved instances"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -279,121 +464,220 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
 
-    # kernel-only duration (no collective): events around bare launches
-    kev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        kev[2 * i].record()
-        solve_mpc_batch(problems[i % ROTATE], out=U_out, **mkw)
-        kev[2 * i + 1].record()
-    torch.cuda.synchronize()
-    kernel_ms = float(np.mean([kev[2 * i].elapsed_time(kev[2 * i + 1]) for i in range(args.steps)]))
+    # ---- N > 1: the gathered U equals a local re-solve of every other rank's shard ----------
+    gather_check = None
+    if world > 1 and args.config != 3:
+        last = step(0)
+        barrier()
+        got = (last.gathered if hasattr(last, "gathered") else U_all).clone()
+        worst = 0.0
+        for r2 in range(world):
+            w2 = make_workload(args, 1000 * r2)
+            p2 = solve_mpc_batch(to_batched(w2, dtype=tdtype, device=dev), **mkw)
+            torch.cuda.synchronize()
+            diff = (got[r2 * B:(r2 + 1) * B] - p2.inputs.reshape(B, -1)).abs().max().item()
+            worst = max(worst, float(diff))
+        flag = torch.tensor([worst], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        gather_check = {"max_abs_diff_vs_local_resolve": float(flag.item()), "ranks_checked": world,
+                        "rows_per_rank": B}
+        assert gather_check["max_abs_diff_vs_local_resolve"] == 0.0, gather_check
 
-    # ---- e2e: host buffers through the C ABI -----------------------------
+    # ---- kernel-only duration (no collective): events around bare launches -----------------
+    kernel_ms = None
+    if args.config != 3:
+        ksteps = min(args.steps, 256)
+        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * ksteps)]
+        torch.cuda.synchronize()
+        for i in range(ksteps):
+            kev[2 * i].record()
+            solve_mpc_batch(problems[i % rotate], out=U_out, **mkw)
+            kev[2 * i + 1].record()
+        torch.cuda.synchronize()
+        kernel_ms = float(np.mean([kev[2 * i].elapsed_time(kev[2 * i + 1]) for i in range(ksteps)]))
+    else:
+        # the solve kernel's share of a cycle: the same problem solved outside the loop
+        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        kev[0].record()
+        for _ in range(50):
+            solve_mpc_batch(problems[0], out=U_out)
+        kev[1].record()
+        torch.cuda.synchronize()
+        kernel_ms = kev[0].elapsed_time(kev[1]) / 50
+
+    # ---- e2e: host buffers through the C ABI ----------------------------------------------
     lib = _capi.load()
-    host_sets = []
-    for w in sets[:4]:
-        hs = {k: torch.from_numpy(np.ascontiguousarray(w[k])).pin_memory()
-              for k in ("A", "B", "C", "e", "x0", "goal")}
-        host_sets.append(hs)
-    U_host = torch.empty((B, n), dtype=torch.float64).pin_memory()
-    st_host = torch.empty(B, dtype=torch.int32).pin_memory()
-    desc = problems[0].desc() if args.method == "active_set" else problems[0].desc(_capi.PDIP)
-    h2d = sum(t.numel() * 8 for t in host_sets[0].values())
-    d2h = U_host.numel() * 8 + st_host.numel() * 4
-    vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    e2e = None
+    if args.config != 3:
+        np_dtype = np.float32 if args.config == 4 else np.float64
+        names = [k for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets") if sets[0][k] is not None]
+        host_sets = []
+        for w in sets[:min(4, rotate)]:
+            host_sets.append({k: torch.from_numpy(np.ascontiguousarray(w[k], dtype=np_dtype)).pin_memory()
+                              for k in names})
+        # one host array for the whole job: rank r's rows land in [r*B, (r+1)*B) -- the gather
+        shm_path = f"/dev/shm/qpmpc_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{world}"
+        if world > 1:
+            U_job = torch.from_file(shm_path + "_U", shared=True, size=world * B * n, dtype=tdtype)
+            st_job = torch.from_file(shm_path + "_st", shared=True, size=world * B, dtype=torch.int32)
+            cudart = torch.cuda.cudart()
+            for t in (U_job, st_job):
+                rc = cudart.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+                assert int(rc) == 0, rc
+        else:
+            U_job = torch.empty(B * n, dtype=tdtype).pin_memory()
+            st_job = torch.empty(B, dtype=torch.int32).pin_memory()
+        U_host = U_job[rank * B * n:(rank + 1) * B * n]
+        st_host = st_job[rank * B:(rank + 1) * B]
+        desc = problems[0].desc() if args.method == "active_set" else problems[0].desc(_capi.PDIP)
+        h2d = sum(host_sets[0][k].numel() * es for k in names)
+        d2h = U_host.numel() * es + st_host.numel() * 4
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
-    def e2e_step(i):
-        hs = host_sets[i % len(host_sets)]
-        ops = _capi.Operands(vp(hs["A"]), vp(hs["B"]), vp(hs["C"]), None, vp(hs["e"]),
-                             vp(hs["x0"]), vp(hs["goal"]), None)
-        outs = _capi.Outputs(vp(U_host), vp(st_host), None, None)
-        rc = lib.qpmpc_b200_solve_host(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs),
-                                       local_rank)
-        assert rc == 0, rc
+        def e2e_step(i):
+            hs = host_sets[i % len(host_sets)]
+            ops = _capi.Operands(*[vp(hs[k]) if k in hs else None
+                                   for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets")])
+            outs = _capi.Outputs(vp(U_host), vp(st_host), None, None)
+            rc = lib.qpmpc_b200_solve_host(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), local_rank)
+            assert rc == 0, rc
+            if world > 1:
+                dist.barrier()  # every rank's rows are in the shared host array: the gather is complete
 
-    e2e_steps = max(4, min(args.steps, 64))
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert int((st_host != 0).sum()) == 0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_steps = max(4, min(args.steps, 64))
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert int((st_job != 0).sum()) == 0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+            # the job-wide host array holds every rank's rows: compare with the device gather
+            # (last step of the e2e loop used host set (e2e_steps-1) % 4 = device set of the same index)
+            chk = step((e2e_steps - 1) % len(host_sets))
+            barrier()
+            ref_rows = (chk.gathered if hasattr(chk, "gathered") else U_all).cpu().reshape(-1)
+            assert torch.equal(ref_rows, U_job), "shared host array differs from the device gather"
+            dist.barrier()
+            cudart = torch.cuda.cudart()
+            for t in (U_job, st_job):
+                cudart.cudaHostUnregister(t.data_ptr())
+            if rank == 0:
+                for suffix in ("_U", "_st"):
+                    try:
+                        os.unlink(shm_path + suffix)
+                    except OSError:
+                        pass
+        e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "call": "qpmpc_b200_solve_host (pinned host buffers; H2D, kernel, D2H pipelined over streams in "
+                       "chunks; sync per step)" + ("; ranks write their rows into one host array shared by the "
+                                                   "job (the gather), barrier per step" if world > 1 else "")}
+    else:
+        # config 3: the state lives on the device for the whole loop; a step uploads the initial
+        # states / target velocities from pinned host memory and reads the final states back
+        x0_host = torch.from_numpy(np.ascontiguousarray(w0["x0"])).pin_memory()
+        v_host = torch.from_numpy(np.ascontiguousarray(w0["v_target"])).pin_memory()
+        xf_host = torch.empty_like(x0_host).pin_memory()
+        vd = torch.empty_like(v_dev)
+        e2e_steps = max(2, min(args.steps, 8))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            problems[0].x0.copy_(x0_host, non_blocking=True)
+            vd.copy_(v_host, non_blocking=True)
+            pendulum_closed_loop(problems[0], vd, CYCLES)
+            xf_host.copy_(problems[0].x0, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * solves_per_step(args) * e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": x0_host.numel() * 8 + v_host.numel() * 8,
+               "d2h_bytes_per_step": xf_host.numel() * 8, "steps": e2e_steps,
+               "call": "pendulum_closed_loop -> qpmpc_b200_pendulum_closed_loop: initial states and target "
+                       "velocities from pinned host memory, final states read back; sync per step"}
     clocks = sampler.stop()
 
-    # ---- roofline denominators ------------------------------------------
+    # ---- roofline denominators ----------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
         try:
             with open(peaks_path) as f:
-                hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+                hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    bytes_per_solve = algorithmic_bytes_per_solve(sets[0])
     achieved_gbs = bytes_per_solve * B / (kernel_ms * 1e-3) / 1e9
     tf = ctypes.c_double(0.0)
     lib.qpmpc_b200_fp64_peak(local_rank, ctypes.byref(tf))
-    # flops the kernel's algorithm needs per solve: condensing
-    # recursions, Cholesky, forward substitutions for t and the m rows of M,
-    # the final two triangular solves, and per active-set iteration one
-    # matrix-vector product with M plus one Householder update of M.
-    nn, mm = n, 2 * N
-    f_setup = N * (4 * 9 + 2 * 2 * 3) * nn + nn**3 / 3 + (mm + 1) * nn * nn + 2 * nn * nn
-    f_iter = 6 * mm * nn
-    flops_per_solve = f_setup + iters_mean * f_iter
-    achieved_tf = flops_per_solve * B / (kernel_ms * 1e-3) / 1e12
+    f_survey, f_exec = flop_models(args, iters_mean)
+    tfl = lambda f: f * B / (kernel_ms * 1e-3) / 1e12  # noqa: E731
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = world * B * args.steps / (total_ms * 1e-3)
+    value = world * solves_per_step(args) * args.steps / (total_ms * 1e-3)
+    traffic, traffic_src = measured_traffic(args)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, world),
-        "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "call": "qpmpc_b200_solve_host (pinned host buffers; H2D, kernel, D2H pipelined over "
-                        "3 streams in 16384-instance chunks; sync per step)"},
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(args), "data": "synthetic",
+        "config": config_dict(args, world,
+                              f"inputs rotate over {rotate} distinct sets ({rotate}x{in_bytes / 1e6:.1f} MB > L2)"
+                              if rotate > 1 else "state resident on the device across the 200 cycles (the workload)"),
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak,
-                     # dram__bytes_read + write of one launch, ncu --set full (profiles/r01r_solve_ti16_f64.txt)
-                     "traffic": 13774336 if (B, N) == (65536, 16) else None, "peak_source": peak_src,
-                     "kernel": "mpc_solve_kernel<double,NP=%d,MR=2>" % (8 if n <= 8 else 16 if n <= 16 else 32)
-                     if n <= 32 else "mpc_solve_cta_kernel<double>", "kernel_ms": kernel_ms,
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "kernel": kernel_name(args), "kernel_ms": kernel_ms,
                      "bytes_per_solve": bytes_per_solve,
                      "note": "latency/FP64-issue bound by design (SURVEY 8d): HBM fraction is "
                              "necessarily tiny; see fp64"},
-        "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": tf.value,
-                 "frac": achieved_tf / tf.value if tf.value > 0 else None,
-                 "flops_per_solve": flops_per_solve, "peak_source": "qpmpc_b200_fp64_peak (DFMA probe)"},
         "iters_mean": iters_mean, "gather": gather_kind,
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }
-    if args.method != "active_set":
-        # the flop model and the ncu traffic figure above belong to the active-set kernel
-        line["roofline"]["kernel"] = line["roofline"]["kernel"].replace("mpc_solve_kernel", "mpc_pdip_kernel")
-        line["roofline"]["traffic"] = None
-        line["fp64"] = None
+    if args.config != 4 and args.method == "active_set":
+        line["fp64"] = {
+            "peak_tflops": tf.value,
+            "peak_source": "qpmpc_b200_fp64_peak: 16 independent DFMA chains per thread, 8 CTAs of 256 threads "
+                           "per SM, 4096 iterations, best of 4 timed launches (CUDA events); not in "
+                           "MEASURED_PEAKS.json",
+            "survey_F": {"flops_per_solve": f_survey, "achieved_tflops": tfl(f_survey),
+                         "frac": tfl(f_survey) / tf.value if tf.value > 0 else None,
+                         "model": "SURVEY 8(d): dense structure-agnostic condensing + 10 interior-point iterations"},
+            "executed": {"flops_per_solve": f_exec, "achieved_tflops": tfl(f_exec),
+                         "frac": tfl(f_exec) / tf.value if tf.value > 0 else None,
+                         "model": "flops of the active-set algorithm at the measured mean iteration count"},
+        }
+    if gather_check is not None:
+        line["gather_check"] = gather_check
+    if args.config == 3:
+        line["closed_loop"] = {"cycles": CYCLES, "unsolved": int(loop_info["unsolved"].item()),
+                               "upright_frac": float((problems[0].x0[:, 1].abs() < 1.2).float().mean().item()),
+                               "launches_per_step": 2 * CYCLES + 1}
     if not args.no_cpu_baseline:
-        v, threads, sample = cpu_arm(sets[0], args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": sample}
+        v, threads, sample = cpu_arm(args, sets[0], args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _StepResult:
+    def __init__(self, status, iters, gathered=None):
+        self.status, self.iters, self.gathered = status, iters, gathered
 
 
 def main():

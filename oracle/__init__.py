@@ -14,9 +14,11 @@ Pieces:
   * :mod:`oracle.pdip_np` -- NumPy model of the interior-point + polish
     iteration the CUDA kernel runs, used to cross-check the active-set solver.
 
-Solver half: PARITY UNPINNED against proxqp/quadprog themselves (the wheels are
-not installable offline and the reference tests hold no numerical QP answer
-beyond ``U = 0``); see the header of ``mpc_oracle.c``.
+Solver half: pinned to PUBLISHED optima (quadprog's documented example, the
+qpsolvers README example, Hock-Schittkowski 21/35/76/118/268 of the
+Maros-Meszaros set: ``tests/published_qps.py``), not to outputs of the proxqp /
+quadprog wheels themselves (not installable offline; the reference tests hold
+no numerical QP answer beyond ``U = 0``); see the header of ``mpc_oracle.c``.
 """
 
 from .capi import (  # noqa: F401

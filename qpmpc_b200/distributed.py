@@ -88,31 +88,47 @@ class PeerGather:
         self.rows, self.n = int(rows_per_rank), int(nb_vars)
         dev = torch.device("cuda", torch.cuda.current_device())
         total = self.world * self.rows
-        self.U_all = symm_mem.empty((total, self.n), dtype=dtype, device=dev)
-        self.status_all = symm_mem.empty((total,), dtype=torch.int32, device=dev)
-        self._hU = symm_mem.rendezvous(self.U_all, self.group)
-        self._hS = symm_mem.rendezvous(self.status_all, self.group)
-        self._ptrU = [int(v) for v in self._hU.buffer_ptrs]
-        self._ptrS = [int(v) for v in self._hS.buffer_ptrs]
-        if len(self._ptrU) != self.world or not all(self._ptrU):
-            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        self.dtype = dtype
+        # Two sets of buffers used alternately: a rank that is one call ahead stores into the set
+        # its peers are NOT reading (they can only be one call behind: the barrier below), so a
+        # result stays valid, in stream order, until the call after the next one.
+        self._sets = []
+        for _ in range(2):
+            U_all = symm_mem.empty((total, self.n), dtype=dtype, device=dev)
+            status_all = symm_mem.empty((total,), dtype=torch.int32, device=dev)
+            hU = symm_mem.rendezvous(U_all, self.group)
+            hS = symm_mem.rendezvous(status_all, self.group)
+            ptrU = [int(v) for v in hU.buffer_ptrs]
+            ptrS = [int(v) for v in hS.buffer_ptrs]
+            if len(ptrU) != self.world or not all(ptrU):
+                raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+            self._sets.append((U_all, status_all, hU, ptrU, ptrS))
+        self._calls = 0
+        self.U_all, self.status_all = self._sets[0][0], self._sets[0][1]
 
     def solve(self, problem, max_iter: int = 0):
         """Solve this rank's ``rows_per_rank`` instances; on return (stream
-        order) ``U_all`` / ``status_all`` hold the rows of every rank."""
+        order) the returned ``U_all`` / ``status_all`` hold the rows of every
+        rank.  They stay valid until the call after the next one (two buffer
+        sets alternate): consume them in stream order before that."""
         from . import _capi
         from .batched import _ptr
 
         if problem.batch_size != self.rows or problem.nb_vars != self.n:
             raise ValueError("problem does not match the gather buffers")
+        if problem.dtype != self.dtype:
+            raise ValueError(f"problem is {problem.dtype}, the gather buffers are {self.dtype}")
+        U_all, status_all, hU, ptrU, ptrS = self._sets[self._calls % 2]
+        self._calls += 1
+        self.U_all, self.status_all = U_all, status_all
         lib = _capi.load()
         desc = problem.desc(_capi.ACTIVE_SET, max_iter, 0.0)
         peers = _capi.Peers()
         peers.count = self.world
         peers.row_offset = self.rank * self.rows
         for r in range(self.world):
-            peers.U[r] = self._ptrU[r]
-            peers.status[r] = self._ptrS[r]
+            peers.U[r] = ptrU[r]
+            peers.status[r] = ptrS[r]
         iters = torch.empty(self.rows, dtype=torch.int32, device=problem.device)
         outs = _capi.Outputs(None, None, _ptr(iters), None)
         ops = problem.operands()
@@ -120,5 +136,5 @@ class PeerGather:
         rc = lib.qpmpc_b200_solve_scatter(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs),
                                           ctypes.byref(peers), stream)
         _capi.check(rc, "qpmpc_b200_solve_scatter")
-        self._hU.barrier()  # every rank's stores have landed everywhere
-        return self.U_all, self.status_all, iters
+        hU.barrier()  # every rank's stores have landed everywhere
+        return U_all, status_all, iters

@@ -422,3 +422,27 @@ def test_non_finite_operands_are_flagged_not_returned():
         assert np.isnan(U[bad]).all()
         good = np.setdiff1d(np.arange(40), bad)
         assert (st[good] == 0).all() and np.isfinite(U[good]).all()
+
+
+# -- published known-answer QPs ---------------------------------------------------------------
+
+@pytest.mark.parametrize("method", ["active_set", "pdip"])
+def test_published_optima_on_the_device(method):
+    """The solver half pinned to answers published by others: quadprog's documented example,
+    the qpsolvers README example and Hock-Schittkowski 21 / 35 / 76 / 118 / 268 (citations in
+    tests/published_qps.py), written as one-step MPC problems and solved through the C ABI by
+    both kernels -- x* to the printed digits, the printed multipliers, and the oracle on the side."""
+    import published_qps
+
+    for make in published_qps.ALL:
+        qp = make()
+        w = published_qps.as_one_step_mpc(qp)
+        _, plan = _solve(w, method=method, tol=1e-9)
+        assert int(plan.status[0]) == 0, qp["name"]
+        x = plan.inputs.reshape(-1).cpu().numpy()
+        bar = max(qp["x_tol"], 1e-7) * max(1.0, np.abs(qp["x"]).max())
+        assert np.abs(x - qp["x"]).max() <= bar, (qp["name"], x, qp["x"])
+        if qp["z"] is not None:
+            assert np.abs(plan.multipliers[0].cpu().numpy() - qp["z"]).max() <= 1e-6
+        ref = _oracle(w)
+        assert ref["status"][0] == 0 and np.abs(x - ref["U"][0]).max() <= U_TOL

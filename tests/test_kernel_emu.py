@@ -342,3 +342,22 @@ def test_random_problems_both_methods(N, nx, nu, nc, ltv, with_C, with_D, cost, 
         assert np.array_equal(both, feas)
     if both.any():
         assert (np.abs(b["U"][both] - ref["U"][both]).max(axis=1) / scale[both]).max() <= U_TOL
+
+
+# -- published known-answer QPs through the device source ------------------------------------
+
+import published_qps  # noqa: E402
+
+
+@pytest.mark.parametrize("method", ["active_set", "pdip"])
+@pytest.mark.parametrize("make", published_qps.ALL, ids=lambda f: f.__name__)
+def test_kernels_reproduce_published_optima(make, method):
+    """quadprog's documented example, the qpsolvers README example, Hock-Schittkowski 21 / 35 /
+    76 / 118 / 268 (tests/published_qps.py) as one-step MPC problems through the fused kernels:
+    the answer is the PUBLISHED x*, not an oracle's."""
+    qp = make()
+    got = emu.solve(published_qps.as_one_step_mpc(qp), method=method, tol=1e-9)
+    assert got["rc"] == 0 and got["status"][0] == 0
+    assert np.abs(got["U"][0] - qp["x"]).max() <= max(qp["x_tol"], 1e-7) * max(1.0, np.abs(qp["x"]).max())
+    if qp["z"] is not None:
+        assert np.abs(got["z"][0] - qp["z"]).max() <= 1e-6
