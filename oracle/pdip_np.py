@@ -37,8 +37,8 @@ def _solve(L, b):
     return np.linalg.solve(np.swapaxes(L, -1, -2), y)[..., 0]
 
 
-def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=3,
-               delta=1e-7, polish_rounds=4):
+def pdip_batch(P, q, G, h, max_iter=40, tol=1e-9, polish=True, polish_steps=8,
+               delta=1e-7, polish_rounds=8):
     """Solve a batch of QPs.  P [B,n,n], q [B,n], G [B,m,n], h [B,m].
 
     Returns dict(U, z, status, iters): status 0 solved, 1 max_iter, 2 numerical.
@@ -151,37 +151,60 @@ def _polish(P, q, G, h, u, s, z, steps, delta, rounds, eps=1e-9, strict=None):
     accepted = np.zeros(B, dtype=bool)
     hrow = np.maximum(1.0, np.abs(h))
     qscale = np.maximum(1.0, np.abs(q).max(axis=1))
+    pmin = np.linalg.eigvalsh(P)[:, 0]  # the kernel uses w_u <= lambda_min(P)
     for _ in range(rounds):
         if accepted.all():
             break
         H = P + np.einsum("bmi,bm,bmj->bij", G, act / delta, G)
         L, spd = _cholesky_each(H)
         lam = np.where(act, lam, 0.0)
-        for _ in range(steps):
-            r1 = np.einsum("bij,bj->bi", P, up) + q + np.einsum("bmn,bm->bn", G, lam)
-            r2 = np.where(act, np.einsum("bmn,bn->bm", G, up) - h, 0.0)
+        frozen = accepted.copy()
+        for step in range(steps + 1):
+            # residuals first; steps move (up, lam) until the stationarity residual is as small as
+            # the parity bar needs (|r1| <= 1e-9 lambda_min(P) |u|) or as rounding allows
+            Pu = np.einsum("bij,bj->bi", P, up)
+            Gtl = np.einsum("bmn,bm->bn", G, lam)
+            Gu = np.einsum("bmn,bn->bm", G, up)
+            r1 = Pu + q + Gtl
+            viol = Gu - h
+            r2 = np.where(act, viol, 0.0)
+            pscale = np.where(strict[:, None], hrow, np.maximum(hrow, np.abs(Gu)))  # row by row
+            dscale = np.where(strict, qscale, np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1)))
+            uscale = np.maximum(1.0, np.abs(up).max(axis=1))
+            rd_tol = np.maximum(1e-9 * pmin * uscale, 64 * 2.3e-16 * dscale)
+            with np.errstate(invalid="ignore"):
+                tight = (np.abs(r1).max(axis=1) <= rd_tol) & (np.abs(r2) <= eps * pscale).all(axis=1)
+            frozen |= tight
+            if step == steps or frozen.all():
+                break
             du = _solve(L, -(r1 + np.einsum("bmn,bm->bn", G, r2 / delta)))
-            lam = lam + np.where(act, (r2 + np.einsum("bmn,bn->bm", G, du)) / delta, 0.0)
+            du = np.where(frozen[:, None], 0.0, du)
+            lam = lam + np.where(act & ~frozen[:, None], (r2 + np.einsum("bmn,bn->bm", G, du)) / delta, 0.0)
             up = up + du
-        Pu = np.einsum("bij,bj->bi", P, up)
-        Gtl = np.einsum("bmn,bm->bn", G, lam)
-        Gu = np.einsum("bmn,bn->bm", G, up)
-        viol = Gu - h
         zscale = np.maximum(1.0, np.abs(lam).max(axis=1, initial=0.0))[:, None]
-        dscale = np.where(strict, qscale, np.maximum(qscale, np.maximum(np.abs(Pu), np.abs(Gtl)).max(axis=1)))
-        pscale = np.where(strict[:, None], hrow, np.maximum(hrow, np.abs(Gu)))  # row by row
-        r_d = Pu + q + Gtl
         with np.errstate(invalid="ignore"):
             finite = np.isfinite(up).all(axis=1) & np.isfinite(lam).all(axis=1)
-        ok = (
-            spd & finite
-            & (viol <= eps * pscale).all(axis=1)
-            & (np.abs(np.where(act, viol, 0.0)) <= eps * pscale).all(axis=1)
-            & (lam >= -eps * zscale).all(axis=1)
-            & (np.abs(r_d).max(axis=1) <= eps * dscale)
-        )
+            ok = (
+                spd & finite
+                & (viol <= eps * pscale).all(axis=1)
+                & (np.abs(np.where(act, viol, 0.0)) <= eps * pscale).all(axis=1)
+                # (a multiplier of -e moves u by up to e |g| / lambda_min(P): held to the same bar)
+                & (lam >= -np.maximum(1e-9 * pmin * uscale, 64 * 2.3e-16 * zscale[:, 0])[:, None]).all(axis=1)
+                & (np.abs(r1).max(axis=1) <= rd_tol)
+            )
         new = ok & ~accepted
         u_out[new], z_out[new] = up[new], lam[new]
         accepted |= ok
-        act = np.where(act, lam > 0.0, viol > 0.0)
+        # correct the guess by ONE row: the most violated row enters; if nothing is violated the
+        # most negative multiplier leaves (changing many rows at once can cycle)
+        vrel = np.where(act, -np.inf, viol / pscale)
+        worst = vrel.argmax(axis=1)
+        has_viol = vrel.max(axis=1) > eps
+        lneg = np.where(act, lam, np.inf)
+        drop = lneg.argmin(axis=1)
+        rows = np.arange(B)
+        act = act.copy()
+        act[rows[has_viol], worst[has_viol]] = True
+        sel = ~has_viol & (lneg.min(axis=1) < 0.0)
+        act[rows[sel], drop[sel]] = False
     return u_out, z_out, accepted

@@ -55,6 +55,9 @@ class BatchedMPCProblem:
             tensor is a per-step stack shared by the batch rather than a
             per-instance stack.
         batch_size: Needed only when no operand carries the batch axis.
+        paired_rows: Whether every ``C_k``, ``D_k`` has the form ``[M; -M]`` (two-sided
+            bounds, e.g. ``|u| <= u_max``): the kernels then keep one row per pair
+            (``qpmpc_b200_desc.paired``).  ``None`` (default) checks the operands once, here.
     """
 
     def __init__(
@@ -75,6 +78,7 @@ class BatchedMPCProblem:
         batch_size: Optional[int] = None,
         dtype: torch.dtype = torch.float64,
         device=None,
+        paired_rows: Optional[bool] = None,
     ) -> None:
         if stage_input_cost_weight <= 0.0:
             raise ProblemDefinitionError("the input weight must be positive")
@@ -110,6 +114,7 @@ class BatchedMPCProblem:
         self.C, self.mode_C = self._matrix("C", C, (nc, nx), True)
         self.D, self.mode_D = self._matrix("D", D, (nc, nu), True)
         self.e, self.mode_e = self._matrix("e", e, (nc,), nc == 0)
+        self.paired_rows = self._rows_paired() if paired_rows is None else bool(paired_rows)
         self.x0 = self.goal = self.targets = None
         self.mode_x0 = self.mode_goal = self.mode_targets = _capi.VEC_ABSENT
         if initial_state is not None:
@@ -131,6 +136,13 @@ class BatchedMPCProblem:
         if not isinstance(value, torch.Tensor):
             value = torch.as_tensor(np.asarray(value))
         return value.to(device=self.device, dtype=self.dtype).contiguous()
+
+    def _rows_paired(self) -> bool:
+        nc = self.ineq_dim
+        if nc == 0 or nc % 2 or (self.C is None and self.D is None):
+            return False
+        h = nc // 2
+        return all(bool(torch.equal(t[..., :h, :], -t[..., h:, :])) for t in (self.C, self.D) if t is not None)
 
     def _set_batch(self, b: int, what: str) -> None:
         if self._batch is None:
@@ -232,6 +244,7 @@ class BatchedMPCProblem:
         d.w_u = self.stage_input_cost_weight
         d.method, d.max_iter, d.tol = method, int(max_iter), float(tol)
         d.flags = 0 if polish else _capi.FLAG_NO_POLISH
+        d.paired = int(self.paired_rows)
         return d
 
     def operands(self) -> _capi.Operands:

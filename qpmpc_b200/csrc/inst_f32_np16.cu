@@ -5,4 +5,5 @@
 namespace qpmpc {
 QPMPC_INSTANTIATE_VARIANT(float, 16, 2, true)
 QPMPC_INSTANTIATE_VARIANT(float, 16, 4, false)
+QPMPC_INSTANTIATE_PAIRED(float, 16)
 }  // namespace qpmpc

@@ -5,4 +5,5 @@
 namespace qpmpc {
 QPMPC_INSTANTIATE_VARIANT(float, 32, 2, false)
 QPMPC_INSTANTIATE_VARIANT(float, 32, 4, false)
+QPMPC_INSTANTIATE_PAIRED(float, 32)
 }  // namespace qpmpc

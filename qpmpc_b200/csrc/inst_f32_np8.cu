@@ -5,4 +5,5 @@
 namespace qpmpc {
 QPMPC_INSTANTIATE_VARIANT(float, 8, 2, true)
 QPMPC_INSTANTIATE_VARIANT(float, 8, 4, true)
+QPMPC_INSTANTIATE_PAIRED(float, 8)
 }  // namespace qpmpc

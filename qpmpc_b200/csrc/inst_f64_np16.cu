@@ -7,4 +7,5 @@ QPMPC_INSTANTIATE_VARIANT(double, 16, 2, true)
 QPMPC_INSTANTIATE_PDIP(16, 2)
 QPMPC_INSTANTIATE_VARIANT(double, 16, 4, false)
 QPMPC_INSTANTIATE_PDIP(16, 4)
+QPMPC_INSTANTIATE_PAIRED(double, 16)
 }  // namespace qpmpc

@@ -7,4 +7,5 @@ QPMPC_INSTANTIATE_VARIANT(double, 32, 2, false)
 QPMPC_INSTANTIATE_PDIP(32, 2)
 QPMPC_INSTANTIATE_VARIANT(double, 32, 4, false)
 QPMPC_INSTANTIATE_PDIP(32, 4)
+QPMPC_INSTANTIATE_PAIRED(double, 32)
 }  // namespace qpmpc

@@ -7,4 +7,5 @@ QPMPC_INSTANTIATE_VARIANT(double, 8, 2, true)
 QPMPC_INSTANTIATE_PDIP(8, 2)
 QPMPC_INSTANTIATE_VARIANT(double, 8, 4, true)
 QPMPC_INSTANTIATE_PDIP(8, 4)
+QPMPC_INSTANTIATE_PAIRED(double, 8)
 }  // namespace qpmpc

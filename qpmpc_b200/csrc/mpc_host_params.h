@@ -15,12 +15,20 @@ namespace qpmpc {
 struct Variant {
     int np, mr;
     bool mreg;
+    bool paired;
 };
 
-// Smallest compiled (NP, MR) that holds n variables and m constraint rows.
-inline bool pick_variant(int n, int m, Variant *out) {
-    static const Variant table[] = {{8, 2, true},  {8, 4, true},   {16, 2, true},
-                                    {16, 4, false}, {32, 2, false}, {32, 4, false}};
+// Smallest compiled (NP, MR) that holds n variables and m constraint rows.  With `paired` rows
+// (desc.paired: every C_k, D_k is [M; -M]) one stored row per lane covers m = 2 NP rows.
+inline bool pick_variant(int n, int m, Variant *out, bool paired = false) {
+    static const Variant table[] = {{8, 2, true, false},   {8, 4, true, false},   {16, 2, true, false},
+                                    {16, 4, false, false}, {32, 2, false, false}, {32, 4, false, false}};
+    if (paired)
+        for (int np = 8; np <= 32; np *= 2)
+            if (n <= np && m <= 2 * np) {
+                *out = Variant{np, 1, true, true};
+                return true;
+            }
     for (const Variant &v : table)
         if (n <= v.np && m <= v.np * v.mr) {
             *out = v;

@@ -47,14 +47,18 @@
 
 namespace qpmpc {
 
-template <typename T, int NP, int MR, bool MREG, bool RS = false>
+// PAIRED: the constraint rows come in pairs [G+; -G+] (two-sided bounds, desc.paired): only the
+// MR * NP rows G+ are kept (as rows of M), each standing for both of its signs; h and a dense G
+// (time-varying models) still hold all 2 MR NP rows.
+template <typename T, int NP, int MR, bool MREG, bool RS = false, bool PAIRED = false>
 struct Lay {
-    static constexpr int MP = MR * NP;     // padded constraint rows
-    static constexpr int LDG = MP + 1;     // G / M by columns: Gc[c*LDG + row]
+    static constexpr int MP = MR * NP;     // padded (stored) constraint rows
+    static constexpr int HP = PAIRED ? 2 * MP : MP;  // padded rows of h and of the dense G
+    static constexpr int LDG = HP + 1;     // G / M by columns: Gc[c*LDG + row]
     static constexpr int LDL = NP + 2;     // L by columns:     Lc[c*LDL + row]
     static constexpr int szG = ((NP * LDG + 3) / 4) * 4;
-    static constexpr int oH = 0;           // hs[MP]
-    static constexpr int oRL = oH + MP;    // psi exchange (A), Lc (B and, if MREG, the final solve)
+    static constexpr int oH = 0;           // hs[HP]
+    static constexpr int oRL = oH + HP;    // psi exchange (A), Lc (B and, if MREG, the final solve)
     static constexpr int szRL = ((NP * LDL + 3) / 4) * 4;
     // R^-1 by columns: its own region when L must survive (MREG), else over L
     static constexpr int oRi = MREG ? oRL + szRL : oRL;
@@ -67,6 +71,7 @@ struct Lay {
     static constexpr int fixed = oW + (ROWS_IN_SMEM ? 3 * MP : 0);  // runtime-sized tail follows (TailLay)
     static_assert(NP * NP <= szRL, "R^-1 must fit in the L region");
     static_assert(8 * NP <= szRL, "psi exchange buffers must fit in the L region");
+    static_assert(!PAIRED || (MREG && !RS), "paired rows: register-resident M, row constants in registers");
 };
 
 // Scratch of the generic (any nx) condensing: psi[2][nx][NP], xbar[2][nx],
@@ -603,10 +608,10 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     shared memory, row l of J is kept in registers and x moves with every
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR, bool MREG, bool RS>  // @phase kernel prologue
+template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false>  // @phase kernel prologue
 __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : QPMPC_MINB / 2) : 1)
     mpc_solve_kernel(const SolveParams p) {
-    using L = Lay<T, NP, MR, MREG, RS>;
+    using L = Lay<T, NP, MR, MREG, RS, PAIRED>;
     using T2 = typename Pair<T>::type;
     constexpr bool HASJ = !MREG;
     constexpr int IPW = 32 / NP;  // instances per warp
@@ -657,8 +662,9 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
     T Prow[NP];
     T qj;
     // prefix-sum table of the stage-cost Hessian: any NP x NP scratch that is free before phase B
-    condense_dispatch<T, NP, MR, false>(p, in, Gc, gt, hs, Lc, MREG ? Ri : Gc, wk + p.scr_off, l, Prow, qj, inst,
-                                        valid);
+    // (the condensing code sizes G by its second integer parameter: all 2 MR NP rows when paired)
+    condense_dispatch<T, NP, PAIRED ? 2 * MR : MR, false>(p, in, Gc, gt, hs, Lc, MREG ? Ri : Gc, wk + p.scr_off, l,
+                                                          Prow, qj, inst, valid);
 
     // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----  // @phase B cholesky
     bool spd = true;
@@ -692,7 +698,12 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
     T Jrow[HASJ ? NP : 1];
     T Mrow[MREG ? MR : 1][NP];
     T x = T(0);
+    // unpaired: viol[s] = G_i x - h_i.  Paired: the stored row G+ stands for G+ x <= h+ and
+    // -G+ x <= h-, i.e. |G+ x - cen| <= wid with cen = (h+ - h-)/2, wid = (h+ + h-)/2; viol[s]
+    // holds G+ x and the violation of the worse sign is |viol[s] - cen[s]| - wid[s].
     T viol[MR];
+    T cen[PAIRED ? MR : 1], wid[PAIRED ? MR : 1];
+    const int half = PAIRED ? (p.nc >> 1) : 1;  // rows per step of G+
     T rowc[RS ? 1 : 3][RS ? 1 : MR];                  // vtol, ginv, |M_i|^2 in registers ...
     T *rowc_s = wk + L::oW;                            // ... or in shared memory [3][MP]
     auto rc_set = [&](int which, int s, T v) {
@@ -715,12 +726,14 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
         }
         // row s of G into dst; row norm and tolerance of the violation test
         auto load_row = [&](int s, T(&dst)[NP]) {
-            const int row = l + s * NP;
-            rowvalid[s] = row < m;
+            const int srow = l + s * NP;  // stored row
+            rowvalid[s] = srow < (PAIRED ? (m >> 1) : m);
             T g2 = T(0), g21 = T(0);
             // (k, r) of this row; its slice of the Toeplitz table runs backwards
             // from gtr[0] = G[row, k nu - 1] (see g_toeplitz)
-            const int rk = rowvalid[s] ? row / p.nc : 0, rr = rowvalid[s] ? row - rk * p.nc : 0;
+            const int rpk = PAIRED ? half : p.nc;  // stored rows per step
+            const int rk = rowvalid[s] ? srow / rpk : 0, rr = rowvalid[s] ? srow - rk * rpk : 0;
+            const int row = PAIRED ? rk * p.nc + rr : srow;  // index of the (+) row in G and h
             const int kb = (toep && rowvalid[s]) ? rk * p.nu : 0;
             const T *gtr = gt ? gt + rr * n + kb - 1 : nullptr;
             const T *Dr = (toep && rowvalid[s] && in[OP_D]) ? in[OP_D] + rk * p.op[OP_D].step + rr * p.nu - kb : nullptr;
@@ -751,8 +764,15 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
             }
             g2 += g21;
             // eps * (max(1, |h_i|) + |G_i|)
-            const T hi = rowvalid[s] ? hs[row] : T(0);
+            T hi = rowvalid[s] ? hs[row] : T(0);
             viol[s] = -hi;
+            if (PAIRED) {
+                const T hm = rowvalid[s] ? hs[row + half] : T(0);
+                cen[PAIRED ? s : 0] = rowvalid[s] ? T(0.5) * (hi - hm) : T(0);
+                wid[PAIRED ? s : 0] = rowvalid[s] ? T(0.5) * (hi + hm) : T(1);
+                hi = fmax(abs_(hi), abs_(hm));
+                viol[s] = T(0);
+            }
             rc_set(0, s, Num<T>::viol_eps * (fmax(T(1), abs_(hi)) + sqrt_(g2)));
             rc_set(1, s, g2 > T(0) ? frsqrt_(g2) : T(1e30));
         };
@@ -768,7 +788,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
             }
             rc_set(2, s, m0 + m1);
             // G x - h with x = -P^-1 q = -J t: G x = -(G J) t = -M t
-            viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : T(-1);
+            viol[s] = rowvalid[s] ? viol[s] - (v0 + v1) : (PAIRED ? T(0) : T(-1));
             if (!MREG) {
                 // In place: this lane is the only reader and writer of its rows of G.
                 const int row = l + s * NP;
@@ -776,7 +796,12 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
                 for (int c = 0; c < NP; ++c) Gc[c * L::LDG + row] = src[c];
             }
         };
-        if (MREG) {
+        if (MREG && MR == 1) {
+            // one stored row per lane (paired rows): t rides along with it
+            load_row(0, Mrow[0]);
+            fsolve<T, NP, L::LDL, 2>(Lc, dv, tq, Mrow[0], Mrow[0]);
+            finish_row(0, Mrow[0]);
+        } else if (MREG) {
             // t rides along with the first two rows of M, solved in place in Mrow
             load_row(0, Mrow[0]);
             load_row(1, Mrow[MREG ? 1 : 0]);
@@ -836,9 +861,18 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
     const int max_iter = p.max_iter;
     int na = 0, it = 0;
     int st = spd ? 0 : 3;
+    if (PAIRED) {
+        // a pair with h+ + h- < 0 admits no point at all: infeasible, as the unpaired iteration
+        // finds out when the second member meets the first in the active set (t1 = t2 = inf)
+        bool bad = false;
+#pragma unroll
+        for (int s = 0; s < MR; ++s) bad = bad || (rowvalid[s] && wid[PAIRED ? s : 0] < -rc_get(0, s));
+        if ((__ballot_sync(FULL_MASK, bad) & segmask) && st == 0) st = 2;
+    }
     bool done = !valid || st != 0 || m == 0;
     bool cont = false;
     int pidx = 0;
+    bool pneg = false;  // paired: the candidate is the (-) member of its pair
     T lam = T(0), lamp = T(0);
     int aidx = -1;
     unsigned actbits = 0;
@@ -853,10 +887,12 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
             int bi = 0;
 #pragma unroll
             for (int s = 0; s < MR; ++s) {
-                const T score = viol[s] * rc_get(1, s);
-                if (sel && rowvalid[s] && !((actbits >> s) & 1) && viol[s] > rc_get(0, s) && score > best) {
+                const T off = PAIRED ? viol[s] - cen[PAIRED ? s : 0] : T(0);
+                const T vs = PAIRED ? abs_(off) - wid[PAIRED ? s : 0] : viol[s];
+                const T score = vs * rc_get(1, s);
+                if (sel && rowvalid[s] && !((actbits >> s) & 1) && vs > rc_get(0, s) && score > best) {
                     best = score;
-                    bi = l + s * NP;
+                    bi = (l + s * NP) | ((PAIRED && off < T(0)) ? 0x8000 : 0);
                 }
             }
             // single-precision keys: the ranking is a heuristic, any violated row is a valid pivot
@@ -868,7 +904,8 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
                 if (!(top > 0.f)) {
                     done = true;  // primal feasible: optimal
                 } else {
-                    pidx = cand_p;
+                    pidx = cand_p & 0x7fff;
+                    pneg = (cand_p & 0x8000) != 0;
                     lamp = T(0);
                 }
             }
@@ -892,14 +929,16 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
                     if (s == pslot) {
+                        // the (-) member of a pair is the row -G+: row p of M is -Mrow
+                        const T sg = (PAIRED && pneg) ? T(-1) : T(1);
 #pragma unroll
                         for (int c = 0; c < NP; c += 2) {
                             T2 v;
-                            v.x = Mrow[MREG ? s : 0][c];
-                            v.y = Mrow[MREG ? s : 0][c + 1];
+                            v.x = sg * Mrow[MREG ? s : 0][c];
+                            v.y = sg * Mrow[MREG ? s : 0][c + 1];
                             *reinterpret_cast<T2 *>(dd + c) = v;
                         }
-                        sc[0] = viol[s];
+                        sc[0] = PAIRED ? abs_(viol[s] - cen[PAIRED ? s : 0]) - wid[PAIRED ? s : 0] : viol[s];
                         sc[1] = rc_get(2, s);
                     }
                 }
@@ -1034,7 +1073,8 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
                 if (l == na) {
                     Ri[na * NP + na] = binv;
                     lam = lamp;
-                    aidx = pidx;
+                    // aidx is the row's index in G / h (what Z and the recovery of x use)
+                    aidx = PAIRED ? (pidx / half) * p.nc + pidx % half + (pneg ? half : 0) : pidx;
                 }
                 if (l == owner) actbits |= 1u << pslot;
                 ++na;
@@ -1043,7 +1083,13 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
         }
         if (__any_sync(FULL_MASK, part)) {  // @phase C drop constraint (Givens)
             // Constraint at active position lidx leaves; p stays the candidate.
-            const int cidx = __shfl_sync(FULL_MASK, aidx, lidx, NP);
+            int cidx = __shfl_sync(FULL_MASK, aidx, lidx, NP);
+            if (PAIRED) {
+                // row index in G -> stored row
+                const int nc_ = p.nc > 0 ? p.nc : 2;
+                const int ck = (cidx >= 0 ? cidx : 0) / nc_, cr = (cidx >= 0 ? cidx : 0) - ck * nc_;
+                cidx = ck * half + (cr >= half ? cr - half : cr);
+            }
             if (part && l == cidx % NP) actbits &= ~(1u << (cidx / NP));
             const T lam_n = __shfl_down_sync(FULL_MASK, lam, 1, NP);
             const int aidx_n = __shfl_down_sync(FULL_MASK, aidx, 1, NP);

@@ -15,6 +15,8 @@ void count_launch();                        // qpmpc_b200.cu
 
 template <typename T, int NP, int MR, bool MREG>
 int launch_solve(SolveParams p, cudaStream_t stream);
+template <typename T, int NP>  // paired rows (desc.paired): one stored row per lane stands for [G+; -G+]
+int launch_solve_paired(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
 int launch_condense(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
@@ -28,11 +30,11 @@ int launch_pdip(SolveParams p, int polish, cudaStream_t stream);  // mpc_pdip.cu
 
 namespace qpmpc {
 
-template <typename T, int NP, int MR, bool MREG, bool RS>
+template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false>
 int launch_solve_variant(SolveParams p, cudaStream_t stream) {
-    using L = Lay<T, NP, MR, MREG, RS>;
+    using L = Lay<T, NP, MR, MREG, RS, PAIRED>;
     constexpr int IPW = 32 / NP;
-    int wpc = env_int("QPMPC_B200_WPC", 8);
+    int wpc = env_int("QPMPC_B200_WPC", (PAIRED && NP == 32) ? 4 : 8);
     if (wpc < 1) wpc = 1;
     if (wpc > 8) wpc = 8;
     size_t smem = 0;
@@ -45,7 +47,7 @@ int launch_solve_variant(SolveParams p, cudaStream_t stream) {
     const size_t pad = (size_t)env_int("QPMPC_B200_SMEM_PAD_KB", 0) * 1024;
     if (pad && smem + pad <= 227 * 1024) smem += pad;
     const int ipc = IPW * wpc;
-    auto kern = mpc_solve_kernel<T, NP, MR, MREG, RS>;
+    auto kern = mpc_solve_kernel<T, NP, MR, MREG, RS, PAIRED>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const int grid = (p.batch + ipc - 1) / ipc;
@@ -67,6 +69,11 @@ int launch_solve(SolveParams p, cudaStream_t stream) {
         if (rs > 0 || (rs < 0 && !p.has_wx)) return launch_solve_variant<T, NP, MR, MREG, true>(p, stream);
     }
     return launch_solve_variant<T, NP, MR, MREG, false>(p, stream);
+}
+
+template <typename T, int NP>
+int launch_solve_paired(SolveParams p, cudaStream_t stream) {
+    return launch_solve_variant<T, NP, 1, true, false, true>(p, stream);
 }
 
 template <typename T, int NP, int MR>
@@ -141,6 +148,7 @@ int launch_pdip(SolveParams p, int polish, cudaStream_t stream) {
 #define QPMPC_INSTANTIATE_VARIANT(T, NP, MR, MREG)                               \
     template int launch_solve<T, NP, MR, MREG>(SolveParams, cudaStream_t);      \
     template int launch_condense<T, NP, MR>(SolveParams, cudaStream_t);
+#define QPMPC_INSTANTIATE_PAIRED(T, NP) template int launch_solve_paired<T, NP>(SolveParams, cudaStream_t);
 // the interior-point kernel is double precision only (qpmpc_b200.cu:solve_impl)
 #define QPMPC_INSTANTIATE_PDIP(NP, MR) template int launch_pdip<double, NP, MR>(SolveParams, int, cudaStream_t);
 

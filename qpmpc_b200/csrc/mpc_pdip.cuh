@@ -22,7 +22,7 @@
 //   C  primal-dual active-set polish: rows with z > s form the active set A; a
 //      few proximal multiplier steps in residual form on the equality QP of A
 //      reuse the same build / factor / solve code with W = 1_A / delta; a
-//      point that fails the KKT test corrects A and repeats (<= 4 rounds).
+//      point that fails the KKT test corrects A by one row and repeats (<= 8 rounds).
 //      An accepted point is the exact solution, as the active-set kernel
 //      returns it: this is what makes |dU| <= 1e-6 hold at w_u = 1e-6
 //   D  U (coalesced), status, iteration count, multipliers
@@ -43,15 +43,21 @@ template <> struct PdipNum<double> {
     static constexpr double tol_min = 1e-13;    // below this the residuals are rounding noise
     static constexpr double delta = 1e-7;       // proximal parameter of the polish
     static constexpr double polish_eps = 1e-9;  // acceptance test of the polished point
+    static constexpr double stat_eps = 1e-9;    // stationarity: |r| <= stat_eps lambda_min(P) |u|, i.e. |du| <= 1e-9 |u|
+    static constexpr double macheps = 2.3e-16;
     static constexpr double step_frac = 0.99;
-    static constexpr int polish_rounds = 4;
+    static constexpr int polish_rounds = 8;
+    static constexpr int polish_steps = 8;      // proximal steps per round, at most
 };
 template <> struct PdipNum<float> {
     static constexpr float tol_min = 1e-6f;
     static constexpr float delta = 1e-3f;
     static constexpr float polish_eps = 1e-4f;
+    static constexpr float stat_eps = 1e-3f;
+    static constexpr float macheps = 1.2e-7f;
     static constexpr float step_frac = 0.99f;
-    static constexpr int polish_rounds = 4;
+    static constexpr int polish_rounds = 8;
+    static constexpr int polish_steps = 8;
 };
 
 // Per-instance shared-memory regions of the interior-point kernel (elements of
@@ -247,14 +253,15 @@ __device__ __forceinline__ T pdip_step(const T (&sl)[MR], const T (&z)[MR], cons
 // lock step; the other groups of the warp run their own instances and the
 // loop ends when every group of the warp is done).
 //   in : Pc, Gc, hs in shared memory, qj = q_l; n, m real sizes (padding
-//        variables have P = identity, q = 0, zero columns of G)
+//        variables have P = identity, q = 0, zero columns of G); pmin, a lower
+//        bound of lambda_min(P) (w_u for a condensed MPC problem, mpc_qp.py:99-105)
 //   out: x (component l of U), z (multipliers of the owned rows), status,
 //        iterations
 // Scratch: Lc [NP*LDL], xs [NP], dv [NP], wv [MP], tv [MP].
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool LS = false>
 __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const T *hs, T *Lc, T *xs, T *dv, T *wv,
-                                          T *tv, int m, int l, bool valid, int max_iter, T tol, bool polish,
+                                          T *tv, int m, int l, bool valid, int max_iter, T tol, bool polish, T pmin,
                                           T &x_out, T (&z_out)[MR], int &st_out, int &it_out) {
     using L = PdipLay<T, NP, MR>;
     constexpr int LDG = L::LDG, LDL = L::LDL;
@@ -429,8 +436,13 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             __syncwarp();
             if (LS) pdip_invert<T, NP, LDL>(Lc, dv, l);
             T rd = T(0), pxp = T(0), gtl = T(0);
-            // steps 0 .. 2 move (up, lam); the last pass only evaluates the residuals
-            for (int step = 0; step <= 3; ++step) {
+            // Proximal steps move (up, lam) until the stationarity residual is as small as the
+            // parity bar needs -- |r1| <= stat_eps lambda_min(P) |u| bounds the distance to the
+            // exact point of this active set by stat_eps |u| -- or as small as rounding lets it
+            // be, and the active rows hold; every pass starts by evaluating the residuals, the
+            // last pass only evaluates them.
+            T g_rd = T(0), g_ds = T(0), rd_tol = T(0), neg_tol = T(0);
+            for (int step = 0;; ++step) {
                 xs[l] = up;
 #pragma unroll
                 for (int s = 0; s < MR; ++s)
@@ -446,10 +458,26 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
                 gtl = pdip_gt_dot<T, LDG>(Gc, tv, m, l);
                 rd = pxp + qj + gtl;  // r1
                 pdip_g_dot<T, NP, MR, LDG>(Gc, xs, rowvalid, l, gx);
+                T act_res = T(-1);
 #pragma unroll
-                for (int s = 0; s < MR; ++s) gx[s] = rowvalid[s] ? gx[s] - hrow[s] : T(0);  // G up - h
+                for (int s = 0; s < MR; ++s) {
+                    gx[s] = rowvalid[s] ? gx[s] - hrow[s] : T(0);  // G up - h
+                    if (act[s]) {
+                        const T hs_ = fmax(T(1), abs_(hrow[s]));
+                        act_res = fmax(act_res, abs_(gx[s]) - eps * (strict ? hs_ : fmax(hs_, abs_(gx[s] + hrow[s]))));
+                    }
+                }
                 __syncwarp();
-                if (step == 3) break;
+                g_rd = pdip_max<T, NP>(abs_(rd));
+                g_ds = pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl)));
+                const T uscale = fmax(T(1), pdip_max<T, NP>(abs_(up)));
+                const T g_ar = pdip_max<T, NP>(act_res);
+                rd_tol = fmax(PdipNum<T>::stat_eps * pmin * uscale,
+                              T(64) * PdipNum<T>::macheps * (strict ? qscale : fmax(qscale, g_ds)));
+                // a multiplier of -e on a row moves u by up to e |g| / lambda_min(P): held to the same bar
+                neg_tol = PdipNum<T>::stat_eps * pmin * uscale;
+                const bool tight = g_rd <= rd_tol && g_ar <= T(0);
+                if (step == PdipNum<T>::polish_steps || __all_sync(FULL_MASK, tight || !need)) break;
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
                     r2[s] = act[s] ? gx[s] : T(0);
@@ -489,12 +517,10 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
             // warp would leave the chain at different links and the device deadlocks)
             const T zscale = fmax(T(1), pdip_max<T, NP>(zmax));
             const T g_viol = pdip_max<T, NP>(viol_ex), g_act = pdip_max<T, NP>(act_ex);
-            const T g_neg = pdip_max<T, NP>(worst_neg), g_rd = pdip_max<T, NP>(abs_(rd));
-            const T g_ds = pdip_max<T, NP>(fmax(abs_(pxp), abs_(gtl)));
+            const T g_neg = pdip_max<T, NP>(worst_neg);
             const T g_bad = pdip_max<T, NP>((finite && abs_(rd) < Num<T>::inf()) ? T(0) : T(1));
-            const T dscale = strict ? qscale : fmax(qscale, g_ds);
             const bool ok = spd && g_bad == T(0) && g_viol <= T(0) && g_act <= T(0) &&
-                            g_neg <= eps * zscale && g_rd <= eps * dscale;
+                            g_neg <= fmax(neg_tol, T(64) * PdipNum<T>::macheps * zscale) && g_rd <= rd_tol;
             if (need && ok) {
                 accepted = true;
                 st = 0;
@@ -502,8 +528,38 @@ __device__ __forceinline__ void pdip_core(const T *Pc, T qj, const T *Gc, const 
 #pragma unroll
                 for (int s = 0; s < MR; ++s) z[s] = lam[s];
             }
+            // correct the guess by ONE row: the most violated row enters; if nothing is violated the
+            // most negative multiplier leaves (changing many rows at once can cycle)
+            T vbest = -Num<T>::inf(), lbest = Num<T>::inf();
+            int vslot = 0, lslot = 0;
 #pragma unroll
-            for (int s = 0; s < MR; ++s) act[s] = rowvalid[s] && (act[s] ? lam[s] > T(0) : gx[s] > T(0));
+            for (int s = 0; s < MR; ++s) {
+                if (rowvalid[s]) {
+                    const T hs_ = fmax(T(1), abs_(hrow[s]));
+                    const T ps = strict ? hs_ : fmax(hs_, abs_(gx[s] + hrow[s]));
+                    const T v = gx[s] / ps;
+                    if (!act[s] && v > vbest) {
+                        vbest = v;
+                        vslot = s;
+                    }
+                    if (act[s] && lam[s] < lbest) {
+                        lbest = lam[s];
+                        lslot = s;
+                    }
+                }
+            }
+            const T gv = pdip_max<T, NP>(vbest), gl = pdip_min<T, NP>(lbest);
+            const unsigned lane_ = threadIdx.x & 31u;
+            const unsigned segm = (NP == 32) ? FULL_MASK : (((1u << (NP & 31)) - 1u) << ((lane_ / NP) * NP));
+            const unsigned bv = __ballot_sync(FULL_MASK, vbest == gv) & segm;
+            const unsigned bl = __ballot_sync(FULL_MASK, lbest == gl) & segm;
+            const bool enter = gv > eps && lane_ == (unsigned)(__ffs(bv) - 1);
+            const bool leave = !(gv > eps) && gl < T(0) && lane_ == (unsigned)(__ffs(bl) - 1);
+#pragma unroll
+            for (int s = 0; s < MR; ++s) {
+                if (enter && s == vslot) act[s] = true;
+                if (leave && s == lslot) act[s] = false;
+            }
         }
         __syncwarp();
     }
@@ -569,8 +625,8 @@ __global__ void __launch_bounds__(256, 1) mpc_pdip_kernel(const SolveParams p, i
 
     T x, z[MR];
     int st, it;
-    pdip_core<T, NP, MR, LS>(Pc, qj, Gc, hs, Lc, xs, dv, wv, tv, m, l, valid, p.max_iter, (T)p.tol, polish != 0, x, z,
-                             st, it);
+    pdip_core<T, NP, MR, LS>(Pc, qj, Gc, hs, Lc, xs, dv, wv, tv, m, l, valid, p.max_iter, (T)p.tol, polish != 0,
+                             (T)p.w_u, x, z, st, it);
 
     // phase D: outputs
     {

@@ -64,10 +64,19 @@ int launch_condense_cta(const SolveParams &p, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
-bool use_cta(int n, int m, Variant *v) { return env_int("QPMPC_B200_FORCE_CTA", 0) != 0 || !pick_variant(n, m, v); }
+// desc.paired is honoured when the rows really split into two halves per step (nc even)
+bool rows_paired(const qpmpc_b200_desc *d) {
+    return d->paired != 0 && d->nc > 0 && (d->nc & 1) == 0 && env_int("QPMPC_B200_NO_PAIRED", 0) == 0;
+}
+bool use_cta(int n, int m, Variant *v, bool paired = false) {
+    return env_int("QPMPC_B200_FORCE_CTA", 0) != 0 || !pick_variant(n, m, v, paired);
+}
 
 template <typename T>
 int dispatch_solve(const SolveParams &p, const Variant &v, cudaStream_t s) {
+    if (v.paired && v.np == 8) return launch_solve_paired<T, 8>(p, s);
+    if (v.paired && v.np == 16) return launch_solve_paired<T, 16>(p, s);
+    if (v.paired && v.np == 32) return launch_solve_paired<T, 32>(p, s);
     if (v.np == 8 && v.mr == 2) return launch_solve<T, 8, 2, true>(p, s);
     if (v.np == 8 && v.mr == 4) return launch_solve<T, 8, 4, true>(p, s);
     if (v.np == 16 && v.mr == 2) return launch_solve<T, 16, 2, true>(p, s);
@@ -246,7 +255,7 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
         const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
         return dispatch_pdip(p, v, polish, s);
     }
-    if (use_cta(p.n, p.m, &v))
+    if (use_cta(p.n, p.m, &v, rows_paired(d)))
         return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);
 }

@@ -193,6 +193,20 @@ def oracle_ops(w: Dict) -> Dict:
     return ops
 
 
+def rows_are_paired(w: Dict) -> bool:
+    """True when every C_k, D_k of the workload has the form [M; -M] (two-sided bounds): what
+    ``qpmpc_b200_desc.paired`` promises to the kernels."""
+    nc = w["nc"]
+    if nc == 0 or nc % 2:
+        return False
+    h = nc // 2
+    for name in ("C", "D"):
+        arr = w[name]
+        if arr is not None and not np.array_equal(arr[..., :h, :], -arr[..., h:, :]):
+            return False
+    return w["C"] is not None or w["D"] is not None
+
+
 def slice_workload(w: Dict, lo: int, hi: int) -> Dict:
     """Instances [lo, hi) of a workload (per-instance operands sliced)."""
     out = dict(w)

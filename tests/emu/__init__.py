@@ -74,7 +74,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
 
-def describe(w, method=0, max_iter=0, tol=0.0, flags=0, dtype=np.float64):
+def describe(w, method=0, max_iter=0, tol=0.0, flags=0, dtype=np.float64, paired=None):
     """(desc, operands, keep-alive arrays) of a workload dict, host pointers:
     the structs of include/qpmpc_b200.h filled the way BatchedMPCProblem fills them."""
     from qpmpc_b200 import _capi
@@ -98,18 +98,24 @@ def describe(w, method=0, max_iter=0, tol=0.0, flags=0, dtype=np.float64):
     d.has_wt, d.has_wx = w["w_t"] is not None, w["w_x"] is not None
     d.w_t, d.w_x, d.w_u = float(w["w_t"] or 0.0), float(w["w_x"] or 0.0), w["w_u"]
     d.method, d.max_iter, d.tol, d.flags = method, max_iter, tol, flags
+    if paired is None:
+        from qpmpc_b200.workloads import rows_are_paired
+
+        paired = rows_are_paired(w)
+    d.paired = int(bool(paired))
     ops = _capi.Operands(*[_ptr(keep.get(k)) for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets")])
     return d, ops, keep
 
 
-def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, descending=False, dtype=np.float64):
+def solve(w, method="active_set", wpc=0, max_iter=0, tol=0.0, polish=True, descending=False, dtype=np.float64,
+          paired=None):
     """qpmpc_b200_solve on the emulator: mpc_solve_kernel / mpc_solve_cta_kernel /
     mpc_pdip_kernel, in ``dtype`` (float64 or float32; U and z come back as float64)."""
     from qpmpc_b200 import _capi
 
     lib = load()
     meth = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}[method]
-    d, ops, keep = describe(w, meth, max_iter, tol, 0 if polish else _capi.FLAG_NO_POLISH, dtype)
+    d, ops, keep = describe(w, meth, max_iter, tol, 0 if polish else _capi.FLAG_NO_POLISH, dtype, paired)
     B, n, m = w["batch"], w["N"] * w["nu"], w["N"] * w["nc"]
     U, Z = np.zeros((B, n), dtype=dtype), np.zeros((B, max(m, 1)), dtype=dtype)
     st, it = np.full(B, -1, np.int32), np.zeros(B, np.int32)
@@ -144,10 +150,11 @@ def pdip_core(P, q, G, h, np_, mr, dtype=0, max_iter=50, tol=1e-9, polish=True):
     B, m, n = G.shape
     U, Z = np.zeros((B, n)), np.zeros((B, max(m, 1)))
     st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    pmin = float(np.linalg.eigvalsh(P).min())  # the kernel gets w_u <= lambda_min(P) from the MPC problem
     with _Checked() as lib:
         rc = lib.pdip_emu_solve(dtype, np_, mr, B, n, m, P.ctypes.data_as(_dp), q.ctypes.data_as(_dp),
                                 G.ctypes.data_as(_dp), h.ctypes.data_as(_dp), max_iter, ctypes.c_double(tol),
-                                int(polish), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
+                                int(polish), ctypes.c_double(pmin), U.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
                                 st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
     assert rc == 0, rc
     return dict(U=U, z=Z[:, :m], status=st, iters=it)

@@ -52,9 +52,9 @@ void launch(int grid, int threads, size_t smem, K kernel) {
     }
 }
 
-template <typename T, int NP, int MR, bool MREG, bool RS>
+template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false>
 int solve_variant(SolveParams p, int wpc) {
-    using L = Lay<T, NP, MR, MREG, RS>;
+    using L = Lay<T, NP, MR, MREG, RS, PAIRED>;
     constexpr int IPW = 32 / NP;
     size_t smem = 0;
     for (;; --wpc) {
@@ -63,7 +63,7 @@ int solve_variant(SolveParams p, int wpc) {
     }
     if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
     const int ipc = IPW * wpc;
-    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_solve_kernel<T, NP, MR, MREG, RS>(p); });
+    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_solve_kernel<T, NP, MR, MREG, RS, PAIRED>(p); });
     return 0;
 }
 
@@ -140,7 +140,7 @@ int condense_cta(const SolveParams &p) {
 // never produces (infeasible rows, m = 0) and the float instantiation.
 template <typename T, int NP, int MR, bool LS>
 int pdip_core_run(int count, int n, int m, const double *P, const double *q, const double *G, const double *h,
-                  int max_iter, double tol, int polish, double *U, double *Z, int *status, int *iters) {
+                  int max_iter, double tol, int polish, double pmin, double *U, double *Z, int *status, int *iters) {
     using L = PdipLay<T, NP, MR>;
     constexpr int IPW = 32 / NP;
     if (count < 1 || count > IPW || n > NP || m > L::MP) return -1;
@@ -168,7 +168,7 @@ int pdip_core_run(int count, int n, int m, const double *P, const double *q, con
         T x, z[MR];
         int st, it;
         pdip_core<T, NP, MR, LS>(wk + L::oP, qj, wk + L::fixed, wk + L::oH, wk + L::oL, xs, dv, wv, tv, m, l, valid,
-                                 max_iter, (T)tol, polish != 0, x, z, st, it);
+                                 max_iter, (T)tol, polish != 0, (T)pmin, x, z, st, it);
         if (!valid) return;
         if (l < n) U[(size_t)sub * n + l] = (double)x;
         for (int s = 0; s < MR; ++s)
@@ -185,11 +185,19 @@ int pdip_core_run(int count, int n, int m, const double *P, const double *q, con
 template <typename T>
 int emu_solve_t(const qpmpc_b200_desc *d, SolveParams &p, int wpc) {
     Variant v;
-    const bool warp_ok = pick_variant(p.n, p.m, &v);
+    // as solve_impl / rows_paired (qpmpc_b200.cu)
+    const bool paired = d->paired != 0 && d->nc > 0 && (d->nc & 1) == 0 && env_int("QPMPC_B200_NO_PAIRED", 0) == 0;
+    const bool warp_ok = pick_variant(p.n, p.m, &v, paired);
     if (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0) {
         int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
         threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
         return solve_cta<T>(p, threads);
+    }
+    if (v.paired) {
+        if (wpc <= 0) wpc = v.np == 32 ? 4 : 8;
+        if (v.np == 8) return solve_variant<T, 8, 1, true, false, true>(p, wpc);
+        if (v.np == 16) return solve_variant<T, 16, 1, true, false, true>(p, wpc);
+        return solve_variant<T, 32, 1, true, false, true>(p, wpc);
     }
     if (wpc <= 0) wpc = 8;
     switch (v.np * 10 + v.mr) {
@@ -208,17 +216,17 @@ int emu_solve_t(const qpmpc_b200_desc *d, SolveParams &p, int wpc) {
 extern "C" {
 
 int pdip_emu_solve(int dtype, int np, int mr, int count, int n, int m, const double *P, const double *q,
-                   const double *G, const double *h, int max_iter, double tol, int polish, double *U, double *Z,
-                   int *status, int *iters) {
+                   const double *G, const double *h, int max_iter, double tol, int polish, double pmin, double *U,
+                   double *Z, int *status, int *iters) {
     // as launch_pdip; the float instantiation (not offered through the ABI) only works with the
     // substitutions: an explicit L^-1 of the late, ill-conditioned H is beyond single precision
     const bool ls = dtype == 0 && env_int("QPMPC_B200_PDIP_SOLVE", 0) != 0;
 #define CASE(T, NP, MR)                                                                                             \
     if (np == NP && mr == MR)                                                                                       \
-        return ls ? pdip_core_run<T, NP, MR, true>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status,    \
-                                                   iters)                                                           \
-                  : pdip_core_run<T, NP, MR, false>(count, n, m, P, q, G, h, max_iter, tol, polish, U, Z, status,   \
-                                                    iters);
+        return ls ? pdip_core_run<T, NP, MR, true>(count, n, m, P, q, G, h, max_iter, tol, polish, pmin, U, Z,     \
+                                                   status, iters)                                                   \
+                  : pdip_core_run<T, NP, MR, false>(count, n, m, P, q, G, h, max_iter, tol, polish, pmin, U, Z,    \
+                                                    status, iters);
     if (dtype == 0) {
         CASE(double, 8, 2)
         CASE(double, 8, 4)

@@ -361,3 +361,43 @@ def test_kernels_reproduce_published_optima(make, method):
     assert np.abs(got["U"][0] - qp["x"]).max() <= max(qp["x_tol"], 1e-7) * max(1.0, np.abs(qp["x"]).max())
     if qp["z"] is not None:
         assert np.abs(got["z"][0] - qp["z"]).max() <= 1e-6
+
+
+# -- paired rows (desc.paired): one stored row stands for [G+; -G+] ---------------------------
+
+@pytest.mark.parametrize("kind", ["ti8", "ti16", "ti32", "pendulum", "pendulum_ltv", "humanoid", "infeasible_pair"])
+def test_paired_row_kernels_match_the_oracle_and_the_unpaired_kernels(kind):
+    """Every BASELINE workload has two-sided bounds (rows [M; -M]): the paired variants keep
+    one row per pair.  Same answers as the oracle and as the unpaired variants, same
+    iteration counts (it is the same active-set iteration); a pair with h+ + h- < 0 is
+    infeasible."""
+    from qpmpc_b200.workloads import rows_are_paired
+
+    w = {"ti8": lambda: triple_integrator_batch(9, N=8, seed=11), "ti16": lambda: triple_integrator_batch(37, seed=12),
+         "ti32": lambda: triple_integrator_batch(5, N=32, seed=13), "pendulum": lambda: pendulum_batch(21, seed=14),
+         "pendulum_ltv": lambda: pendulum_batch(7, seed=15, ltv_model=True), "humanoid": lambda: humanoid_batch(11, seed=16),
+         "infeasible_pair": lambda: humanoid_batch(6, seed=17)}[kind]()
+    if kind == "infeasible_pair":
+        w["e"][1, 5, :] = [0.05, -0.06]   # x <= 0.05 and -x <= -0.06: no such x
+        w["e"][4, 9, :] = [-0.3, 0.2]
+    assert rows_are_paired(w)
+    paired = _check(w, paired=True)
+    plain = _check(w, paired=False)
+    ok = plain["status"] == 0
+    assert np.array_equal(paired["status"], plain["status"])
+    assert np.array_equal(paired["iters"][ok], plain["iters"][ok])  # (an infeasible pair is seen before iterating)
+    assert np.abs(paired["U"][ok] - plain["U"][ok]).max() <= 1e-9
+    assert np.abs(paired["z"][ok] - plain["z"][ok]).max() <= 1e-9 * max(1.0, np.abs(plain["z"][ok]).max())
+    if kind == "infeasible_pair":
+        assert paired["status"][1] == 2 and paired["status"][4] == 2 and ok.sum() == 4
+
+
+def test_unpaired_rows_are_not_taken_for_pairs():
+    from qpmpc_b200.workloads import rows_are_paired
+
+    w = triple_integrator_batch(3, seed=1)
+    w["C"] = w["C"].copy()
+    w["C"][1, 1, 2] = -0.5  # instance 1: second row is no longer minus the first
+    assert not rows_are_paired(w)
+    assert not rows_are_paired(random_batch(2, 4, 3, 1, 2))
+    _check(w)
