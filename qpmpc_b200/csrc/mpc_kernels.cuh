@@ -40,6 +40,10 @@
 #ifndef QPMPC_MINB_F32
 #define QPMPC_MINB_F32 3
 #endif
+// paired-row variants (one stored row per lane): resident CTAs of 8 warps per SM, double precision
+#ifndef QPMPC_MINB_PAIRED
+#define QPMPC_MINB_PAIRED 2
+#endif
 #ifndef QPMPC_SYNC_TAIL
 #define QPMPC_SYNC_TAIL 1
 #endif
@@ -226,46 +230,82 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
     const bool stageP = p.has_wx != 0, stageq = p.q_wx != 0;
     const bool fast = !DUMP && toep && nc == 2 && (!stageP || nu == 1);
     if (fast) {
-        T Bl[NX], Cr[2 * NX];
+        // No N-step loop: psi_N[:, l] = A^(N-1-kb) B[:, jb] and the free response of step k,
+        // y_k = A^k x0, are powers of one matrix, so lane l builds "its" two vectors from the
+        // binary digits of its exponents while A is squared log2(N) times (the same squarings
+        // for every lane).  Lane k < N then owns the h rows of step k; x_N = A y_(N-1).
+        T Cr[2 * NX], Ap[NX * NX], y[NX];
+        const int ev = (l < n) ? N - 1 - kb : 0;
 #pragma unroll
         for (int t = 0; t < NX; ++t) {
-            Bl[t] = Bk[t * nu + jb];
+            psi[t] = (l < n) ? Bk[t * nu + jb] : T(0);
+            y[t] = xb[t];
             Cr[t] = hasC ? Ck[t] : T(0);
             Cr[NX + t] = hasC ? Ck[NX + t] : T(0);
         }
-#pragma unroll 2
-        for (int k = 0; k < N; ++k) {
-            T h0 = ek[0], h1 = ek[1];
-            T pn[NX], xn[NX];
+#pragma unroll
+        for (int t = 0; t < NX * NX; ++t) Ap[t] = Ar[t];
+#pragma unroll 1
+        for (int bit = 1; bit < N; bit <<= 1) {
+            const bool sv = (ev & bit) != 0, sy = (l & bit) != 0;
+            T nv[NX], ny[NX];
 #pragma unroll
             for (int t = 0; t < NX; ++t) {
-                h0 -= Cr[t] * xb[t];
-                h1 -= Cr[NX + t] * xb[t];
                 T a = T(0), b = T(0);
 #pragma unroll
                 for (int s = 0; s < NX; ++s) {
-                    a += Ar[t * NX + s] * psi[s];
-                    b += Ar[t * NX + s] * xb[s];
+                    a += Ap[t * NX + s] * psi[s];
+                    b += Ap[t * NX + s] * y[s];
                 }
-                pn[t] = (k == kb) ? Bl[t] : a;
-                xn[t] = b;
-            }
-            if (l == 0) {
-                hs[2 * k] = h0;
-                hs[2 * k + 1] = h1;
-            }
-            if (stageq) {
-                // q += w_x psi_k'(phi_k x0 - target_k), column l of psi_k is in registers
-                const T *tg = in[OP_TGT] + k * NX;
-#pragma unroll
-                for (int t = 0; t < NX; ++t) qj += (w_x * psi[t]) * (xb[t] - tg[t]);
+                nv[t] = a;
+                ny[t] = b;
             }
 #pragma unroll
             for (int t = 0; t < NX; ++t) {
-                psi[t] = pn[t];
-                xb[t] = xn[t];
+                psi[t] = sv ? nv[t] : psi[t];
+                y[t] = sy ? ny[t] : y[t];
             }
-            ek += stepE;
+            if ((bit << 1) < N) {
+                T sq[NX * NX];
+#pragma unroll
+                for (int t = 0; t < NX * NX; ++t) {
+                    T a = T(0);
+#pragma unroll
+                    for (int s = 0; s < NX; ++s) a += Ap[(t / NX) * NX + s] * Ap[s * NX + t % NX];
+                    sq[t] = a;
+                }
+#pragma unroll
+                for (int t = 0; t < NX * NX; ++t) Ap[t] = sq[t];
+            }
+        }
+        if (l < N) {
+            const T *ekk = ek + l * stepE;
+            T h0 = ekk[0], h1 = ekk[1];
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {
+                h0 -= Cr[t] * y[t];
+                h1 -= Cr[NX + t] * y[t];
+            }
+            hs[2 * l] = h0;
+            hs[2 * l + 1] = h1;
+        }
+        {
+            T yl[NX];
+#pragma unroll
+            for (int t = 0; t < NX; ++t) yl[t] = __shfl_sync(FULL_MASK, y[t], N - 1, NP);
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {
+                T b = T(0);
+#pragma unroll
+                for (int s = 0; s < NX; ++s) b += Ar[t * NX + s] * yl[s];
+                xb[t] = b;
+            }
+        }
+        if (stageq && l < N) {
+            // y_k - target_k for the stage cost's share of q (below, once the table of psi is shared)
+            const T *tg = in[OP_TGT] + l * NX;
+#pragma unroll
+            for (int t = 0; t < NX; ++t) xch[l * NX + t] = y[t] - tg[t];
         }
         if (stageP) {
             // P += w_x sum_k psi_k' psi_k with psi_k[:, c] = v_(k-1-c), v_e = A^e B = psi_N[:, n-1-e]:
@@ -277,6 +317,15 @@ __device__ __forceinline__ void condense_reg(const SolveParams &p, const T *cons
                 for (int t = 0; t < NX; ++t) W[t * NP + (n - 1 - l)] = psi[t];
             }
             __syncwarp();
+            if (stageq) {
+                // q_l += w_x sum_{k > l} psi_k[:, l]'(y_k - target_k),  psi_k[:, l] = v_(k-1-l)   (nu = 1)
+                T acc = T(0);
+                for (int k = l + 1; k < N; ++k) {
+#pragma unroll
+                    for (int t = 0; t < NX; ++t) acc += W[t * NP + k - 1 - l] * xch[k * NX + t];
+                }
+                qj += w_x * acc;
+            }
             if (l < N) {
                 T acc = T(0);
                 for (int u = 0; u + l < N; ++u) {
@@ -609,7 +658,9 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false>  // @phase kernel prologue
-__global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : QPMPC_MINB / 2) : 1)
+__global__ void __launch_bounds__(256, (NP <= 16 && MREG)
+                                           ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : (PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
+                                           : 1)
     mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, MREG, RS, PAIRED>;
     using T2 = typename Pair<T>::type;
@@ -1008,7 +1059,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
             done = true;
             act = false;
         }
-        const T t = fmin(t1, t2);
+        const T t = t2 < t1 ? t2 : t1;  // (neither is NaN here: plain select, not fmin)
         {
             // unconditional updates with a zero step where nothing moves (all
             // operands are finite on finished instances, so 0 * v adds nothing)
@@ -1073,8 +1124,8 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
                 if (l == na) {
                     Ri[na * NP + na] = binv;
                     lam = lamp;
-                    // aidx is the row's index in G / h (what Z and the recovery of x use)
-                    aidx = PAIRED ? (pidx / half) * p.nc + pidx % half + (pneg ? half : 0) : pidx;
+                    // paired: stored row | sign bit; turned into the row's index in G / h after the loop
+                    aidx = PAIRED ? (pidx | (pneg ? 0x8000 : 0)) : pidx;
                 }
                 if (l == owner) actbits |= 1u << pslot;
                 ++na;
@@ -1084,12 +1135,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
         if (__any_sync(FULL_MASK, part)) {  // @phase C drop constraint (Givens)
             // Constraint at active position lidx leaves; p stays the candidate.
             int cidx = __shfl_sync(FULL_MASK, aidx, lidx, NP);
-            if (PAIRED) {
-                // row index in G -> stored row
-                const int nc_ = p.nc > 0 ? p.nc : 2;
-                const int ck = (cidx >= 0 ? cidx : 0) / nc_, cr = (cidx >= 0 ? cidx : 0) - ck * nc_;
-                cidx = ck * half + (cr >= half ? cr - half : cr);
-            }
+            if (PAIRED) cidx &= 0x7fff;  // stored row
             if (part && l == cidx % NP) actbits &= ~(1u << (cidx / NP));
             const T lam_n = __shfl_down_sync(FULL_MASK, lam, 1, NP);
             const int aidx_n = __shfl_down_sync(FULL_MASK, aidx, 1, NP);
@@ -1158,6 +1204,11 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG) ? (sizeof(T) == 4 ? QP
         __syncwarp();
     }
 
+    if (PAIRED && aidx >= 0) {
+        // stored row | sign -> index of the row in G / h
+        const int sr = aidx & 0x7fff, sk = sr / half;
+        aidx = sk * p.nc + (sr - sk * half) + ((aidx & 0x8000) ? half : 0);
+    }
     // The warps of the CTA leave the iteration at different times but hold the
     // CTA's resources until the last one is done: let them run the (unrolled,
     // one-shot) recovery code together so that they share instruction fetches.
