@@ -19,6 +19,8 @@ template <typename T, int NP>  // paired rows (desc.paired): one stored row per 
 int launch_solve_paired(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
 int launch_condense(SolveParams p, cudaStream_t stream);
+template <typename T, int NP>  // structure-exploiting kernel for terminal-cost problems (mpc_lr_kernel.cuh)
+int launch_solve_lr(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
 int launch_pdip(SolveParams p, int polish, cudaStream_t stream);  // mpc_pdip.cuh
 

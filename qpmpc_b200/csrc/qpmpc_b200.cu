@@ -14,6 +14,7 @@
 #include "mpc_host_params.h"
 #include "mpc_integrate.cuh"
 #include "mpc_launch.cuh"
+#include "mpc_lr_kernel.cuh"
 #include "mpc_plant.cuh"
 
 using namespace qpmpc;
@@ -255,6 +256,12 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
         const int polish = (d->flags & QPMPC_B200_FLAG_NO_POLISH) ? 0 : 1;
         return dispatch_pdip(p, v, polish, s);
     }
+    // Terminal-cost problems with a long horizon: the structure-exploiting kernel (rank-nx Hessian,
+    // Toeplitz G, one CTA of n threads per instance); QPMPC_B200_LR=0 switches it off.
+    const int lr = env_int("QPMPC_B200_LR", -1);
+    if (d->dtype == QPMPC_B200_F64 && lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 &&
+        lr_applicable(p, rows_paired(d)) && p.n > 16)
+        return p.n <= 32 ? launch_solve_lr<double, 32>(p, s) : launch_solve_lr<double, 64>(p, s);
     if (use_cta(p.n, p.m, &v, rows_paired(d)))
         return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);

@@ -42,7 +42,7 @@ def load():
     deps = [os.path.join(HERE, "kernel_emu.cpp"), os.path.join(HERE, "warp_emu.h"),
             os.path.join(ROOT, "include", "qpmpc_b200.h")]
     deps += [os.path.join(csrc, f) for f in ("mpc_common.cuh", "mpc_kernels.cuh", "mpc_pdip.cuh",
-                                             "mpc_cta_kernel.cuh", "mpc_integrate.cuh", "mpc_plant.cuh",
+                                             "mpc_cta_kernel.cuh", "mpc_lr_kernel.cuh", "mpc_integrate.cuh", "mpc_plant.cuh",
                                              "mpc_host_params.h")]
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DQPMPC_HOST_EMU",

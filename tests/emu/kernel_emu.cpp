@@ -18,6 +18,7 @@
 #include "qpmpc_b200/csrc/mpc_host_params.h"
 #include "qpmpc_b200/csrc/mpc_pdip.cuh"  // brings mpc_common.cuh and mpc_kernels.cuh
 #include "qpmpc_b200/csrc/mpc_cta_kernel.cuh"
+#include "qpmpc_b200/csrc/mpc_lr_kernel.cuh"
 #include "qpmpc_b200/csrc/mpc_integrate.cuh"
 #include "qpmpc_b200/csrc/mpc_plant.cuh"
 
@@ -181,12 +182,30 @@ int pdip_core_run(int count, int n, int m, const double *P, const double *q, con
     return 0;
 }
 
+// launch_solve_lr (inst_lr.cu): one CTA of NP threads per instance
+template <typename T, int NP>
+int solve_lr(SolveParams p) {
+    const size_t smem = lr_layout_smem<T, NP>(&p);
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    switch (p.nx) {
+        case 2: launch(p.batch, NP, smem, [&]() { mpc_solve_lr_kernel<T, NP, 2>(p); }); return 0;
+        case 3: launch(p.batch, NP, smem, [&]() { mpc_solve_lr_kernel<T, NP, 3>(p); }); return 0;
+        case 4: launch(p.batch, NP, smem, [&]() { mpc_solve_lr_kernel<T, NP, 4>(p); }); return 0;
+    }
+    return QPMPC_B200_ESHAPE;
+}
+
 // the active-set kernels of one dtype: warp kernel variants, or the CTA kernel
 template <typename T>
 int emu_solve_t(const qpmpc_b200_desc *d, SolveParams &p, int wpc) {
     Variant v;
     // as solve_impl / rows_paired (qpmpc_b200.cu)
     const bool paired = d->paired != 0 && d->nc > 0 && (d->nc & 1) == 0 && env_int("QPMPC_B200_NO_PAIRED", 0) == 0;
+    if constexpr (sizeof(T) == 8) {
+        const int lr = env_int("QPMPC_B200_LR", -1);
+        if (lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 && lr_applicable(p, paired) && p.n > 16)
+            return p.n <= 32 ? solve_lr<T, 32>(p) : solve_lr<T, 64>(p);
+    }
     const bool warp_ok = pick_variant(p.n, p.m, &v, paired);
     if (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0) {
         int threads = env_int("QPMPC_B200_CTA_THREADS", 256);

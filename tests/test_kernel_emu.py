@@ -401,3 +401,47 @@ def test_unpaired_rows_are_not_taken_for_pairs():
     assert not rows_are_paired(w)
     assert not rows_are_paired(random_batch(2, 4, 3, 1, 2))
     _check(w)
+
+
+# -- structure-exploiting long-horizon kernel (mpc_lr_kernel.cuh) -----------------------------
+
+@pytest.mark.parametrize("kind", ["ti64", "ti48", "ti33", "humanoid40", "ti24_forced", "ti32_forced", "infeasible"])
+def test_low_rank_hessian_kernel(kind, monkeypatch):
+    """Terminal-cost problems with n > 32 (and, with QPMPC_B200_LR=1, n > 16) run on the kernel
+    that never factors the n x n Hessian: P = w_u I + w_t psi' psi, J from 3 x 3 algebra, rows of
+    M in O(n nx).  Same exact answers and iteration counts as the oracle; multipliers too."""
+    if kind.endswith("forced"):
+        monkeypatch.setenv("QPMPC_B200_LR", "1")
+    w = {"ti64": lambda: triple_integrator_batch(5, N=64, seed=21), "ti48": lambda: triple_integrator_batch(3, N=48, seed=22),
+         "ti33": lambda: triple_integrator_batch(3, N=33, seed=23), "humanoid40": lambda: humanoid_batch(4, N=40, seed=24),
+         "ti24_forced": lambda: triple_integrator_batch(4, N=24, seed=25),
+         "ti32_forced": lambda: triple_integrator_batch(4, N=32, seed=26),
+         "infeasible": lambda: humanoid_batch(3, N=36, seed=27)}[kind]()
+    if kind == "infeasible":
+        w["e"][1, 0, :] = [-0.5, -0.5]      # the k = 0 rows cannot be repaired (no D)
+        w["e"][2, 20, :] = [0.05, -0.06]    # a pair that admits no point
+    got = _check(w)
+    ref = _oracle(w)
+    ok = ref["status"] == 0
+    assert np.array_equal(got["iters"][ok], ref["iters"][ok])
+    if kind == "infeasible":
+        assert list(got["status"]) == [0, 2, 2]
+    # multipliers: stationarity of the returned pair (U, z) on the oracle's condensed QP
+    b = int(np.flatnonzero(ok)[0])
+    pick = lambda a, flag: None if a is None else (a[b] if flag else a)
+    ops = oracle_ops(w)
+    c = oracle.condense(w["N"], w["nx"], w["nu"], w["nc"], *[pick(*ops[k][:2]) for k in ("A", "B", "C", "D", "e")],
+                        w["x0"][b], w["goal"][b], None, w["w_t"], w["w_x"], w["w_u"])
+    res = oracle.kkt(c["P"], c["q"], c["G"], c["h"], got["U"][b], got["z"][b])
+    assert res[0] <= 1e-9 and res[1] <= 1e-9 and res[2] <= 1e-12 and res[3] <= 1e-9
+
+
+def test_low_rank_kernel_is_only_used_where_it_applies(monkeypatch):
+    """Stage cost, D rows, unpaired rows or time-varying operands keep the dense kernels."""
+    monkeypatch.setenv("QPMPC_B200_LR", "1")
+    w = triple_integrator_batch(2, N=24, seed=3)
+    w["w_x"] = 0.5
+    w["targets"] = np.zeros((2, 24 * 3))
+    _check(w)                                   # stage cost: P is not low rank
+    _check(pendulum_batch(3, N=20, seed=4))     # D rows and a stage cost
+    _check(triple_integrator_batch(2, N=24, seed=5), paired=False)
