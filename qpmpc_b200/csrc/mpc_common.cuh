@@ -136,6 +136,150 @@ template <> struct Num<float> {
     static constexpr float dep_eps = 1e-10f;
 };
 
+// Element i of an array the compiler keeps in registers, for an index that is only known at run
+// time but is UNIFORM over the warp (a position in the working set): a switch over static
+// indices (a jump table, one taken branch) instead of spilling the array to local memory.
+template <typename T, int NP>
+__device__ __forceinline__ T reg_get(const T (&a)[NP], int i) {
+    static_assert(NP <= 64, "reg_get covers 64 entries");
+    switch (i) {
+        case 0: if (0 < NP) return a[0 < NP ? 0 : 0]; break;
+        case 1: if (1 < NP) return a[1 < NP ? 1 : 0]; break;
+        case 2: if (2 < NP) return a[2 < NP ? 2 : 0]; break;
+        case 3: if (3 < NP) return a[3 < NP ? 3 : 0]; break;
+        case 4: if (4 < NP) return a[4 < NP ? 4 : 0]; break;
+        case 5: if (5 < NP) return a[5 < NP ? 5 : 0]; break;
+        case 6: if (6 < NP) return a[6 < NP ? 6 : 0]; break;
+        case 7: if (7 < NP) return a[7 < NP ? 7 : 0]; break;
+        case 8: if (8 < NP) return a[8 < NP ? 8 : 0]; break;
+        case 9: if (9 < NP) return a[9 < NP ? 9 : 0]; break;
+        case 10: if (10 < NP) return a[10 < NP ? 10 : 0]; break;
+        case 11: if (11 < NP) return a[11 < NP ? 11 : 0]; break;
+        case 12: if (12 < NP) return a[12 < NP ? 12 : 0]; break;
+        case 13: if (13 < NP) return a[13 < NP ? 13 : 0]; break;
+        case 14: if (14 < NP) return a[14 < NP ? 14 : 0]; break;
+        case 15: if (15 < NP) return a[15 < NP ? 15 : 0]; break;
+        case 16: if (16 < NP) return a[16 < NP ? 16 : 0]; break;
+        case 17: if (17 < NP) return a[17 < NP ? 17 : 0]; break;
+        case 18: if (18 < NP) return a[18 < NP ? 18 : 0]; break;
+        case 19: if (19 < NP) return a[19 < NP ? 19 : 0]; break;
+        case 20: if (20 < NP) return a[20 < NP ? 20 : 0]; break;
+        case 21: if (21 < NP) return a[21 < NP ? 21 : 0]; break;
+        case 22: if (22 < NP) return a[22 < NP ? 22 : 0]; break;
+        case 23: if (23 < NP) return a[23 < NP ? 23 : 0]; break;
+        case 24: if (24 < NP) return a[24 < NP ? 24 : 0]; break;
+        case 25: if (25 < NP) return a[25 < NP ? 25 : 0]; break;
+        case 26: if (26 < NP) return a[26 < NP ? 26 : 0]; break;
+        case 27: if (27 < NP) return a[27 < NP ? 27 : 0]; break;
+        case 28: if (28 < NP) return a[28 < NP ? 28 : 0]; break;
+        case 29: if (29 < NP) return a[29 < NP ? 29 : 0]; break;
+        case 30: if (30 < NP) return a[30 < NP ? 30 : 0]; break;
+        case 31: if (31 < NP) return a[31 < NP ? 31 : 0]; break;
+        case 32: if (32 < NP) return a[32 < NP ? 32 : 0]; break;
+        case 33: if (33 < NP) return a[33 < NP ? 33 : 0]; break;
+        case 34: if (34 < NP) return a[34 < NP ? 34 : 0]; break;
+        case 35: if (35 < NP) return a[35 < NP ? 35 : 0]; break;
+        case 36: if (36 < NP) return a[36 < NP ? 36 : 0]; break;
+        case 37: if (37 < NP) return a[37 < NP ? 37 : 0]; break;
+        case 38: if (38 < NP) return a[38 < NP ? 38 : 0]; break;
+        case 39: if (39 < NP) return a[39 < NP ? 39 : 0]; break;
+        case 40: if (40 < NP) return a[40 < NP ? 40 : 0]; break;
+        case 41: if (41 < NP) return a[41 < NP ? 41 : 0]; break;
+        case 42: if (42 < NP) return a[42 < NP ? 42 : 0]; break;
+        case 43: if (43 < NP) return a[43 < NP ? 43 : 0]; break;
+        case 44: if (44 < NP) return a[44 < NP ? 44 : 0]; break;
+        case 45: if (45 < NP) return a[45 < NP ? 45 : 0]; break;
+        case 46: if (46 < NP) return a[46 < NP ? 46 : 0]; break;
+        case 47: if (47 < NP) return a[47 < NP ? 47 : 0]; break;
+        case 48: if (48 < NP) return a[48 < NP ? 48 : 0]; break;
+        case 49: if (49 < NP) return a[49 < NP ? 49 : 0]; break;
+        case 50: if (50 < NP) return a[50 < NP ? 50 : 0]; break;
+        case 51: if (51 < NP) return a[51 < NP ? 51 : 0]; break;
+        case 52: if (52 < NP) return a[52 < NP ? 52 : 0]; break;
+        case 53: if (53 < NP) return a[53 < NP ? 53 : 0]; break;
+        case 54: if (54 < NP) return a[54 < NP ? 54 : 0]; break;
+        case 55: if (55 < NP) return a[55 < NP ? 55 : 0]; break;
+        case 56: if (56 < NP) return a[56 < NP ? 56 : 0]; break;
+        case 57: if (57 < NP) return a[57 < NP ? 57 : 0]; break;
+        case 58: if (58 < NP) return a[58 < NP ? 58 : 0]; break;
+        case 59: if (59 < NP) return a[59 < NP ? 59 : 0]; break;
+        case 60: if (60 < NP) return a[60 < NP ? 60 : 0]; break;
+        case 61: if (61 < NP) return a[61 < NP ? 61 : 0]; break;
+        case 62: if (62 < NP) return a[62 < NP ? 62 : 0]; break;
+        case 63: if (63 < NP) return a[63 < NP ? 63 : 0]; break;
+    }
+    return a[0];
+}
+template <typename T, int NP>
+__device__ __forceinline__ void reg_sub(T (&a)[NP], int i, T v) {
+    switch (i) {
+        case 0: if (0 < NP) a[0 < NP ? 0 : 0] -= v; break;
+        case 1: if (1 < NP) a[1 < NP ? 1 : 0] -= v; break;
+        case 2: if (2 < NP) a[2 < NP ? 2 : 0] -= v; break;
+        case 3: if (3 < NP) a[3 < NP ? 3 : 0] -= v; break;
+        case 4: if (4 < NP) a[4 < NP ? 4 : 0] -= v; break;
+        case 5: if (5 < NP) a[5 < NP ? 5 : 0] -= v; break;
+        case 6: if (6 < NP) a[6 < NP ? 6 : 0] -= v; break;
+        case 7: if (7 < NP) a[7 < NP ? 7 : 0] -= v; break;
+        case 8: if (8 < NP) a[8 < NP ? 8 : 0] -= v; break;
+        case 9: if (9 < NP) a[9 < NP ? 9 : 0] -= v; break;
+        case 10: if (10 < NP) a[10 < NP ? 10 : 0] -= v; break;
+        case 11: if (11 < NP) a[11 < NP ? 11 : 0] -= v; break;
+        case 12: if (12 < NP) a[12 < NP ? 12 : 0] -= v; break;
+        case 13: if (13 < NP) a[13 < NP ? 13 : 0] -= v; break;
+        case 14: if (14 < NP) a[14 < NP ? 14 : 0] -= v; break;
+        case 15: if (15 < NP) a[15 < NP ? 15 : 0] -= v; break;
+        case 16: if (16 < NP) a[16 < NP ? 16 : 0] -= v; break;
+        case 17: if (17 < NP) a[17 < NP ? 17 : 0] -= v; break;
+        case 18: if (18 < NP) a[18 < NP ? 18 : 0] -= v; break;
+        case 19: if (19 < NP) a[19 < NP ? 19 : 0] -= v; break;
+        case 20: if (20 < NP) a[20 < NP ? 20 : 0] -= v; break;
+        case 21: if (21 < NP) a[21 < NP ? 21 : 0] -= v; break;
+        case 22: if (22 < NP) a[22 < NP ? 22 : 0] -= v; break;
+        case 23: if (23 < NP) a[23 < NP ? 23 : 0] -= v; break;
+        case 24: if (24 < NP) a[24 < NP ? 24 : 0] -= v; break;
+        case 25: if (25 < NP) a[25 < NP ? 25 : 0] -= v; break;
+        case 26: if (26 < NP) a[26 < NP ? 26 : 0] -= v; break;
+        case 27: if (27 < NP) a[27 < NP ? 27 : 0] -= v; break;
+        case 28: if (28 < NP) a[28 < NP ? 28 : 0] -= v; break;
+        case 29: if (29 < NP) a[29 < NP ? 29 : 0] -= v; break;
+        case 30: if (30 < NP) a[30 < NP ? 30 : 0] -= v; break;
+        case 31: if (31 < NP) a[31 < NP ? 31 : 0] -= v; break;
+        case 32: if (32 < NP) a[32 < NP ? 32 : 0] -= v; break;
+        case 33: if (33 < NP) a[33 < NP ? 33 : 0] -= v; break;
+        case 34: if (34 < NP) a[34 < NP ? 34 : 0] -= v; break;
+        case 35: if (35 < NP) a[35 < NP ? 35 : 0] -= v; break;
+        case 36: if (36 < NP) a[36 < NP ? 36 : 0] -= v; break;
+        case 37: if (37 < NP) a[37 < NP ? 37 : 0] -= v; break;
+        case 38: if (38 < NP) a[38 < NP ? 38 : 0] -= v; break;
+        case 39: if (39 < NP) a[39 < NP ? 39 : 0] -= v; break;
+        case 40: if (40 < NP) a[40 < NP ? 40 : 0] -= v; break;
+        case 41: if (41 < NP) a[41 < NP ? 41 : 0] -= v; break;
+        case 42: if (42 < NP) a[42 < NP ? 42 : 0] -= v; break;
+        case 43: if (43 < NP) a[43 < NP ? 43 : 0] -= v; break;
+        case 44: if (44 < NP) a[44 < NP ? 44 : 0] -= v; break;
+        case 45: if (45 < NP) a[45 < NP ? 45 : 0] -= v; break;
+        case 46: if (46 < NP) a[46 < NP ? 46 : 0] -= v; break;
+        case 47: if (47 < NP) a[47 < NP ? 47 : 0] -= v; break;
+        case 48: if (48 < NP) a[48 < NP ? 48 : 0] -= v; break;
+        case 49: if (49 < NP) a[49 < NP ? 49 : 0] -= v; break;
+        case 50: if (50 < NP) a[50 < NP ? 50 : 0] -= v; break;
+        case 51: if (51 < NP) a[51 < NP ? 51 : 0] -= v; break;
+        case 52: if (52 < NP) a[52 < NP ? 52 : 0] -= v; break;
+        case 53: if (53 < NP) a[53 < NP ? 53 : 0] -= v; break;
+        case 54: if (54 < NP) a[54 < NP ? 54 : 0] -= v; break;
+        case 55: if (55 < NP) a[55 < NP ? 55 : 0] -= v; break;
+        case 56: if (56 < NP) a[56 < NP ? 56 : 0] -= v; break;
+        case 57: if (57 < NP) a[57 < NP ? 57 : 0] -= v; break;
+        case 58: if (58 < NP) a[58 < NP ? 58 : 0] -= v; break;
+        case 59: if (59 < NP) a[59 < NP ? 59 : 0] -= v; break;
+        case 60: if (60 < NP) a[60 < NP ? 60 : 0] -= v; break;
+        case 61: if (61 < NP) a[61 < NP ? 61 : 0] -= v; break;
+        case 62: if (62 < NP) a[62 < NP ? 62 : 0] -= v; break;
+        case 63: if (63 < NP) a[63 < NP ? 63 : 0] -= v; break;
+    }
+}
+
 #ifdef QPMPC_HOST_EMU
 // ---- host stand-ins: the copy happens at issue time, the barrier is a no-op --
 __device__ __forceinline__ void mbar_init(uint64_t *, unsigned) {}

@@ -1077,34 +1077,25 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
         if (__any_sync(FULL_MASK, full)) {  // @phase C add constraint (Householder)
             // Constraint p enters: reflect d2 = -m2 onto beta e_na.  H = I - tau v v',
             // v = d2 - beta e_na = -(m2 + beta e_na), applied to columns >= na of M (and J).
-            const T mna = d2[na < NP ? na : NP - 1];
+            const int nac = na < NP ? na : NP - 1;
+            const T mna = d2[nac];
             const T alpha = a2 * ainv;
-            const T beta = (mna < T(0)) ? -alpha : alpha;
+            // (instances of the warp that do not add a row ride along with beta = tau = 0: their
+            // a2 may be zero and alpha not finite)
+            const T beta = full ? ((mna < T(0)) ? -alpha : alpha) : T(0);
             const T binv = (mna < T(0)) ? -ainv : ainv;
             const T tau = full ? rcp_(a2 + beta * mna) : T(0);
-            __syncwarp();
-            if (full && l == na) d2[l] = mna + beta;  // d2 becomes -v
-            __syncwarp();
-            T dj = T(0), dj1 = T(0);
+            // -v = d2 + beta e_na: the products M v (and J v) are the products with d2 computed
+            // above plus one entry of the row -- a switch over registers, na being uniform over
+            // the lanes of an instance -- and the update is one pass over d2 plus that entry
+            T dj = T(0);
+            if (HASJ) dj = (z + reg_get<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0) * beta) * tau;
             T dm[MR];
 #pragma unroll
-            for (int s = 0; s < MR; ++s) dm[s] = T(0);
-#pragma unroll
-            for (int c = 0; c < NP; c += 2) {
-                const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-                if (HASJ) {
-                    dj += Jrow[HASJ ? c : 0] * v.x;
-                    dj1 += Jrow[HASJ ? c + 1 : 0] * v.y;
-                }
-#pragma unroll
-                for (int s = 0; s < MR; ++s) {
-                    dm[s] += mget(s, c) * v.x;
-                    dm[s] += mget(s, c + 1) * v.y;
-                }
+            for (int s = 0; s < MR; ++s) {
+                const T mcol = MREG ? reg_get<T, NP>(Mrow[MREG ? s : 0], nac) : Gc[nac * L::LDG + l + s * NP];
+                dm[s] = (gz[s] + mcol * beta) * tau;
             }
-            dj = (dj + dj1) * tau;
-#pragma unroll
-            for (int s = 0; s < MR; ++s) dm[s] *= tau;
 #pragma unroll
             for (int c = 0; c < NP; c += 2) {
                 const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
@@ -1117,6 +1108,14 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
                     mset(s, c, mget(s, c) - dm[s] * v.x);
                     mset(s, c + 1, mget(s, c + 1) - dm[s] * v.y);
                 }
+            }
+            if (HASJ) reg_sub<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0, dj * beta);
+#pragma unroll
+            for (int s = 0; s < MR; ++s) {
+                if (MREG)
+                    reg_sub<T, NP>(Mrow[MREG ? s : 0], nac, dm[s] * beta);
+                else
+                    Gc[nac * L::LDG + l + s * NP] -= dm[s] * beta;
             }
             if (full) {
                 // R gains the column [d1; beta]: R^-1 gains [-r / beta; 1 / beta]

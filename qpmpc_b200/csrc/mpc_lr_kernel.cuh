@@ -34,29 +34,40 @@ struct LrLay {
     static constexpr int oGt = oPsi + NXM * NP;     // Toeplitz table of the (+) row: gt[e] = c' A^e B
     static constexpr int oH = oGt + NP;             // h, all 2 N rows
     static constexpr int oRi = oH + 2 * NP;         // R^-1 by columns: Ri[k*NP + row]
-    static constexpr int oD = oRi + NP * NP;        // draw, dd, d2, tq, cand, lam [NP each]
+    static constexpr int oD = oRi + NP * NP;        // draw, q, d2, tq, cand, lam [NP each]
     static constexpr int oA = oD + 6 * NP;          // aidx [NP] (int), padded to NP elements
     static constexpr int oRed = oA + NP;            // reduction slots: 8 x 8 bytes (16 elements), then 48 values
-    static constexpr int oSc = oRed + 16 + 48;      // scalars published with d
-    static constexpr int fixed = oSc + 8;           // the staged inputs follow
+    static constexpr int oSc = oRed + 16 + 48;      // scalars published with d [8], W = (kappa I + K)^-1 [16]
+    static constexpr int fixed = oSc + 8 + 16;      // the staged inputs follow
 };
 
 // ---- reductions over the NP threads of the CTA (one or two warps) -----------------------------
 // `red` holds two sets of slots used alternately (parity), so one barrier per call is enough.
 template <int NP>
-__device__ __forceinline__ unsigned long long lr_max_u64(unsigned long long key, unsigned long long *red, int &par) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(FULL_MASK, key, off);
-        key = o > key ? o : key;
-    }
+__device__ __forceinline__ unsigned lr_max_u32(unsigned key, unsigned long long *red, int &par) {
+    key = __reduce_max_sync(FULL_MASK, key);  // REDUX
+    if (NP == 32) return key;
+    unsigned *slot = reinterpret_cast<unsigned *>(red + (par & 1) * 4);
+    par ^= 1;
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = key;
+    __syncthreads();
+    const unsigned a = slot[0], b = slot[1];
+    return a > b ? a : b;
+}
+template <int NP>
+__device__ __forceinline__ unsigned long long lr_min_u64(unsigned long long key, unsigned long long *red, int &par) {
+    // two REDUX: the high words, then the low words of those that tie
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_min_sync(FULL_MASK, hi);
+    const unsigned ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xffffffffu);
+    key = ((unsigned long long)mh << 32) | ml;
     if (NP == 32) return key;
     unsigned long long *slot = red + (par & 1) * 4;
     par ^= 1;
     if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = key;
     __syncthreads();
     const unsigned long long a = slot[0], b = slot[1];
-    return a > b ? a : b;
+    return a < b ? a : b;
 }
 template <typename T, int NP, int NV>
 __device__ __forceinline__ void lr_sum(T (&v)[NV], T *red, int &par) {
@@ -128,15 +139,20 @@ __device__ __forceinline__ void inv_lower_small(const T (&l)[NX * NX], T (&out)[
     }
 }
 
+// resident CTAs per SM the NP = 64 variant is compiled for (caps registers at 65536 / (64 * this))
+#ifndef QPMPC_LR_MINB
+#define QPMPC_LR_MINB 4
+#endif
+
 template <typename T, int NP, int NX>  // @phase LR kernel
-__global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(NP, NP == 32 ? 8 : QPMPC_LR_MINB) mpc_solve_lr_kernel(const SolveParams p) {
     using L = LrLay<T, NP>;
     using T2 = typename Pair<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *sm = reinterpret_cast<T *>(smem_raw + 16);
     T *psis = sm + L::oPsi, *gt = sm + L::oGt, *hs = sm + L::oH, *Ri = sm + L::oRi;
-    T *draw = sm + L::oD, *dd = draw + NP, *d2 = draw + 2 * NP, *tq = draw + 3 * NP, *cands = draw + 4 * NP;
+    T *draw = sm + L::oD, *qs = draw + NP, *d2 = draw + 2 * NP, *tq = draw + 3 * NP, *cands = draw + 4 * NP;
     T *lams = draw + 5 * NP;
     int *aidxs = reinterpret_cast<int *>(sm + L::oA);
     unsigned long long *redk = reinterpret_cast<unsigned long long *>(sm + L::oRed);
@@ -339,6 +355,13 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
             }
     }
 
+    // (kept for phase D in shared memory, not in registers, like psi)
+    qs[l] = qj;
+    if (l == 0) {
+#pragma unroll
+        for (int t = 0; t < NX * NX; ++t) sc[8 + t] = Wm[t];
+    }
+
     // ---- phase B: t = J'q, the owned row of M = G J, violations  // @phase LR rows of M
     T Mrow[NP];
     T viol, cen, wid, vtol, ginv, mn2;
@@ -411,7 +434,7 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
     const T INF = Num<T>::inf();
     {
         // a pair with h+ + h- < 0 admits no point at all
-        const unsigned long long bad = lr_max_u64<NP>((rowvalid && wid < -vtol) ? 1ull : 0ull, redk, par);
+        const unsigned bad = lr_max_u32<NP>((rowvalid && wid < -vtol) ? 1u : 0u, redk, par);
         if (bad && st == 0) st = 2;
     }
     lr_sync<NP>();
@@ -420,14 +443,16 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
             const T off = viol - cen;
             const T vs = abs_(off) - wid;
             const float score = (float)(vs * ginv);
-            unsigned long long key = 0ull;
+            // single-precision key with the row and its sign in the low 7 bits (the ranking is a
+            // heuristic: any violated row is a valid pivot; ties go to the lowest row)
+            unsigned key = 0u;
             if (rowvalid && !active && vs > vtol && score > 0.f)
-                key = ((unsigned long long)__float_as_uint(fmaxf(score, 1e-37f)) << 32) |
-                      (unsigned)((NP - 1 - l) << 1) | (off < T(0) ? 1u : 0u);
-            key = lr_max_u64<NP>(key, redk, par);
-            if (key == 0ull) break;  // primal feasible: optimal
-            pidx = NP - 1 - (int)((key & 0xffffffffull) >> 1);
-            pneg = (key & 1ull) != 0;
+                key = (__float_as_uint(fmaxf(score, 1e-37f)) & ~127u) | (unsigned)((NP - 1 - l) << 1) |
+                      (off < T(0) ? 1u : 0u);
+            key = lr_max_u32<NP>(key, redk, par);
+            if (key == 0u) break;  // primal feasible: optimal
+            pidx = NP - 1 - (int)((key & 127u) >> 1);
+            pneg = (key & 1u) != 0;
             lamp = T(0);
         }
         if (++it > p.max_iter) {
@@ -450,11 +475,10 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         lr_sync<NP>();
         const T dl = draw[l];
         const T d2l = (l >= na) ? dl : T(0);
-        dd[l] = (l < na) ? dl : T(0);
-        d2[l] = d2l;
+        d2[l] = d2l;  // the part of d outside the working set, zero-padded; the rest is read from draw
         T a2v[1] = {d2l * d2l};
-        lr_sync<NP>();              // dd, d2 complete (and the slots of lr_sum's previous use are free)
-        lr_sum<T, NP, 1>(a2v, redv, par);
+        lr_sum<T, NP, 1>(a2v, redv, par);  // (its barrier also publishes d2)
+        if (NP == 32) __syncwarp();
         const T a2 = a2v[0];
         // -G z = M2 m2 for the owned row
         T gz0 = T(0), gz1 = T(0);
@@ -469,11 +493,12 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         T rv = T(0);
         {
             T rv1 = T(0);
-            for (int k = 0; k < na; k += 2) {
-                const T2 dk = *reinterpret_cast<const T2 *>(dd + k);
+            for (int k = 0; k + 1 < na; k += 2) {
+                const T2 dk = *reinterpret_cast<const T2 *>(draw + k);
                 rv += Ri[k * NP + l] * dk.x;
                 rv1 += Ri[(k + 1) * NP + l] * dk.y;
             }
+            if (na & 1) rv += Ri[(na - 1) * NP + l] * draw[na - 1];
             rv += rv1;
         }
         const T lam = lams[l];
@@ -481,8 +506,8 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         cands[l] = cand;
         // smallest ratio, ties to the lowest position: the low 6 bits of the key carry the position
         unsigned long long kmin = ((unsigned long long)__double_as_longlong((double)cand) & ~63ull) | (unsigned)l;
-        kmin = ~lr_max_u64<NP>(~kmin, redk, par);
-        lr_sync<NP>();  // cands visible (one warp: the reduction did not synchronise memory)
+        kmin = lr_min_u64<NP>(kmin, redk, par);  // (two warps: its barrier also publishes cands)
+        if (NP == 32) __syncwarp();
         const int lidx = (int)(kmin & 63ull);
         const T t1 = cands[lidx];
         const T violp = sc[0], dn2 = sc[1];
@@ -500,28 +525,21 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         const bool full = !zzero && t2 <= t1;
         if (full) {  // @phase LR add constraint
             // Householder: reflect d2 onto beta e_na, applied to the columns >= na of M
-            const T mna = d2[na < NP ? na : NP - 1];
+            const T mna = draw[na < NP ? na : NP - 1];
             const T alpha = a2 * ainv;
             const T beta = (mna < T(0)) ? -alpha : alpha;
             const T binv = (mna < T(0)) ? -ainv : ainv;
             const T tau = rcp_(a2 + beta * mna);
-            lr_sync<NP>();
-            if (l == na) d2[l] = mna + beta;  // d2 becomes -v
-            lr_sync<NP>();
-            T dm0 = T(0), dm1 = T(0);
-#pragma unroll
-            for (int c = 0; c < NP; c += 2) {
-                const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-                dm0 += Mrow[c] * v.x;
-                dm1 += Mrow[c + 1] * v.y;
-            }
-            const T dm = (dm0 + dm1) * tau;
+            // -v = d2 + beta e_na: M v is the product with d2 computed above plus one entry of the
+            // row (na is uniform: a switch over registers), and the update is one pass over d2
+            const T dm = (gz + reg_get<T, NP>(Mrow, na) * beta) * tau;
 #pragma unroll
             for (int c = 0; c < NP; c += 2) {
                 const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
                 Mrow[c] -= dm * v.x;
                 Mrow[c + 1] -= dm * v.y;
             }
+            reg_sub<T, NP>(Mrow, na, dm * beta);
             // R gains the column [d1; beta]: R^-1 gains [-r / beta; 1 / beta]
             if (l < na) Ri[na * NP + l] = rv * binv;
             if (l == na) {
@@ -592,7 +610,10 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
     lr_sync<NP>();
     T x = T(0);
     {
-        T w = qj;
+        T w = qs[l];
+        T psl[NX];
+#pragma unroll
+        for (int t = 0; t < NX; ++t) psl[t] = psis[t * NP + l];
         if (st == 0) {
             for (int i = 0; i < na; ++i) {
                 const int ai = aidxs[i];
@@ -603,7 +624,7 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         }
         T pw[NX];
 #pragma unroll
-        for (int t = 0; t < NX; ++t) pw[t] = psi[t] * w;
+        for (int t = 0; t < NX; ++t) pw[t] = psl[t] * w;
         lr_sync<NP>();
         lr_sum<T, NP, NX>(pw, redv, par);
         T corr = T(0);
@@ -611,13 +632,13 @@ __global__ void __launch_bounds__(NP, NP == 32 ? 8 : 4) mpc_solve_lr_kernel(cons
         for (int i = 0; i < NX; ++i) {
             T s = T(0);
 #pragma unroll
-            for (int j = 0; j < NX; ++j) s += Wm[i * NX + j] * pw[j];
-            corr += psi[i] * s;
+            for (int j = 0; j < NX; ++j) s += sc[8 + i * NX + j] * pw[j];
+            corr += psl[i] * s;
         }
         x = -(w - corr) * rcp_(w_u);
     }
     {
-        const unsigned long long bad = lr_max_u64<NP>((l < n && !(abs_(x) < INF)) ? 1ull : 0ull, redk, par);
+        const unsigned bad = lr_max_u32<NP>((l < n && !(abs_(x) < INF)) ? 1u : 0u, redk, par);
         if (st == 0 && bad) st = 3;
     }
     const T xo = (st == 0) ? x : Num<T>::nan();

@@ -366,13 +366,15 @@ def test_kernels_reproduce_published_optima(make, method):
 # -- paired rows (desc.paired): one stored row stands for [G+; -G+] ---------------------------
 
 @pytest.mark.parametrize("kind", ["ti8", "ti16", "ti32", "pendulum", "pendulum_ltv", "humanoid", "infeasible_pair"])
-def test_paired_row_kernels_match_the_oracle_and_the_unpaired_kernels(kind):
-    """Every BASELINE workload has two-sided bounds (rows [M; -M]): the paired variants keep
+def test_paired_row_kernels_match_the_oracle_and_the_unpaired_kernels(kind, monkeypatch):
+    """(QPMPC_B200_LR=0: the warp kernels, not the long-horizon kernel that takes n > 16.)
+    Every BASELINE workload has two-sided bounds (rows [M; -M]): the paired variants keep
     one row per pair.  Same answers as the oracle and as the unpaired variants, same
     iteration counts (it is the same active-set iteration); a pair with h+ + h- < 0 is
     infeasible."""
     from qpmpc_b200.workloads import rows_are_paired
 
+    monkeypatch.setenv("QPMPC_B200_LR", "0")
     w = {"ti8": lambda: triple_integrator_batch(9, N=8, seed=11), "ti16": lambda: triple_integrator_batch(37, seed=12),
          "ti32": lambda: triple_integrator_batch(5, N=32, seed=13), "pendulum": lambda: pendulum_batch(21, seed=14),
          "pendulum_ltv": lambda: pendulum_batch(7, seed=15, ltv_model=True), "humanoid": lambda: humanoid_batch(11, seed=16),
