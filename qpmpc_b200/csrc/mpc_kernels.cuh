@@ -1085,37 +1085,80 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
             const T beta = full ? ((mna < T(0)) ? -alpha : alpha) : T(0);
             const T binv = (mna < T(0)) ? -ainv : ainv;
             const T tau = full ? rcp_(a2 + beta * mna) : T(0);
-            // -v = d2 + beta e_na: the products M v (and J v) are the products with d2 computed
-            // above plus one entry of the row -- a switch over registers, na being uniform over
-            // the lanes of an instance -- and the update is one pass over d2 plus that entry
-            T dj = T(0);
-            if (HASJ) dj = (z + reg_get<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0) * beta) * tau;
-            T dm[MR];
-#pragma unroll
-            for (int s = 0; s < MR; ++s) {
-                const T mcol = MREG ? reg_get<T, NP>(Mrow[MREG ? s : 0], nac) : Gc[nac * L::LDG + l + s * NP];
-                dm[s] = (gz[s] + mcol * beta) * tau;
-            }
-#pragma unroll
-            for (int c = 0; c < NP; c += 2) {
-                const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
-                if (HASJ) {
-                    Jrow[HASJ ? c : 0] -= dj * v.x;
-                    Jrow[HASJ ? c + 1 : 0] -= dj * v.y;
-                }
+            // One instance per warp (NP = 32): na is uniform, so one entry of a register row can be
+            // taken by a switch and the product M v reuses the product with d2 from above.  With
+            // several instances per warp the switch would diverge: two passes over d2 are cheaper.
+            constexpr bool ONEPASS = (NP == 32);
+            if (ONEPASS) {
+                // -v = d2 + beta e_na: the products M v (and J v) are the products with d2 computed
+                // above plus one entry of the row -- a switch over registers, na being uniform over
+                // the lanes of an instance -- and the update is one pass over d2 plus that entry
+                T dj = T(0);
+                if (HASJ) dj = (z + reg_get<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0) * beta) * tau;
+                T dm[MR];
 #pragma unroll
                 for (int s = 0; s < MR; ++s) {
-                    mset(s, c, mget(s, c) - dm[s] * v.x);
-                    mset(s, c + 1, mget(s, c + 1) - dm[s] * v.y);
+                    const T mcol = MREG ? reg_get<T, NP>(Mrow[MREG ? s : 0], nac) : Gc[nac * L::LDG + l + s * NP];
+                    dm[s] = (gz[s] + mcol * beta) * tau;
                 }
-            }
-            if (HASJ) reg_sub<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0, dj * beta);
 #pragma unroll
-            for (int s = 0; s < MR; ++s) {
-                if (MREG)
-                    reg_sub<T, NP>(Mrow[MREG ? s : 0], nac, dm[s] * beta);
-                else
-                    Gc[nac * L::LDG + l + s * NP] -= dm[s] * beta;
+                for (int c = 0; c < NP; c += 2) {
+                    const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
+                    if (HASJ) {
+                        Jrow[HASJ ? c : 0] -= dj * v.x;
+                        Jrow[HASJ ? c + 1 : 0] -= dj * v.y;
+                    }
+#pragma unroll
+                    for (int s = 0; s < MR; ++s) {
+                        mset(s, c, mget(s, c) - dm[s] * v.x);
+                        mset(s, c + 1, mget(s, c + 1) - dm[s] * v.y);
+                    }
+                }
+                if (HASJ) reg_sub<T, HASJ ? NP : 1>(Jrow, HASJ ? nac : 0, dj * beta);
+#pragma unroll
+                for (int s = 0; s < MR; ++s) {
+                    if (MREG)
+                        reg_sub<T, NP>(Mrow[MREG ? s : 0], nac, dm[s] * beta);
+                    else
+                        Gc[nac * L::LDG + l + s * NP] -= dm[s] * beta;
+                }
+            } else {
+                __syncwarp();
+                if (full && l == na) d2[l] = mna + beta;  // d2 becomes -v
+                __syncwarp();
+                T dj = T(0), dj1 = T(0);
+                T dm[MR];
+#pragma unroll
+                for (int s = 0; s < MR; ++s) dm[s] = T(0);
+#pragma unroll
+                for (int c = 0; c < NP; c += 2) {
+                    const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
+                    if (HASJ) {
+                        dj += Jrow[HASJ ? c : 0] * v.x;
+                        dj1 += Jrow[HASJ ? c + 1 : 0] * v.y;
+                    }
+#pragma unroll
+                    for (int s = 0; s < MR; ++s) {
+                        dm[s] += mget(s, c) * v.x;
+                        dm[s] += mget(s, c + 1) * v.y;
+                    }
+                }
+                dj = (dj + dj1) * tau;
+#pragma unroll
+                for (int s = 0; s < MR; ++s) dm[s] *= tau;
+#pragma unroll
+                for (int c = 0; c < NP; c += 2) {
+                    const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
+                    if (HASJ) {
+                        Jrow[HASJ ? c : 0] -= dj * v.x;
+                        Jrow[HASJ ? c + 1 : 0] -= dj * v.y;
+                    }
+#pragma unroll
+                    for (int s = 0; s < MR; ++s) {
+                        mset(s, c, mget(s, c) - dm[s] * v.x);
+                        mset(s, c + 1, mget(s, c + 1) - dm[s] * v.y);
+                    }
+                }
             }
             if (full) {
                 // R gains the column [d1; beta]: R^-1 gains [-r / beta; 1 / beta]
