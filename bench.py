@@ -312,19 +312,22 @@ def kernel_name(args):
     t = "float" if args.config == 4 else "double"
     if args.method == "pdip":
         return f"mpc_pdip_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
+    terminal_only = args.config != 3  # config 3 has a stage cost
+    if t == "double" and terminal_only and 16 < n <= 64:
+        return f"mpc_solve_lr_kernel<double,NP={32 if n <= 32 else 64}>"  # structure-exploiting (rank-nx Hessian)
     if n > 32:
         return f"mpc_solve_cta_kernel<{t}>"
-    return f"mpc_solve_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
+    return f"mpc_solve_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32},paired rows>"
 
 
-def measured_traffic(args):
-    """dram bytes (read + write) of one launch from the newest committed ncu summary of this
-    kernel and shape (profiles/*.txt written by tools/ncu_summary.py), with its file name;
-    (None, None) when there is none -- never a constant."""
-    want = "mpc_pdip_kernel" if args.method == "pdip" else ("mpc_solve_cta_kernel" if args.horizon > 32
-                                                           else "mpc_solve_kernel")
+def measured_profile(args):
+    """Figures of the newest committed ncu summary of this kernel and shape (profiles/r*_*.txt,
+    written by tools/ncu_summary.py): dram bytes (read + write) of one launch, and the flops the
+    launch executed (opcode counts of the profiler) per solve.  Missing entries are None --
+    never a constant."""
+    want = kernel_name(args).split("<")[0]
     tag = {2: "ti16", 3: "pend", 4: "hum", 5: f"ti{args.horizon}"}[args.config]
-    best = (None, None)
+    best = {"traffic": None, "flops_per_solve": None, "source": None}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_*.txt"))):
         base = os.path.basename(path)
         if tag not in base:
@@ -333,7 +336,7 @@ def measured_traffic(args):
             text = open(path).read()
         except OSError:
             continue
-        m = re.search(r"== kernel: void (?:qpmpc::)?(\w+)<[^\n]*grid \((\d+)", text)
+        m = re.search(r"== kernel: void (?:qpmpc::)?(\w+)<", text)
         if not m or m.group(1) != want:
             continue
         vals = {}
@@ -342,8 +345,14 @@ def measured_traffic(args):
             if mm:
                 mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[mm.group(2)]
                 vals[key] = float(mm.group(1)) * mult
-        if len(vals) == 2:
-            best = (sum(vals.values()), base)
+        if len(vals) != 2:
+            continue
+        best = {"traffic": sum(vals.values()), "flops_per_solve": None, "source": base}
+        mb = re.search(r"instances_per_launch (\d+)", text)
+        mf = re.search(r"flops_fp(?:64|32)_per_launch (\d+)", text if args.config != 4 else text[text.find("fp32 warp"):])
+        if mb and mf and int(mf.group(1)) > 0:
+            best["flops_per_solve"] = int(mf.group(1)) / int(mb.group(1))
+            best["profile_batch"] = int(mb.group(1))
     return best
 
 
@@ -359,11 +368,20 @@ def flop_models(args, iters_mean):
         + 2 * nx * n * n + (2 * N * nx * n * n if has_wx else 0)
     f_iter = 2 * m * n * n + n**3 / 3 + 6 * n * n + 12 * m * n
     survey = f_cond + 10 * f_iter
-    # executed by the active-set kernel: condensing recursions, Cholesky, forward substitutions for
-    # t and the m rows of M, the final two triangular solves, and per iteration one matrix-vector
-    # product with M plus one Householder update of M
-    f_setup = N * (4 * nx * nx + 2 * nc * nx) * n + n**3 / 3 + (m + 1) * n * n + 2 * n * n
-    executed = f_setup + iters_mean * 6 * m * n
+    # executed by the active-set kernels at the measured mean iteration count (paired rows: one
+    # stored row per [M; -M] pair, mp = m / 2 rows of M):
+    mp = m // 2
+    if 16 < n <= 64 and not has_wx and args.config != 4:
+        # long-horizon kernel: matrix powers, 3 x 3 algebra, rows of M in O(n nx), one product with M
+        # and one Householder update per iteration, recovery of x by Woodbury
+        f_setup = 2 * nx**3 * 6 + 4 * nx * nx * 6 + mp * (4 * nx * n + 4 * n) + 8 * nx * n
+        executed = f_setup + iters_mean * (4 * mp * n + n * n / 2)
+    else:
+        # warp kernel: matrix powers, Cholesky, forward substitutions for t and the rows of M, the
+        # final two triangular solves; per iteration a product with M, a Householder update (two
+        # passes) and the product with R^-1
+        f_setup = 2 * nx**3 * 4 + 4 * nx * nx * 4 + n**3 / 3 + (mp + 1) * n * n + 2 * n * n
+        executed = f_setup + iters_mean * (6 * mp * n + n * n / 2)
     return survey, executed
 
 
@@ -577,8 +595,9 @@ def run_b200(args, rank, local_rank, world):
                         pass
         e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "call": "qpmpc_b200_solve_host (pinned host buffers; H2D, kernel, D2H pipelined over streams in "
-                       "chunks; sync per step)" + ("; ranks write their rows into one host array shared by the "
+               "call": "qpmpc_b200_solve_host (pinned host buffers, zero-copy: one kernel launch whose bulk-TMA staging "
+                       "reads the operands from host memory over PCIe and whose epilogue stores U / status into host "
+                       "memory; sync per step)" + ("; ranks write their rows into one host array shared by the "
                                                    "job (the gather), barrier per step" if world > 1 else "")}
     else:
         # config 3: the state lives on the device for the whole loop; a step uploads the initial
@@ -628,7 +647,10 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     value = world * solves_per_step(args) * args.steps / (total_ms * 1e-3)
-    traffic, traffic_src = measured_traffic(args)
+    prof = measured_profile(args)
+    traffic, traffic_src = prof["traffic"], prof["source"]
+    if traffic is not None and prof.get("profile_batch") not in (None, B):
+        traffic = traffic * B / prof["profile_batch"]  # the summary's launch had another batch
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -648,7 +670,7 @@ def run_b200(args, rank, local_rank, world):
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }
-    if args.config != 4 and args.method == "active_set":
+    if args.config != 4:
         line["fp64"] = {
             "peak_tflops": tf.value,
             "peak_source": "qpmpc_b200_fp64_peak: 16 independent DFMA chains per thread, 8 CTAs of 256 threads "
@@ -659,8 +681,17 @@ def run_b200(args, rank, local_rank, world):
                          "model": "SURVEY 8(d): dense structure-agnostic condensing + 10 interior-point iterations"},
             "executed": {"flops_per_solve": f_exec, "achieved_tflops": tfl(f_exec),
                          "frac": tfl(f_exec) / tf.value if tf.value > 0 else None,
-                         "model": "flops of the active-set algorithm at the measured mean iteration count"},
+                         "model": "flops the kernel's algorithm needs at the measured mean iteration count "
+                                  "(paired rows, structure exploited; a lower bound of what is executed)"},
         }
+        if args.method != "active_set":
+            del line["fp64"]["executed"]  # (the model above is the active-set algorithm's)
+        if prof["flops_per_solve"]:
+            fm = prof["flops_per_solve"]
+            line["fp64"]["executed_ncu"] = {
+                "flops_per_solve": fm, "achieved_tflops": tfl(fm), "frac": tfl(fm) / tf.value if tf.value > 0 else None,
+                "model": "DFMA/DMUL/DADD warp instructions the profiler counted for one launch x 32 lanes "
+                         f"(profiles/{prof['source']}), at this run's kernel time"}
     if gather_check is not None:
         line["gather_check"] = gather_check
     if args.config == 3:

@@ -151,10 +151,21 @@ int qpmpc_b200_solve_scatter(const qpmpc_b200_desc *desc, const qpmpc_b200_opera
                              const qpmpc_b200_outputs *out, const qpmpc_b200_peers *peers,
                              void *stream);
 
-/* Same with HOST buffers: copies operands to the device (pinned staging,
- * buffers cached inside the library per calling thread), solves, copies the
- * outputs back and synchronises.  This is the call a host program that has no
- * device memory of its own binds. */
+/* Same with HOST buffers; synchronises before returning.  This is the call a
+ * host program that has no device memory of its own binds.
+ *  - PINNED (page-locked) buffers, the fast path: zero-copy.  Page-locked host
+ *    memory is mapped into the device's address space, so ONE launch of the
+ *    solve kernel does everything: each CTA's bulk-TMA staging pulls its
+ *    operands over PCIe, the epilogue stores the U rows (and status) straight
+ *    into the caller's buffers.  Upload, compute and download overlap CTA by
+ *    CTA; only operands shared by the batch are copied to the device first.
+ *    (QPMPC_B200_HOST_ZEROCOPY=0: staged instead -- chunks of the batch whose
+ *    upload, kernel and download overlap on three streams, captured once into
+ *    a CUDA graph per (descriptor, pointers) and replayed.)
+ *  - pageable buffers: staged through device buffers the library caches per
+ *    calling thread, copied straight from / to the caller's pointers.
+ * Cached buffers, streams and graphs are freed when the calling thread exits
+ * or switches to another device. */
 int qpmpc_b200_solve_host(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
                           const qpmpc_b200_outputs *out, int device);
 

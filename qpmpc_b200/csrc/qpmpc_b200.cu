@@ -109,21 +109,75 @@ int dispatch_condense(const SolveParams &p, const Variant &v, cudaStream_t s) {
 }
 
 // ---- host-buffer entry: cached device buffers, one set per calling thread ----
+// A replayable CUDA graph of one host-buffer solve: the chunked copies and kernels of
+// qpmpc_b200_solve_host for one (descriptor, host pointers, chunk) combination.
+struct HostGraph {
+    qpmpc_b200_desc desc;
+    qpmpc_b200_operands in;
+    qpmpc_b200_outputs out;
+    int chunk = 0;
+    int kernels = 0;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long last_use = 0;
+};
+
 struct HostCache {
     static constexpr int NSTREAM = 3;
+    static constexpr int NGRAPH = 8;
     int device = -1;
     cudaStream_t stream[NSTREAM] = {nullptr, nullptr, nullptr};
-    cudaEvent_t shared_ready = nullptr;
+    cudaEvent_t shared_ready = nullptr, fork = nullptr, join[NSTREAM] = {nullptr, nullptr, nullptr};
     void *buf[OP_COUNT] = {nullptr};
     size_t cap[OP_COUNT] = {0};
     void *U = nullptr, *Z = nullptr;
     int32_t *status = nullptr, *iters = nullptr;
     size_t capU = 0, capZ = 0, capS = 0, capI = 0;
+    HostGraph graphs[NGRAPH];
+    unsigned long long clock = 0;
+
+    void drop_graphs() {
+        for (HostGraph &g : graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = HostGraph();
+        }
+    }
+    // Frees everything (under the device it was created on).
+    void release() {
+        if (device < 0) return;
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cudaSetDevice(device) == cudaSuccess) {
+            drop_graphs();
+            for (int i = 0; i < NSTREAM; ++i) {
+                if (stream[i]) cudaStreamDestroy(stream[i]);
+                if (join[i]) cudaEventDestroy(join[i]);
+            }
+            if (shared_ready) cudaEventDestroy(shared_ready);
+            if (fork) cudaEventDestroy(fork);
+            for (int o = 0; o < OP_COUNT; ++o)
+                if (buf[o]) cudaFree(buf[o]);
+            if (U) cudaFree(U);
+            if (Z) cudaFree(Z);
+            if (status) cudaFree(status);
+            if (iters) cudaFree(iters);
+        }
+        if (cur >= 0) cudaSetDevice(cur);
+        *this = HostCache();
+    }
+    HostCache() = default;
+    HostCache(const HostCache &) = default;
+    HostCache &operator=(const HostCache &) = default;
+    ~HostCache() {
+        // thread exit: release unless the CUDA runtime is already being torn down
+        if (device >= 0 && cudaFree(nullptr) == cudaSuccess) release();
+    }
 };
 thread_local HostCache g_cache;
 
-cudaError_t ensure(void **ptr, size_t *cap, size_t bytes) {
+// `bytes` fit in the cached buffer; *grew is set when it had to be reallocated.
+cudaError_t ensure(void **ptr, size_t *cap, size_t bytes, bool *grew = nullptr) {
     if (bytes <= *cap) return cudaSuccess;
+    if (grew) *grew = true;
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
     *cap = 0;
@@ -131,6 +185,18 @@ cudaError_t ensure(void **ptr, size_t *cap, size_t bytes) {
     if (e == cudaSuccess) *cap = bytes;
     return e;
 }
+
+// Device address of a page-locked host buffer (nullptr if `p` is pageable or not mapped).
+void *mapped_pointer(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+bool is_pinned(const void *p) { return !p || mapped_pointer(p) != nullptr; }
 
 // FP64 FMA peak probe: 16 independent dependent chains per thread.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
@@ -392,14 +458,14 @@ int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *i
     if (e != cudaSuccess) return (int)e;
     HostCache &c = g_cache;
     if (c.device != device) {
-        c = HostCache();
+        c.release();  // buffers, streams and graphs of the device this thread used before
         c.device = device;
         for (int i = 0; i < HostCache::NSTREAM; ++i) {
-            e = cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking);
-            if (e != cudaSuccess) return (int)e;
+            if ((e = cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
         }
-        e = cudaEventCreateWithFlags(&c.shared_ready, cudaEventDisableTiming);
-        if (e != cudaSuccess) return (int)e;
+        if ((e = cudaEventCreateWithFlags(&c.shared_ready, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        if ((e = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
     }
     SolveParams p;
     fill_params(d, in, &p);
@@ -407,69 +473,207 @@ int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *i
     const char *host[OP_COUNT] = {(const char *)in->A, (const char *)in->B, (const char *)in->C, (const char *)in->D,
                                   (const char *)in->e, (const char *)in->x0, (const char *)in->goal,
                                   (const char *)in->targets};
+
+    // ZERO-COPY (the default with page-locked buffers): no staging copies at all.  Page-locked
+    // host memory is mapped into the device's address space, so the solve kernel's own bulk-TMA
+    // staging pulls each CTA's operands over PCIe and its epilogue stores the U rows straight
+    // into the caller's buffer: upload, compute and download overlap CTA by CTA inside ONE kernel.
+    // Only operands shared by the batch (read by every CTA) are copied to the device first.
+    if (env_int("QPMPC_B200_HOST_ZEROCOPY", 1) != 0) {
+        void *map_in[OP_COUNT] = {nullptr};
+        bool ok = true;
+        for (int o = 0; o < OP_COUNT && ok; ++o)
+            if (p.op[o].ptr) ok = (map_in[o] = mapped_pointer(host[o])) != nullptr;
+        void *mU = ok ? mapped_pointer(out->U) : nullptr, *mS = ok ? mapped_pointer(out->status) : nullptr;
+        void *mI = (ok && out->iters) ? mapped_pointer(out->iters) : nullptr;
+        void *mZ = (ok && out->Z) ? mapped_pointer(out->Z) : nullptr;
+        ok = ok && mU && mS && (!out->iters || mI) && (!out->Z || mZ);
+        if (ok) {
+            for (int o = 0; o < OP_COUNT; ++o) {
+                const OperandView &v = p.op[o];
+                if (!v.ptr || v.per_instance) continue;
+                bool moved = false;
+                if ((e = ensure(&c.buf[o], &c.cap[o], (size_t)v.sz * es, &moved)) != cudaSuccess) return (int)e;
+                if (moved) c.drop_graphs();  // (graphs of the staged path hold the old address)
+                e = cudaMemcpyAsync(c.buf[o], host[o], (size_t)v.sz * es, cudaMemcpyHostToDevice, c.stream[0]);
+                if (e != cudaSuccess) return (int)e;
+                map_in[o] = c.buf[o];
+            }
+            const qpmpc_b200_operands dev = {map_in[OP_A], map_in[OP_B], map_in[OP_C], map_in[OP_D],
+                                             map_in[OP_E], map_in[OP_X0], map_in[OP_GOAL], map_in[OP_TGT]};
+            const qpmpc_b200_outputs dout = {mU, (int32_t *)mS, (int32_t *)mI, mZ};
+            rc = qpmpc_b200_solve(d, &dev, &dout, c.stream[0]);
+            e = cudaStreamSynchronize(c.stream[0]);  // (also after a failed launch: the shared copies are in flight)
+            if (rc) return rc;
+            return (int)e;
+        }
+    }
     // Device copies of the operands and outputs, cached per calling thread.
+    bool grew = false;
     for (int o = 0; o < OP_COUNT; ++o) {
         const OperandView &v = p.op[o];
         if (!v.ptr) continue;
         const size_t bytes = (size_t)v.sz * (v.per_instance ? d->batch : 1) * es;
-        if ((e = ensure(&c.buf[o], &c.cap[o], bytes)) != cudaSuccess) return (int)e;
+        if ((e = ensure(&c.buf[o], &c.cap[o], bytes, &grew)) != cudaSuccess) return (int)e;
     }
     const size_t rU = (size_t)p.n * es, rZ = (size_t)p.m * es;
-    if ((e = ensure(&c.U, &c.capU, rU * d->batch)) != cudaSuccess) return (int)e;
-    if ((e = ensure((void **)&c.status, &c.capS, (size_t)d->batch * 4)) != cudaSuccess) return (int)e;
-    if (out->iters && (e = ensure((void **)&c.iters, &c.capI, (size_t)d->batch * 4)) != cudaSuccess) return (int)e;
+    if ((e = ensure(&c.U, &c.capU, rU * d->batch, &grew)) != cudaSuccess) return (int)e;
+    if ((e = ensure((void **)&c.status, &c.capS, (size_t)d->batch * 4, &grew)) != cudaSuccess) return (int)e;
+    if (out->iters && (e = ensure((void **)&c.iters, &c.capI, (size_t)d->batch * 4, &grew)) != cudaSuccess)
+        return (int)e;
     const bool wantZ = out->Z && rZ;
-    if (wantZ && (e = ensure(&c.Z, &c.capZ, rZ * d->batch)) != cudaSuccess) return (int)e;
-    // Operands shared by the batch go up once; every chunk waits for them.
-    bool any_shared = false;
-    for (int o = 0; o < OP_COUNT; ++o) {
-        const OperandView &v = p.op[o];
-        if (!v.ptr || v.per_instance) continue;
-        cudaMemcpyAsync(c.buf[o], host[o], (size_t)v.sz * es, cudaMemcpyHostToDevice, c.stream[0]);
-        any_shared = true;
-    }
-    if (any_shared) cudaEventRecord(c.shared_ready, c.stream[0]);
-    // Chunks of the batch round-robin over the streams so that the upload of
-    // one chunk, the kernel of the previous one and the download of the one
-    // before overlap (host buffers should be pinned for that).
+    if (wantZ && (e = ensure(&c.Z, &c.capZ, rZ * d->batch, &grew)) != cudaSuccess) return (int)e;
+    if (grew) c.drop_graphs();  // they hold the old device addresses
+
+    // Pinned host buffers: the whole pipeline below is captured once into a CUDA graph per
+    // (descriptor, pointers) and replayed -- one launch per call instead of ~10 stream
+    // operations per chunk, which is what allows chunks small enough to hide the first upload and
+    // the last download.  Pageable buffers (no overlap possible anyway) take the direct path.
+    bool pinned = env_int("QPMPC_B200_HOST_GRAPH", 1) != 0;
+    for (int o = 0; o < OP_COUNT && pinned; ++o)
+        if (p.op[o].ptr) pinned = is_pinned(host[o]);
+    pinned = pinned && is_pinned(out->U) && is_pinned(out->status) && is_pinned(out->iters) && is_pinned(out->Z);
     int chunk = env_int("QPMPC_B200_HOST_CHUNK", 16384);
     if (chunk < 256) chunk = 256;
-    int idx = 0;
-    for (int lo = 0; lo < d->batch; lo += chunk, ++idx) {
-        const int cnt = d->batch - lo < chunk ? d->batch - lo : chunk;
-        cudaStream_t s = c.stream[idx % HostCache::NSTREAM];
-        if (any_shared && idx % HostCache::NSTREAM != 0 && idx < HostCache::NSTREAM)
-            cudaStreamWaitEvent(s, c.shared_ready, 0);
-        qpmpc_b200_operands dev;
-        const void **devp[OP_COUNT] = {&dev.A, &dev.B, &dev.C, &dev.D, &dev.e, &dev.x0, &dev.goal, &dev.targets};
-        for (int o = 0; o < OP_COUNT; ++o) {
-            *devp[o] = nullptr;
-            const OperandView &v = p.op[o];
-            if (!v.ptr) continue;
-            if (!v.per_instance) {
-                *devp[o] = c.buf[o];
-                continue;
-            }
-            const size_t off = (size_t)lo * v.sz * es, bytes = (size_t)cnt * v.sz * es;
-            e = cudaMemcpyAsync((char *)c.buf[o] + off, host[o] + off, bytes, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) return (int)e;
-            *devp[o] = (char *)c.buf[o] + off;
+    // Chunk schedule: full chunks in the middle, a short ramp at both ends -- nothing overlaps
+    // the first upload and the last download, so those chunks are a quarter and a half of a
+    // full one (QPMPC_B200_HOST_RAMP=0: uniform chunks).
+    int sched[64], nsched = 0;
+    {
+        const bool ramp = env_int("QPMPC_B200_HOST_RAMP", 1) != 0 && d->batch >= 3 * chunk && chunk >= 1024;
+        int left = d->batch;
+        const int head[2] = {chunk / 4, chunk / 2};
+        int tail = ramp ? chunk / 4 + chunk / 2 : 0;
+        if (ramp)
+            for (int h : head) sched[nsched++] = h, left -= h;
+        while (left - tail > 0 && nsched < 60) {
+            const int c0 = left - tail < chunk ? left - tail : chunk;
+            sched[nsched++] = c0;
+            left -= c0;
         }
-        qpmpc_b200_desc dc = *d;
-        dc.batch = cnt;
-        qpmpc_b200_outputs dout = {(char *)c.U + rU * lo, c.status + lo, out->iters ? c.iters + lo : nullptr,
-                                   wantZ ? (char *)c.Z + rZ * lo : nullptr};
-        rc = qpmpc_b200_solve(&dc, &dev, &dout, s);
-        if (rc) return rc;
-        cudaMemcpyAsync((char *)out->U + rU * lo, dout.U, rU * cnt, cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(out->status + lo, dout.status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
-        if (dout.iters) cudaMemcpyAsync(out->iters + lo, dout.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
-        if (dout.Z) cudaMemcpyAsync((char *)out->Z + rZ * lo, dout.Z, rZ * cnt, cudaMemcpyDeviceToHost, s);
+        if (ramp) sched[nsched++] = chunk / 2, sched[nsched++] = chunk / 4, left -= tail;
+        if (left > 0) sched[nsched - 1] += left;  // (more than 60 chunks: the last one takes the rest)
     }
-    for (int i = 0; i < HostCache::NSTREAM; ++i) {
-        cudaError_t ei = cudaStreamSynchronize(c.stream[i]);
-        if (ei != cudaSuccess) e = ei;
+
+    // Enqueues the pipeline on the cache's streams: operands shared by the batch go up once and
+    // every chunk waits for them; chunks of the batch round-robin over the streams so that the
+    // upload of one chunk, the kernel of the previous one and the download of the one before
+    // overlap.  Returns the number of kernels enqueued (< 0: an error code of the ABI, with
+    // *cuda_err set for CUDA errors).
+    auto enqueue = [&](cudaError_t *cuda_err) -> int {
+        int kernels = 0;
+        bool any_shared = false;
+        for (int o = 0; o < OP_COUNT; ++o) {
+            const OperandView &v = p.op[o];
+            if (!v.ptr || v.per_instance) continue;
+            *cuda_err = cudaMemcpyAsync(c.buf[o], host[o], (size_t)v.sz * es, cudaMemcpyHostToDevice, c.stream[0]);
+            if (*cuda_err != cudaSuccess) return -1000;
+            any_shared = true;
+        }
+        if (any_shared) cudaEventRecord(c.shared_ready, c.stream[0]);
+        int lo = 0;
+        for (int idx = 0; idx < nsched; lo += sched[idx], ++idx) {
+            const int cnt = sched[idx];
+            cudaStream_t s = c.stream[idx % HostCache::NSTREAM];
+            if (any_shared && idx % HostCache::NSTREAM != 0 && idx < HostCache::NSTREAM)
+                cudaStreamWaitEvent(s, c.shared_ready, 0);
+            qpmpc_b200_operands dev;
+            const void **devp[OP_COUNT] = {&dev.A, &dev.B, &dev.C, &dev.D, &dev.e, &dev.x0, &dev.goal, &dev.targets};
+            for (int o = 0; o < OP_COUNT; ++o) {
+                *devp[o] = nullptr;
+                const OperandView &v = p.op[o];
+                if (!v.ptr) continue;
+                if (!v.per_instance) {
+                    *devp[o] = c.buf[o];
+                    continue;
+                }
+                const size_t off = (size_t)lo * v.sz * es, bytes = (size_t)cnt * v.sz * es;
+                *cuda_err = cudaMemcpyAsync((char *)c.buf[o] + off, host[o] + off, bytes, cudaMemcpyHostToDevice, s);
+                if (*cuda_err != cudaSuccess) return -1000;
+                *devp[o] = (char *)c.buf[o] + off;
+            }
+            qpmpc_b200_desc dc = *d;
+            dc.batch = cnt;
+            qpmpc_b200_outputs dout = {(char *)c.U + rU * lo, c.status + lo, out->iters ? c.iters + lo : nullptr,
+                                       wantZ ? (char *)c.Z + rZ * lo : nullptr};
+            const int krc = qpmpc_b200_solve(&dc, &dev, &dout, s);
+            if (krc) {
+                *cuda_err = krc > 0 ? (cudaError_t)krc : cudaSuccess;
+                return krc > 0 ? -1000 : krc;
+            }
+            ++kernels;
+            cudaError_t e1 = cudaMemcpyAsync((char *)out->U + rU * lo, dout.U, rU * cnt, cudaMemcpyDeviceToHost, s);
+            cudaError_t e2 = cudaMemcpyAsync(out->status + lo, dout.status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
+            cudaError_t e3 = cudaSuccess, e4 = cudaSuccess;
+            if (dout.iters) e3 = cudaMemcpyAsync(out->iters + lo, dout.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s);
+            if (dout.Z) e4 = cudaMemcpyAsync((char *)out->Z + rZ * lo, dout.Z, rZ * cnt, cudaMemcpyDeviceToHost, s);
+            for (cudaError_t ei : {e1, e2, e3, e4})
+                if (ei != cudaSuccess) {
+                    *cuda_err = ei;
+                    return -1000;
+                }
+        }
+        return kernels;
+    };
+    // Waits for everything in flight; the first error wins (never returns with copies or
+    // kernels still running on the caller's buffers).
+    auto drain = [&](cudaError_t first) -> cudaError_t {
+        for (int i = 0; i < HostCache::NSTREAM; ++i) {
+            cudaError_t ei = cudaStreamSynchronize(c.stream[i]);
+            if (first == cudaSuccess) first = ei;
+        }
+        return first;
+    };
+
+    if (pinned) {
+        HostGraph *g = nullptr, *victim = &c.graphs[0];
+        for (HostGraph &cand : c.graphs) {
+            if (cand.exec && cand.chunk == chunk && !std::memcmp(&cand.desc, d, sizeof(*d)) &&
+                !std::memcmp(&cand.in, in, sizeof(*in)) && !std::memcmp(&cand.out, out, sizeof(*out)))
+                g = &cand;
+            if (cand.last_use < victim->last_use) victim = &cand;
+        }
+        if (!g) {
+            cudaError_t ce = cudaSuccess;
+            cudaGraph_t graph = nullptr;
+            if ((e = cudaStreamBeginCapture(c.stream[0], cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return (int)e;
+            cudaEventRecord(c.fork, c.stream[0]);
+            for (int i = 1; i < HostCache::NSTREAM; ++i) cudaStreamWaitEvent(c.stream[i], c.fork, 0);
+            const int kernels = enqueue(&ce);
+            for (int i = 1; i < HostCache::NSTREAM; ++i) {
+                cudaEventRecord(c.join[i], c.stream[i]);
+                cudaStreamWaitEvent(c.stream[0], c.join[i], 0);
+            }
+            e = cudaStreamEndCapture(c.stream[0], &graph);
+            if (kernels < 0 || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (kernels < 0 && kernels != -1000) return kernels;
+                return (int)(ce != cudaSuccess ? ce : e);
+            }
+            if (victim->exec) cudaGraphExecDestroy(victim->exec);
+            *victim = HostGraph();
+            e = cudaGraphInstantiate(&victim->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return (int)e;
+            victim->desc = *d;
+            victim->in = *in;
+            victim->out = *out;
+            victim->chunk = chunk;
+            victim->kernels = kernels;
+            g = victim;
+            g_launches.fetch_sub(kernels);  // counted while capturing; every replay counts them below
+        }
+        g->last_use = ++c.clock;
+        e = cudaGraphLaunch(g->exec, c.stream[0]);
+        for (int k = 0; k < g->kernels && e == cudaSuccess; ++k) count_launch();
+        cudaError_t es0 = cudaStreamSynchronize(c.stream[0]);
+        return (int)(e != cudaSuccess ? e : es0);
     }
+    cudaError_t ce = cudaSuccess;
+    const int kernels = enqueue(&ce);
+    e = drain(ce);
+    if (kernels < 0 && kernels != -1000) return kernels;
     return (int)e;
 }
 

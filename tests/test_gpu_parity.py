@@ -446,3 +446,48 @@ def test_published_optima_on_the_device(method):
             assert np.abs(plan.multipliers[0].cpu().numpy() - qp["z"]).max() <= 1e-6
         ref = _oracle(w)
         assert ref["status"][0] == 0 and np.abs(x - ref["U"][0]).max() <= U_TOL
+
+
+@pytest.mark.parametrize("path", ["zero_copy", "staged_graph", "staged_streams", "pageable"])
+@pytest.mark.parametrize("kind", ["ti", "pendulum"])
+def test_solve_host_paths_are_bit_identical(path, kind, monkeypatch):
+    """qpmpc_b200_solve_host with page-locked buffers (zero-copy: the kernel's bulk-TMA staging
+    reads the host buffers itself; or staged in chunks, as a replayed CUDA graph or on streams)
+    and with pageable ones returns exactly the rows of the device entry -- U, status, iterations,
+    multipliers -- also when called again (graph replay) and with operands shared by the batch."""
+    import ctypes
+
+    import torch
+
+    from qpmpc_b200 import _capi
+    from qpmpc_b200.workloads import pendulum_batch, triple_integrator_batch
+
+    B = 20000  # more than one chunk
+    w = triple_integrator_batch(B, seed=19) if kind == "ti" else pendulum_batch(B, seed=20)
+    prob, plan = _solve(w)
+    if path != "zero_copy":
+        monkeypatch.setenv("QPMPC_B200_HOST_ZEROCOPY", "0")
+    if path == "staged_streams":
+        monkeypatch.setenv("QPMPC_B200_HOST_GRAPH", "0")
+    monkeypatch.setenv("QPMPC_B200_HOST_CHUNK", "4096")
+    names = [k for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets") if w[k] is not None]
+
+    def buf(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t if path == "pageable" else t.pin_memory()
+
+    host = {k: buf(w[k]) for k in names}
+    n, m = w["N"] * w["nu"], w["N"] * w["nc"]
+    U, Z = buf(np.zeros((B, n))), buf(np.zeros((B, m)))
+    st, it = buf(np.full(B, -1, dtype=np.int32)), buf(np.zeros(B, dtype=np.int32))
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    ops = _capi.Operands(*[vp(host[k]) if k in host else None for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets")])
+    outs = _capi.Outputs(vp(U), vp(st), vp(it), vp(Z))
+    desc = prob.desc()
+    lib = _capi.load()
+    for rep in range(3):
+        U.zero_()
+        assert lib.qpmpc_b200_solve_host(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), 0) == 0
+        assert torch.equal(U, plan.inputs.reshape(B, n).cpu())
+        assert torch.equal(st, plan.status.cpu()) and torch.equal(it, plan.iters.cpu())
+        assert torch.equal(Z, plan.multipliers.cpu())

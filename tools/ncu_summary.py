@@ -64,7 +64,10 @@ def phase_of(table, fname, line):
 
 def main():
     rep = sys.argv[1]
-    top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 25
+    for a in sys.argv[2:]:
+        if a.startswith("--batch="):  # instances solved by the profiled launch (for per-solve figures)
+            print(f"instances_per_launch {int(a.split('=')[1])}")
     raw = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "raw", "--csv"))))
     hdr, units = raw[0], raw[1]
     for row in raw[2:]:
@@ -86,6 +89,23 @@ def main():
             cur = r[1]
         elif len(r) > 7 and r[0].isdigit() and r[2] == "-":
             lines.append((cur, int(r[0]), int(r[6] or 0), int(r[7] or 0), r[1].strip()))
+    # executed floating-point instructions of the launch, by opcode (SASS rows of the source page):
+    # the flops the kernel really executes, counted by the profiler instead of a model
+    ops = defaultdict(int)
+    for r in src:
+        if len(r) > 7 and r[0] == "" and r[2] not in ("", "-"):
+            try:
+                e = int(r[7])
+            except ValueError:
+                continue
+            op = re.sub(r"^@!?U?P\d+\s+", "", r[3].strip()).split()[0].split(".")[0] if r[3].strip() else "?"
+            ops[op] += e
+    f64 = {k: ops.get(k, 0) for k in ("DFMA", "DMUL", "DADD")}
+    f32 = {k: ops.get(k, 0) for k in ("FFMA", "FMUL", "FADD")}
+    print(f"  fp64 warp instructions executed: " + ", ".join(f"{k} {v}" for k, v in f64.items())
+          + f"  => flops_fp64_per_launch {32 * (2 * f64['DFMA'] + f64['DMUL'] + f64['DADD'])}")
+    print(f"  fp32 warp instructions executed: " + ", ".join(f"{k} {v}" for k, v in f32.items())
+          + f"  => flops_fp32_per_launch {32 * (2 * f32['FFMA'] + f32['FMUL'] + f32['FADD'])}")
     ts = sum(x[2] for x in lines) or 1
     ti = sum(x[3] for x in lines) or 1
     agg = defaultdict(lambda: [0, 0])
