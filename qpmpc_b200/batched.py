@@ -40,6 +40,16 @@ def _require_cuda(device) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
 
+def _device_guard(device):
+    """Context that makes ``device`` current for the launch."""
+    return torch.cuda.device(device)
+
+
+def _stream_ptr(device):
+    """The caller's current CUDA stream on ``device`` as a ``cudaStream_t``."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -262,6 +272,14 @@ class BatchedMPCProblem:
         first = problems[0]
         N = first.nb_timesteps
         packed = [pack_problem(p) for p in problems]
+        for p_, pk in zip(problems, packed):
+            same = (p_.nb_timesteps == N and p_.terminal_cost_weight == first.terminal_cost_weight
+                    and p_.stage_state_cost_weight == first.stage_state_cost_weight
+                    and p_.stage_input_cost_weight == first.stage_input_cost_weight
+                    and pk["row_map"] == packed[0]["row_map"] and pk["nc"] == packed[0]["nc"])
+            if not same:
+                raise ProblemDefinitionError(
+                    "from_problems needs problems with the same horizon, weights and per-step row counts")
 
         def stack(key):
             vals = [pk[key] for pk in packed]
@@ -419,14 +437,18 @@ def solve_mpc_batch(
         raise ProblemDefinitionError(f"unknown method {method!r}")
     desc = problem.desc(meth, max_iter, tol, polish)
     B, n, m = problem.batch_size, problem.nb_vars, problem.nb_rows
-    with torch.cuda.device(problem.device):
+    if out is not None and (tuple(out.shape) != (B, n) or out.dtype != problem.dtype
+                            or out.device != problem.device or not out.is_contiguous()):
+        raise ProblemDefinitionError(
+            f"out must be a contiguous {problem.dtype} tensor of shape {(B, n)} on {problem.device}")
+    with _device_guard(problem.device):
         U = out if out is not None else torch.empty((B, n), dtype=problem.dtype, device=problem.device)
         status = torch.empty(B, dtype=torch.int32, device=problem.device)
         iters = torch.empty(B, dtype=torch.int32, device=problem.device)
         Z = torch.empty((B, m), dtype=problem.dtype, device=problem.device) if return_multipliers else None
         outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), _ptr(Z))
         ops = problem.operands()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        stream = _stream_ptr(problem.device)
         rc = lib.qpmpc_b200_solve(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), stream)
     _capi.check(rc, "qpmpc_b200_solve")
     return BatchedPlan(problem, U, status, iters, Z)
@@ -440,12 +462,12 @@ def condense_batch(problem: BatchedMPCProblem, fields: Sequence[str] = ("P", "q"
     n, m, nx = problem.nb_vars, problem.nb_rows, problem.state_dim
     shapes = dict(P=(B, n, n), q=(B, n), G=(B, m, n), h=(B, m), Phi=(B, N * nx, nx),
                   Psi=(B, N * nx, n), phi_last=(B, nx, nx), psi_last=(B, nx, n))
-    with torch.cuda.device(problem.device):
+    with _device_guard(problem.device):
         out = {k: torch.zeros(shapes[k], dtype=problem.dtype, device=problem.device) for k in fields}
         qf = _capi.QPFields(*[_ptr(out.get(k)) for k in
                               ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")])
         ops = problem.operands()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        stream = _stream_ptr(problem.device)
         rc = lib.qpmpc_b200_condense(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(qf), stream)
     _capi.check(rc, "qpmpc_b200_condense")
     return out
@@ -457,10 +479,10 @@ def integrate_batch(problem: BatchedMPCProblem, inputs: torch.Tensor) -> torch.T
     desc = problem.desc()
     B, N, nx = problem.batch_size, problem.nb_timesteps, problem.state_dim
     U = inputs.reshape(B, -1).to(problem.dtype).contiguous()
-    with torch.cuda.device(problem.device):
+    with _device_guard(problem.device):
         X = torch.empty((B, N + 1, nx), dtype=problem.dtype, device=problem.device)
         ops = problem.operands()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(problem.device).cuda_stream)
+        stream = _stream_ptr(problem.device)
         rc = lib.qpmpc_b200_integrate(ctypes.byref(desc), ctypes.byref(ops), _ptr(U), _ptr(X), stream)
     _capi.check(rc, "qpmpc_b200_integrate")
     return X
@@ -493,7 +515,7 @@ def pendulum_closed_loop(
     dev, dt_ = problem.device, problem.dtype
     if problem.x0 is None or problem.mode_x0 != _capi.VEC_BATCH:
         raise ProblemDefinitionError("per-instance initial states [B, 4] are required")
-    with torch.cuda.device(dev):
+    with _device_guard(dev):
         problem.goal = torch.empty((B, nx), dtype=dt_, device=dev)
         problem.mode_goal = _capi.VEC_BATCH
         problem.targets = torch.empty((B, N * nx), dtype=dt_, device=dev)
@@ -516,7 +538,7 @@ def pendulum_closed_loop(
         loop = _capi.ClosedLoop(int(cycles), int(substeps), sampling_period / substeps,
                                 float(sampling_period), float(length), float(gravity),
                                 _ptr(v), _ptr(traj), _ptr(unsolved))
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        stream = _stream_ptr(dev)
         rc = lib.qpmpc_b200_pendulum_closed_loop(ctypes.byref(desc), ctypes.byref(ops),
                                                  ctypes.byref(outs), ctypes.byref(loop), stream)
     _capi.check(rc, "qpmpc_b200_pendulum_closed_loop")

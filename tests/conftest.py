@@ -81,3 +81,24 @@ def golden_problem(g):
     if g["targets"] is not None:
         prob.update_target_states(g["targets"])
     return prob
+
+
+@pytest.fixture
+def emulated_engine(monkeypatch):
+    """The host-side surface (MPCProblem / MPCQP / solve_mpc / Plan) on a machine without a GPU:
+    the C-ABI entry points it calls are served by the DEVICE SOURCE compiled for the host
+    (tests/emu) on CPU tensors.  Only tests use this seam; the product has no CPU path."""
+    import contextlib
+    import ctypes
+
+    import torch
+
+    import emu
+    from qpmpc_b200 import _capi, batched
+
+    fake = emu.EmulatedLibrary()
+    monkeypatch.setattr(_capi, "load", lambda: fake)
+    monkeypatch.setattr(batched, "_require_cuda", lambda device: torch.device("cpu"))
+    monkeypatch.setattr(batched, "_device_guard", lambda device: contextlib.nullcontext())
+    monkeypatch.setattr(batched, "_stream_ptr", lambda device: ctypes.c_void_p(0))
+    return fake

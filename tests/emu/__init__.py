@@ -191,3 +191,35 @@ def pendulum_closed_loop(w, cycles, substeps=15, length=0.6, gravity=9.81, metho
         rc = lib.emu_pendulum_closed_loop(ctypes.byref(d), ctypes.byref(ops), ctypes.byref(outs), ctypes.byref(loop))
     assert rc == 0, rc
     return traj, int(unsolved[0])
+
+
+class EmulatedLibrary:
+    """Stands in for ``libqpmpc_b200.so`` in CPU tests of the HOST-side surface: the entry points
+    ``qpmpc_b200/batched.py`` calls, served by the device source compiled for the host (this
+    module) on CPU tensors.  Test infrastructure: installed by the ``emulated_engine`` fixture of
+    ``tests/conftest.py`` only; the product never imports it."""
+
+    def __init__(self):
+        self.lib = load()
+        self.calls = 0
+
+    def qpmpc_b200_solve(self, desc, ops, outs, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_solve(desc, ops, outs, 0)
+
+    def qpmpc_b200_condense(self, desc, ops, fields, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_condense(desc, ops, fields)
+
+    def qpmpc_b200_integrate(self, desc, ops, U, X, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_integrate(desc, ops, U, X)
+
+    def qpmpc_b200_strerror(self, code):
+        return f"emulated engine: error {code}".encode()
+
+    def qpmpc_b200_launch_count(self):
+        return self.calls

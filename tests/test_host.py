@@ -295,3 +295,29 @@ def test_product_library_is_not_a_host_emulation_build():
     assert "emu_" not in syms and "pdip_emu" not in syms
     elf = subprocess.run(["cuobjdump", "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
+
+
+def test_batched_front_end_validates_its_arguments(emulated_engine):
+    """``out=`` must match the problem (shape, dtype, device, contiguity); ``from_problems``
+    refuses problems that differ in weights or row pattern (they would silently be solved with
+    the first problem's)."""
+    import torch
+
+    from qpmpc_b200 import BatchedMPCProblem, ProblemDefinitionError, solve_mpc_batch
+    from qpmpc_b200.workloads import to_batched, triple_integrator_batch
+
+    prob = to_batched(triple_integrator_batch(3, seed=2))
+    good = torch.empty((3, 16), dtype=torch.float64)
+    assert solve_mpc_batch(prob, out=good).inputs.data_ptr() == good.data_ptr()
+    for bad in (torch.empty((3, 16), dtype=torch.float32), torch.empty((4, 16), dtype=torch.float64),
+                torch.empty((16, 3), dtype=torch.float64).t()):
+        with pytest.raises(ProblemDefinitionError):
+            solve_mpc_batch(prob, out=bad)
+    a = golden_problem(load_golden("triple_integrator"))
+    b = golden_problem(load_golden("triple_integrator"))
+    b.stage_input_cost_weight = 1e-3
+    with pytest.raises(ProblemDefinitionError):
+        BatchedMPCProblem.from_problems([a, b])
+    both = BatchedMPCProblem.from_problems([a, golden_problem(load_golden("triple_integrator"))])
+    plan = solve_mpc_batch(both)
+    assert torch.equal(plan.inputs[0], plan.inputs[1]) and int(plan.status.sum()) == 0
