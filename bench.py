@@ -393,7 +393,7 @@ def run_b200(args, rank, local_rank, world):
 
     import torch
 
-    from qpmpc_b200 import _capi, pendulum_closed_loop, solve_mpc_batch
+    from qpmpc_b200 import _capi, factor_model, pendulum_closed_loop, solve_mpc_batch
     from qpmpc_b200.workloads import algorithmic_bytes_per_solve, to_batched
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -435,12 +435,18 @@ def run_b200(args, rank, local_rank, world):
     x0_init = torch.as_tensor(w0["x0"]).to(dev) if args.config == 3 else None
     v_dev = torch.as_tensor(w0["v_target"]).to(dev) if args.config == 3 else None
     loop_info = {}
+    # config 3: the model (A, B, D, weights) is shared by the batch and constant over the loop --
+    # factored once (qpmpc_b200_factor), every cycle then only rebuilds q and h.
+    # QPMPC_B200_BENCH_FACTORED=0 re-condenses every instance every cycle instead.
+    model = None
+    if args.config == 3 and os.environ.get("QPMPC_B200_BENCH_FACTORED", "1") != "0":
+        model = factor_model(problems[0])
 
     def step(i):
         if args.config == 3:
             problems[0].x0.copy_(x0_init)
-            plan, _, unsolved = pendulum_closed_loop(problems[0], v_dev, CYCLES)
-            loop_info["unsolved"] = unsolved
+            plan, _, unsolved, stats = pendulum_closed_loop(problems[0], v_dev, CYCLES, factored=model, stats=True)
+            loop_info["unsolved"], loop_info["stats"] = unsolved, stats
             return plan
         if gather is not None:
             U, status, iters = gather.solve(problems[i % rotate])
@@ -519,7 +525,7 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
         kev[0].record()
         for _ in range(50):
-            solve_mpc_batch(problems[0], out=U_out)
+            solve_mpc_batch(problems[0], out=U_out, factored=model)
         kev[1].record()
         torch.cuda.synchronize()
         kernel_ms = kev[0].elapsed_time(kev[1]) / 50
@@ -612,7 +618,7 @@ def run_b200(args, rank, local_rank, world):
         for _ in range(e2e_steps):
             problems[0].x0.copy_(x0_host, non_blocking=True)
             vd.copy_(v_host, non_blocking=True)
-            pendulum_closed_loop(problems[0], vd, CYCLES)
+            pendulum_closed_loop(problems[0], vd, CYCLES, factored=model)
             xf_host.copy_(problems[0].x0, non_blocking=True)
             torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -695,9 +701,21 @@ def run_b200(args, rank, local_rank, world):
     if gather_check is not None:
         line["gather_check"] = gather_check
     if args.config == 3:
-        line["closed_loop"] = {"cycles": CYCLES, "unsolved": int(loop_info["unsolved"].item()),
-                               "upright_frac": float((problems[0].x0[:, 1].abs() < 1.2).float().mean().item()),
-                               "launches_per_step": 2 * CYCLES + 1}
+        hist = loop_info["stats"]["iterations"].cpu().numpy().astype(float) / B
+        useful = int(loop_info["stats"]["upright"].item())
+        line["closed_loop"] = {
+            "cycles": CYCLES, "unsolved": int(loop_info["unsolved"].item()),
+            "upright_frac_final": float((problems[0].x0[:, 1].abs() < 1.2).float().mean().item()),
+            "useful_solves_per_step": useful, "useful_frac": useful / (B * CYCLES),
+            "value_useful_only": value * useful / (B * CYCLES),
+            "note": "useful = (instance, cycle) pairs solved from a state with |pitch| <= 1.2 rad; `value` "
+                    "counts every solve, value_useful_only only those",
+            "mean_iterations_per_cycle": {"cycle_0": hist[0], "cycle_1": hist[1], "cycle_2": hist[2],
+                                          "cycles_3_9": float(hist[3:10].mean()), "cycles_10_49": float(hist[10:50].mean()),
+                                          "cycles_50_199": float(hist[50:].mean())},
+            "model": "factored once (qpmpc_b200_factor), q and h per cycle" if model is not None
+                     else "condensed and factored per instance and cycle",
+            "launches_per_step": 2 * CYCLES + 1}
     if not args.no_cpu_baseline:
         v, threads, sample = cpu_arm(args, sets[0], args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}

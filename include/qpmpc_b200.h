@@ -180,6 +180,26 @@ typedef struct qpmpc_b200_qp_fields {
 int qpmpc_b200_condense(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
                         const qpmpc_b200_qp_fields *out, void *stream);
 
+/* SHARED-MODEL FAST PATH: factor once per model, then per solve only the vectors
+ * change.  The batched form of keeping one MPCQP and calling update_cost_vector /
+ * update_constraint_vector between solves (qpmpc/mpc_qp.py:129-163): when A, B, C, D
+ * are shared by the batch (modes SHARED_LTI / SHARED_LTV, or ABSENT for C, D), the
+ * condensed P and G, the Cholesky factor of P, M = G L^-T and the linear maps
+ * x0, goal, targets -> q and x0 -> h are the same for every instance and every call.
+ *   qpmpc_b200_factor          condenses the model (batch is ignored; in->x0 only has to
+ *                              be valid) and writes the record: `record` is a device
+ *                              buffer of qpmpc_b200_factor_bytes(desc) bytes.
+ *   qpmpc_b200_solve_factored  solves desc->batch instances that share the record: only
+ *                              e, x0, goal, targets are read from `in` (same modes,
+ *                              weights and dimensions as at factor time).
+ * Needs desc->paired rows with nc even, N*nu <= 32 and N*nc <= 64, and the default
+ * method; QPMPC_B200_EUNSUPPORTED otherwise (qpmpc_b200_factor_bytes returns 0). */
+size_t qpmpc_b200_factor_bytes(const qpmpc_b200_desc *desc);
+int qpmpc_b200_factor(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in, void *record,
+                      void *stream);
+int qpmpc_b200_solve_factored(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                              const void *record, const qpmpc_b200_outputs *out, void *stream);
+
 /* X[b, k+1] = A_k X[b, k] + B_k U[b, k], X[b, 0] = x0[b]; X is [batch, N+1, nx].
  * Replaces MPCProblem.integrate (qpmpc/mpc_problem.py:316-335).  Uses
  * desc->mode_A/B/x0, in->A/B/x0; U is [batch, N*nu]. */
@@ -208,6 +228,13 @@ typedef struct qpmpc_b200_closed_loop {
     const void *v_target;    /* [batch] target ground velocity, dtype of desc */
     void *trajectory;        /* optional [cycles + 1, batch, 4] states after each cycle */
     int32_t *unsolved;       /* optional device counter, incremented per missing plan */
+    const void *record;      /* optional: record of qpmpc_b200_factor for this model -- every
+                                cycle then runs qpmpc_b200_solve_factored (the model is
+                                condensed and factored once instead of batch x cycles times) */
+    int32_t *upright;        /* optional device counter: (instance, cycle) pairs whose pitch
+                                was within +-1.2 rad when the cycle's MPC was solved */
+    int64_t *iterations;     /* optional [cycles] device array: solver iterations summed over
+                                the batch, per cycle (needs out->iters) */
 } qpmpc_b200_closed_loop;
 
 int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,

@@ -23,7 +23,9 @@ __version__ = "0.1.0"
 from .batched import (  # noqa: E402
     BatchedMPCProblem,
     BatchedPlan,
+    FactoredModel,
     condense_batch,
+    factor_model,
     integrate_batch,
     pendulum_closed_loop,
     problem_to_batch,
@@ -33,8 +35,8 @@ from .mpc_qp import MPCQP  # noqa: E402
 from .solve_mpc import solve_mpc  # noqa: E402  (rebinds the name from module to function)
 
 __all__ = [
-    "BackendError", "BatchedMPCProblem", "BatchedPlan", "MPCProblem", "MPCQP",
+    "BackendError", "BatchedMPCProblem", "BatchedPlan", "FactoredModel", "MPCProblem", "MPCQP",
     "Plan", "PlanError", "ProblemDefinitionError", "QPMPCException", "QPProblem",
-    "Solution", "StateError", "condense_batch", "integrate_batch", "pendulum_closed_loop",
+    "Solution", "StateError", "condense_batch", "factor_model", "integrate_batch", "pendulum_closed_loop",
     "solve_mpc", "solve_mpc_batch",
 ]

@@ -25,7 +25,8 @@ EXPORTS = (
     "qpmpc_b200_integrate", "qpmpc_b200_workspace_bytes", "qpmpc_b200_max_vars",
     "qpmpc_b200_max_rows", "qpmpc_b200_launch_count", "qpmpc_b200_strerror",
     "qpmpc_b200_version", "qpmpc_b200_fp64_peak", "qpmpc_b200_pendulum_closed_loop",
-    "qpmpc_b200_solve_scatter",
+    "qpmpc_b200_solve_scatter", "qpmpc_b200_factor_bytes", "qpmpc_b200_factor",
+    "qpmpc_b200_solve_factored",
 )
 
 
@@ -87,7 +88,8 @@ class ClosedLoop(ctypes.Structure):
         ("dt", ctypes.c_double), ("sampling_period", ctypes.c_double),
         ("length", ctypes.c_double), ("gravity", ctypes.c_double),
         ("v_target", ctypes.c_void_p), ("trajectory", ctypes.c_void_p),
-        ("unsolved", ctypes.c_void_p),
+        ("unsolved", ctypes.c_void_p), ("record", ctypes.c_void_p),
+        ("upright", ctypes.c_void_p), ("iterations", ctypes.c_void_p),
     ]
 
 
@@ -115,7 +117,11 @@ def load():
         P(Desc), P(Operands), P(Outputs), P(ClosedLoop), ctypes.c_void_p]
     lib.qpmpc_b200_solve_scatter.argtypes = [
         P(Desc), P(Operands), P(Outputs), P(Peers), ctypes.c_void_p]
-    for name in ("solve", "solve_host", "condense", "integrate", "version",
+    lib.qpmpc_b200_factor_bytes.argtypes = [P(Desc)]
+    lib.qpmpc_b200_factor_bytes.restype = ctypes.c_size_t
+    lib.qpmpc_b200_factor.argtypes = [P(Desc), P(Operands), ctypes.c_void_p, ctypes.c_void_p]
+    lib.qpmpc_b200_solve_factored.argtypes = [P(Desc), P(Operands), ctypes.c_void_p, P(Outputs), ctypes.c_void_p]
+    for name in ("solve", "solve_host", "condense", "integrate", "version", "factor", "solve_factored",
                  "max_vars", "max_rows", "pendulum_closed_loop", "solve_scatter"):
         getattr(lib, f"qpmpc_b200_{name}").restype = ctypes.c_int
     lib.qpmpc_b200_max_vars.argtypes = [ctypes.c_int]

@@ -414,6 +414,43 @@ class BatchedPlan:
         return self._states
 
 
+class FactoredModel:
+    """The record of :func:`factor_model`: everything of the condensed QP that does not depend
+    on the initial / goal / target states, computed once for a model shared by the batch --
+    the batched counterpart of keeping one ``MPCQP`` and only calling ``update_cost_vector`` /
+    ``update_constraint_vector`` between solves (``qpmpc/mpc_qp.py:129-163``).  Valid as long as
+    A, B, C, D, the weights and the presence of goal / targets stay as they were."""
+
+    def __init__(self, record: torch.Tensor, signature):
+        self.record = record
+        self.signature = signature
+
+
+def _model_signature(problem: "BatchedMPCProblem"):
+    return (problem.nb_timesteps, problem.state_dim, problem.input_dim, problem.ineq_dim, problem.dtype,
+            problem.terminal_cost_weight, problem.stage_state_cost_weight, problem.stage_input_cost_weight,
+            problem.mode_A, problem.mode_B, problem.mode_C, problem.mode_D,
+            problem.mode_goal != _capi.VEC_ABSENT, problem.mode_targets != _capi.VEC_ABSENT,
+            *(None if t is None else t.data_ptr() for t in (problem.A, problem.B, problem.C, problem.D)))
+
+
+def factor_model(problem: BatchedMPCProblem) -> FactoredModel:
+    """Condense and factor the model of ``problem`` once (``qpmpc_b200_factor``).  Needs A, B, C,
+    D shared by the batch and paired constraint rows; raises ``BackendError`` otherwise."""
+    lib = _capi.load()
+    desc = problem.desc()
+    nbytes = int(lib.qpmpc_b200_factor_bytes(ctypes.byref(desc)))
+    if nbytes == 0:
+        raise BackendError("the shared-model fast path needs A, B, C, D shared by the batch, paired "
+                           "constraint rows and N*nu <= 32")
+    with _device_guard(problem.device):
+        record = torch.empty(nbytes // problem.x0.element_size(), dtype=problem.dtype, device=problem.device)
+        ops = problem.operands()
+        rc = lib.qpmpc_b200_factor(ctypes.byref(desc), ctypes.byref(ops), _ptr(record), _stream_ptr(problem.device))
+    _capi.check(rc, "qpmpc_b200_factor")
+    return FactoredModel(record, _model_signature(problem))
+
+
 def solve_mpc_batch(
     problem: BatchedMPCProblem,
     method: str = "active_set",
@@ -422,9 +459,12 @@ def solve_mpc_batch(
     return_multipliers: bool = False,
     out: Optional[torch.Tensor] = None,
     polish: bool = True,
+    factored: Optional[FactoredModel] = None,
 ) -> BatchedPlan:
     """Condense and solve every instance of ``problem`` on its CUDA device.
 
+    ``factored`` (a :class:`FactoredModel` of this problem's shared model) skips condensing
+    and factoring: only q and h are rebuilt per instance.
     ``method="active_set"`` (default) is the exact Goldfarb-Idnani kernel;
     ``method="pdip"`` the Mehrotra interior-point kernel stopped at ``tol``
     (default 1e-9), followed by an active-set ``polish`` -- the role a
@@ -449,8 +489,15 @@ def solve_mpc_batch(
         outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), _ptr(Z))
         ops = problem.operands()
         stream = _stream_ptr(problem.device)
-        rc = lib.qpmpc_b200_solve(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), stream)
-    _capi.check(rc, "qpmpc_b200_solve")
+        if factored is not None:
+            if factored.signature != _model_signature(problem):
+                raise ProblemDefinitionError("the factored model belongs to another problem (model, weights or "
+                                             "presence of goal / targets changed): call factor_model again")
+            rc = lib.qpmpc_b200_solve_factored(ctypes.byref(desc), ctypes.byref(ops), _ptr(factored.record),
+                                               ctypes.byref(outs), stream)
+        else:
+            rc = lib.qpmpc_b200_solve(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs), stream)
+    _capi.check(rc, "qpmpc_b200_solve_factored" if factored is not None else "qpmpc_b200_solve")
     return BatchedPlan(problem, U, status, iters, Z)
 
 
@@ -497,6 +544,8 @@ def pendulum_closed_loop(
     gravity: float = 9.81,
     sampling_period: float = 0.1,
     record: bool = False,
+    factored: Optional[FactoredModel] = None,
+    stats: bool = False,
 ):
     """Receding-horizon closed loop of the wheeled inverted pendulum on the
     device (``examples/wheeled_inverted_pendulum.py:99-118``, batched): per
@@ -505,8 +554,13 @@ def pendulum_closed_loop(
     under the first input.  ``problem.x0`` is the state and is updated in
     place; goal / targets are (re)allocated per instance.
 
+    ``factored``: the model's :func:`factor_model` record (goal and targets must be present in
+    the problem it was made from); every cycle then only rebuilds q and h.
+
     Returns ``(plan_of_last_cycle, trajectory or None, unsolved_count_tensor)``;
-    trajectory is [cycles + 1, B, 4].  Asynchronous on the current stream.
+    trajectory is [cycles + 1, B, 4].  With ``stats`` a fourth value: dict(upright = device
+    counter of (instance, cycle) pairs solved with |pitch| <= 1.2 rad, iterations = [cycles]
+    solver iterations summed over the batch).  Asynchronous on the current stream.
     """
     lib = _capi.load()
     B, N, nx = problem.batch_size, problem.nb_timesteps, problem.state_dim
@@ -532,14 +586,22 @@ def pendulum_closed_loop(
         iters = torch.zeros(B, dtype=torch.int32, device=dev)
         traj = torch.empty((cycles + 1, B, nx), dtype=dt_, device=dev) if record else None
         unsolved = torch.zeros(1, dtype=torch.int32, device=dev)
+        upright = torch.zeros(1, dtype=torch.int32, device=dev) if stats else None
+        iter_hist = torch.zeros(max(cycles, 1), dtype=torch.int64, device=dev) if stats else None
+        if factored is not None and factored.signature != _model_signature(problem):
+            raise ProblemDefinitionError("the factored model belongs to another problem")
         desc = problem.desc()
         ops = problem.operands()
         outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), None)
         loop = _capi.ClosedLoop(int(cycles), int(substeps), sampling_period / substeps,
                                 float(sampling_period), float(length), float(gravity),
-                                _ptr(v), _ptr(traj), _ptr(unsolved))
+                                _ptr(v), _ptr(traj), _ptr(unsolved),
+                                _ptr(factored.record) if factored is not None else None,
+                                _ptr(upright), _ptr(iter_hist))
         stream = _stream_ptr(dev)
         rc = lib.qpmpc_b200_pendulum_closed_loop(ctypes.byref(desc), ctypes.byref(ops),
                                                  ctypes.byref(outs), ctypes.byref(loop), stream)
     _capi.check(rc, "qpmpc_b200_pendulum_closed_loop")
+    if stats:
+        return BatchedPlan(problem, U, status, iters), traj, unsolved, dict(upright=upright, iterations=iter_hist)
     return BatchedPlan(problem, U, status, iters), traj, unsolved

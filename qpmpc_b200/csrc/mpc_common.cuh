@@ -56,6 +56,8 @@ struct SolveParams {
     int *peer_status[8];
     // condensed-field dump (condense kernel only)
     void *P, *q, *G, *h, *Phi, *Psi, *phi_last, *psi_last;
+    // shared-model fast path (mpc_factor.cuh): the record of the model, staged once per CTA
+    const void *record;
 };
 
 template <typename T> struct Pair;

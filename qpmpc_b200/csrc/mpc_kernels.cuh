@@ -30,6 +30,7 @@
 #pragma once
 
 #include "mpc_common.cuh"
+#include "mpc_factor.cuh"  // FactorLay: the record of the shared-model fast path (PRE)
 
 // Resident CTAs of 128 threads per SM the register-resident variants are
 // compiled for (caps registers per thread at 65536 / (128 * QPMPC_MINB)).
@@ -54,7 +55,9 @@ namespace qpmpc {
 // PAIRED: the constraint rows come in pairs [G+; -G+] (two-sided bounds, desc.paired): only the
 // MR * NP rows G+ are kept (as rows of M), each standing for both of its signs; h and a dense G
 // (time-varying models) still hold all 2 MR NP rows.
-template <typename T, int NP, int MR, bool MREG, bool RS = false, bool PAIRED = false>
+// PRE: shared-model fast path (mpc_factor.cuh): L, M, G come from the record of the model, the
+// per-instance region keeps only h, R^-1 and the small vectors.
+template <typename T, int NP, int MR, bool MREG, bool RS = false, bool PAIRED = false, bool PRE = false>
 struct Lay {
     static constexpr int MP = MR * NP;     // padded (stored) constraint rows
     static constexpr int HP = PAIRED ? 2 * MP : MP;  // padded rows of h and of the dense G
@@ -63,7 +66,7 @@ struct Lay {
     static constexpr int szG = ((NP * LDG + 3) / 4) * 4;
     static constexpr int oH = 0;           // hs[HP]
     static constexpr int oRL = oH + HP;    // psi exchange (A), Lc (B and, if MREG, the final solve)
-    static constexpr int szRL = ((NP * LDL + 3) / 4) * 4;
+    static constexpr int szRL = PRE ? 0 : ((NP * LDL + 3) / 4) * 4;
     // R^-1 by columns: its own region when L must survive (MREG), else over L
     static constexpr int oRi = MREG ? oRL + szRL : oRL;
     static constexpr int oV = oRL + szRL + (MREG ? NP * NP : 0);  // qs, xs, dv, dd, d2 [NP each], sc[8]
@@ -73,9 +76,10 @@ struct Lay {
     static constexpr bool ROWS_IN_SMEM = RS;
     static constexpr int oW = oV + szV;
     static constexpr int fixed = oW + (ROWS_IN_SMEM ? 3 * MP : 0);  // runtime-sized tail follows (TailLay)
-    static_assert(NP * NP <= szRL, "R^-1 must fit in the L region");
-    static_assert(8 * NP <= szRL, "psi exchange buffers must fit in the L region");
+    static_assert(PRE || NP * NP <= szRL, "R^-1 must fit in the L region");
+    static_assert(PRE || 8 * NP <= szRL, "psi exchange buffers must fit in the L region");
     static_assert(!PAIRED || (MREG && !RS), "paired rows: register-resident M, row constants in registers");
+    static_assert(!PRE || (PAIRED && MR == 1), "shared-model fast path: paired rows, one stored row per lane");
 };
 
 // Scratch of the generic (any nx) condensing: psi[2][nx][NP], xbar[2][nx],
@@ -657,12 +661,12 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     shared memory, row l of J is kept in registers and x moves with every
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
-template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false>  // @phase kernel prologue
+template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false, bool PRE = false>  // @phase kernel prologue
 __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
                                            ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : (PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
                                            : 1)
     mpc_solve_kernel(const SolveParams p) {
-    using L = Lay<T, NP, MR, MREG, RS, PAIRED>;
+    using L = Lay<T, NP, MR, MREG, RS, PAIRED, PRE>;
     using T2 = typename Pair<T>::type;
     constexpr bool HASJ = !MREG;
     constexpr int IPW = 32 / NP;  // instances per warp
@@ -709,22 +713,57 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
         in[o] = v.ptr ? inbase + v.smem_off + (v.per_instance ? (valid ? iic : 0) * v.sz : 0) : nullptr;
     }
 
+    // ---- shared-model fast path: the record of the model, once per CTA -------  // @phase PRE record
+    const FactorLay F = factor_layout(NP, p.nx, p.N, p.q_wx != 0);
+    const T *rec = inbase + p.input_elems;
+    if (PRE) {
+        const T *src = static_cast<const T *>(p.record);
+        T *dst = inbase + p.input_elems;
+        for (int i = threadIdx.x; i < F.total / 2; i += blockDim.x)
+            reinterpret_cast<T2 *>(dst)[i] = reinterpret_cast<const T2 *>(src)[i];
+        __syncthreads();
+    }
+
     // ---- phase A -----------------------------------------------------------
-    T Prow[NP];
+    T Prow[PRE ? 1 : NP];
     T qj;
+    bool spd = true;
+    if constexpr (!PRE) {
     // prefix-sum table of the stage-cost Hessian: any NP x NP scratch that is free before phase B
     // (the condensing code sizes G by its second integer parameter: all 2 MR NP rows when paired)
     condense_dispatch<T, NP, PAIRED ? 2 * MR : MR, false>(p, in, Gc, gt, hs, Lc, MREG ? Ri : Gc, wk + p.scr_off, l,
                                                           Prow, qj, inst, valid);
+    } else {
+        // q = Fx x0 - Fg goal - Ft targets (update_cost_vector, mpc_qp.py:139-149, as linear maps)
+        T a0 = T(0), a1 = T(0);
+        for (int t = 0; t < p.nx; ++t) {
+            a0 += rec[F.oFx + t * NP + l] * in[OP_X0][t];
+            if (p.q_wt) a1 += rec[F.oFg + t * NP + l] * in[OP_GOAL][t];
+        }
+        if (p.q_wx) {
+            const T *tg = in[OP_TGT];
+            const int cnt = p.N * p.nx;
+            T b0 = T(0), b1 = T(0);
+            int j = 0;
+            for (; j + 1 < cnt; j += 2) {
+                b0 += rec[F.oFt + j * NP + l] * tg[j];
+                b1 += rec[F.oFt + (j + 1) * NP + l] * tg[j + 1];
+            }
+            if (j < cnt) b0 += rec[F.oFt + j * NP + l] * tg[j];
+            a1 += b0 + b1;
+        }
+        qj = a0 - a1;
+        spd = rec[F.oDv + l] > T(0);  // NaN if the model's Hessian is not positive definite
+    }
 
     // ---- phase B: Cholesky, row l of L in Prow, columns published in Lc -----  // @phase B cholesky
-    bool spd = true;
     qs[l] = qj;
     // Shared vectors start finite: lanes of finished instances keep computing
     // with them (their results are multiplied by a zero step).
     dd[l] = T(0);
     d2[l] = T(0);
     if (l < 2) sc[l] = T(0);
+    if constexpr (!PRE) {
 #pragma unroll
     for (int c = 0; c < NP; ++c) {
         const T piv = __shfl_sync(FULL_MASK, Prow[c], c, NP);
@@ -741,6 +780,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
             Prow[i] -= lc * v.x;
             Prow[i + 1] -= lc * v.y;
         }
+    }
     }
 
     // Forward substitutions with L, lane-local.  t = L^-1 q always; row l of
@@ -767,7 +807,44 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
         return RS ? rowc_s[which * L::MP + l + s * NP] : rowc[RS ? 0 : which][RS ? 0 : s];
     };
     bool rowvalid[MR];
-    {
+    if constexpr (PRE) {  // @phase PRE vectors
+        // t = L^-1 q by the explicit inverse of the record, h = e -/+ Hx x0 for the pair of this
+        // lane's stored row (update_constraint_vector, mpc_qp.py:161-163), its row of M and the
+        // violations -M t - h; nothing else is per instance
+        __syncwarp();
+        T t0 = T(0), t1 = T(0);
+#pragma unroll
+        for (int k = 0; k < NP; k += 2) {
+            const T2 v = *reinterpret_cast<const T2 *>(qs + k);
+            t0 += rec[F.oLinv + k * NP + l] * v.x;
+            t1 += rec[F.oLinv + (k + 1) * NP + l] * v.y;
+        }
+        xs[l] = t0 + t1;
+        __syncwarp();
+        const int srow = l;
+        rowvalid[0] = srow < (m >> 1);
+        const int rk = rowvalid[0] ? srow / half : 0, rr = rowvalid[0] ? srow - rk * half : 0;
+        T hx = T(0);
+        for (int t = 0; t < p.nx; ++t) hx += rec[F.oHx + t * NP + srow] * in[OP_X0][t];
+        const T *ek = in[OP_E] + rk * p.op[OP_E].step;
+        const T hp = rowvalid[0] ? ek[rr] - hx : T(0), hm = rowvalid[0] ? ek[rr + half] + hx : T(0);
+        cen[0] = rowvalid[0] ? T(0.5) * (hp - hm) : T(0);
+        wid[0] = rowvalid[0] ? T(0.5) * (hp + hm) : T(1);
+        T v0 = T(0), v1 = T(0);
+#pragma unroll
+        for (int c = 0; c < NP; c += 2) {
+            const T2 tv = *reinterpret_cast<const T2 *>(xs + c);
+            const T ma = rec[F.oM + c * NP + srow], mb = rec[F.oM + (c + 1) * NP + srow];
+            Mrow[0][c] = ma;
+            Mrow[0][c + 1] = mb;
+            v0 += ma * tv.x;
+            v1 += mb * tv.y;
+        }
+        viol[0] = rowvalid[0] ? -(v0 + v1) : T(0);
+        rc_set(0, 0, Num<T>::viol_eps * (fmax(T(1), fmax(abs_(hp), abs_(hm))) + rec[F.oRowc + srow]));
+        rc_set(1, 0, rowvalid[0] ? rec[F.oRowc + NP + srow] : T(1e30));
+        rc_set(2, 0, rec[F.oRowc + 2 * NP + srow]);
+    } else {
         T tq[NP];
 #pragma unroll
         for (int c = 0; c < NP; c += 2) {
@@ -1273,20 +1350,21 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
                         const T *Dk = in[OP_D] ? in[OP_D] + ki * p.op[OP_D].step : nullptr;
                         g = g_toeplitz<T>(gt, Dk, n, p.nu, ki, ri, l);
                     } else {
-                        g = Gc[l * L::LDG + ai];
+                        g = (PRE ? rec + F.oG : Gc)[l * L::LDG + ai];
                     }
                     w += li * g;
                 }
             }
         }
         // forward: L y = w, lane c finalises y_c and broadcasts it
-        const T dinv = dv[l];
+        const T *Lfin = PRE ? rec + F.oL : Lc, *dvfin = PRE ? rec + F.oDv : dv;  // the model's factor
+        const T dinv = dvfin[l];
         T y = T(0);
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
             const T yc = __shfl_sync(FULL_MASK, w * dinv, c, NP);
             if (l == c) y = yc;
-            if (l > c) w -= Lc[c * L::LDL + l] * yc;
+            if (l > c) w -= Lfin[c * L::LDL + l] * yc;
         }
         // backward: L' x = -y
         T s2 = -y;
@@ -1294,7 +1372,7 @@ __global__ void __launch_bounds__(256, (NP <= 16 && MREG)
         for (int c = NP - 1; c >= 0; --c) {
             const T xc = __shfl_sync(FULL_MASK, s2 * dinv, c, NP);
             if (l == c) x = xc;
-            if (l < c) s2 -= Lc[l * L::LDL + c] * xc;
+            if (l < c) s2 -= Lfin[l * L::LDL + c] * xc;
         }
     }
 

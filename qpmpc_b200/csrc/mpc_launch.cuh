@@ -21,6 +21,8 @@ template <typename T, int NP, int MR>
 int launch_condense(SolveParams p, cudaStream_t stream);
 template <typename T, int NP>  // structure-exploiting kernel for terminal-cost problems (mpc_lr_kernel.cuh)
 int launch_solve_lr(SolveParams p, cudaStream_t stream);
+template <typename T, int NP>  // shared-model fast path (mpc_factor.cuh): p.record holds the model's factor
+int launch_solve_pre(SolveParams p, cudaStream_t stream);
 template <typename T, int NP, int MR>
 int launch_pdip(SolveParams p, int polish, cudaStream_t stream);  // mpc_pdip.cuh
 
@@ -76,6 +78,47 @@ int launch_solve(SolveParams p, cudaStream_t stream) {
 template <typename T, int NP>
 int launch_solve_paired(SolveParams p, cudaStream_t stream) {
     return launch_solve_variant<T, NP, 1, true, false, true>(p, stream);
+}
+
+// Shared-model fast path: per-instance region = Lay<PRE>::fixed, then the CTA's inputs (only the
+// operands that still vary per solve: e, x0, goal, targets), then the record of the model.
+template <typename T, int NP>
+int launch_solve_pre(SolveParams p, cudaStream_t stream) {
+    using L = Lay<T, NP, 1, true, false, true, true>;
+    constexpr int IPW = 32 / NP;
+    for (int o : {OP_A, OP_B, OP_C, OP_D}) p.op[o] = OperandView{nullptr, 0, 0, 0, 0};  // in the record
+    p.toeplitz = 0;
+    p.inst_stride = (L::fixed + 3) / 4 * 4;
+    p.gt_off = p.g_off = p.scr_off = 0;
+    const FactorLay F = factor_layout(NP, p.nx, p.N, p.q_wx != 0);
+    int wpc = env_int("QPMPC_B200_WPC", 8);
+    wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+    size_t smem = 0;
+    for (;; --wpc) {
+        const int ipc = IPW * wpc;
+        int off = 0;
+        p.present_mask = 0;
+        for (int o = 0; o < OP_COUNT; ++o) {
+            OperandView &v = p.op[o];
+            if (!v.ptr) continue;
+            p.present_mask |= 1 << o;
+            v.smem_off = off;
+            off += (v.sz * (v.per_instance ? ipc : 1) + 3) / 4 * 4;
+        }
+        p.input_elems = off;
+        smem = 16 + ((size_t)ipc * p.inst_stride + off + F.total) * sizeof(T);
+        if (smem <= 227 * 1024 || wpc == 1) break;
+    }
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    const int ipc = IPW * wpc;
+    auto kern = mpc_solve_kernel<T, NP, 1, true, false, true, true>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (p.batch + ipc - 1) / ipc;
+    if (grid == 0) return 0;
+    kern<<<grid, wpc * 32, smem, stream>>>(p);
+    count_launch();
+    return (int)cudaGetLastError();
 }
 
 template <typename T, int NP, int MR>
@@ -150,7 +193,9 @@ int launch_pdip(SolveParams p, int polish, cudaStream_t stream) {
 #define QPMPC_INSTANTIATE_VARIANT(T, NP, MR, MREG)                               \
     template int launch_solve<T, NP, MR, MREG>(SolveParams, cudaStream_t);      \
     template int launch_condense<T, NP, MR>(SolveParams, cudaStream_t);
-#define QPMPC_INSTANTIATE_PAIRED(T, NP) template int launch_solve_paired<T, NP>(SolveParams, cudaStream_t);
+#define QPMPC_INSTANTIATE_PAIRED(T, NP)                                         \
+    template int launch_solve_paired<T, NP>(SolveParams, cudaStream_t);         \
+    template int launch_solve_pre<T, NP>(SolveParams, cudaStream_t);
 // the interior-point kernel is double precision only (qpmpc_b200.cu:solve_impl)
 #define QPMPC_INSTANTIATE_PDIP(NP, MR) template int launch_pdip<double, NP, MR>(SolveParams, int, cudaStream_t);
 

@@ -26,6 +26,9 @@ struct PendulumStepParams {
     void *targets;        // [batch, N * 4] out
     void *traj;           // optional [batch, 4] slot of the recorded trajectory
     int *unsolved;        // optional counter of (instance, cycle) pairs without a plan
+    int *upright;         // optional counter of (instance, cycle) pairs solved with |pitch| <= 1.2 rad
+    const int *iters;     // optional [batch] solver iterations of the cycle that just ended ...
+    long long *iter_sum;  // ... summed over the batch into this slot
 };
 
 template <typename T>
@@ -38,6 +41,10 @@ __global__ void __launch_bounds__(128) pendulum_step_kernel(const PendulumStepPa
         const bool ok = p.status[b] == 0;
         const T u = ok ? static_cast<const T *>(p.U)[(size_t)b * p.n] : T(0);
         if (!ok && p.unsolved) atomicAdd(p.unsolved, 1);
+        // the MPC of this cycle was solved from the state before the plant moves
+        if (p.upright && abs_(th) <= T(1.2)) atomicAdd(p.upright, 1);
+        if (p.iter_sum && p.iters) atomicAdd(reinterpret_cast<unsigned long long *>(p.iter_sum),
+                                             (unsigned long long)p.iters[b]);
         const T dt = (T)p.dt, w2 = (T)p.omega2, g = (T)p.g;
         for (int s = 0; s < p.substeps; ++s) {
             // second-order Taylor step of the nonlinear dynamics (systems/...:150-160)

@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "mpc_cta_kernel.cuh"
+#include "mpc_factor.cuh"
 #include "mpc_host_params.h"
 #include "mpc_integrate.cuh"
 #include "mpc_launch.cuh"
@@ -367,6 +368,102 @@ int qpmpc_b200_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in,
     return d->dtype == QPMPC_B200_F64 ? dispatch_condense<double>(p, v, s) : dispatch_condense<float>(p, v, s);
 }
 
+// ---- shared-model fast path (mpc_factor.cuh) ----------------------------------------------
+namespace {
+bool shared_mode(int mode, bool optional) {
+    return mode == QPMPC_B200_SHARED_LTI || mode == QPMPC_B200_SHARED_LTV || (optional && mode == QPMPC_B200_ABSENT);
+}
+// NP of the paired variant that serves the factored path, 0 if the problem does not qualify.
+int factor_np(const qpmpc_b200_desc *d) {
+    if (!d || d->N <= 0 || d->nx <= 0 || d->nu <= 0 || d->nc <= 0 || !rows_paired(d)) return 0;
+    if (!shared_mode(d->mode_A, false) || !shared_mode(d->mode_B, false) || !shared_mode(d->mode_C, true) ||
+        !shared_mode(d->mode_D, true) || d->method != QPMPC_B200_ACTIVE_SET)
+        return 0;
+    Variant v;
+    if (!pick_variant(d->N * d->nu, d->N * d->nc, &v, true) || !v.paired) return 0;
+    return v.np;
+}
+// scratch behind the record: the condensed fields of the model (P, G, Phi, Psi, phi_N, psi_N)
+size_t factor_scratch_elems(const qpmpc_b200_desc *d) {
+    const size_t n = (size_t)d->N * d->nu, m = (size_t)d->N * d->nc, nx = d->nx, N = d->N;
+    return n * n + m * n + N * nx * nx + N * nx * n + nx * nx + nx * n + 16;
+}
+bool factor_has_ft(const qpmpc_b200_desc *d) {
+    return d->has_wx && d->w_x > 1e-10 && d->mode_targets != QPMPC_B200_VEC_ABSENT &&
+           !(d->has_wt && d->w_t > 1e-10 && d->mode_goal == QPMPC_B200_VEC_ABSENT);
+}
+}  // namespace
+
+size_t qpmpc_b200_factor_bytes(const qpmpc_b200_desc *d) {
+    const int np = factor_np(d);
+    if (!np) return 0;
+    const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
+    return ((size_t)factor_layout(np, d->nx, d->N, factor_has_ft(d)).total + factor_scratch_elems(d)) * es;
+}
+
+int qpmpc_b200_factor(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, void *record, void *stream) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!record) return QPMPC_B200_EINVAL;
+    const int np = factor_np(d);
+    if (!np) return QPMPC_B200_EUNSUPPORTED;
+    const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
+    const FactorLay F = factor_layout(np, d->nx, d->N, factor_has_ft(d));
+    const size_t n = (size_t)d->N * d->nu, m = (size_t)d->N * d->nc, nx = d->nx, N = d->N;
+    // the model's MPCQP fields (one instance), into the scratch behind the record
+    char *scr = static_cast<char *>(record) + (size_t)F.total * es;
+    qpmpc_b200_qp_fields f;
+    f.P = scr, scr += n * n * es;
+    f.G = scr, scr += m * n * es;
+    f.Phi = scr, scr += N * nx * nx * es;
+    f.Psi = scr, scr += N * nx * n * es;
+    f.phi_last = scr, scr += nx * nx * es;
+    f.psi_last = scr;
+    f.q = f.h = nullptr;
+    qpmpc_b200_desc d1 = *d;
+    d1.batch = 1;
+    if ((rc = qpmpc_b200_condense(&d1, in, &f, stream)) != 0) return rc;
+    SolveParams sp;
+    fill_params(d, in, &sp);
+    FactorParams fp;
+    fp.N = d->N, fp.nx = d->nx, fp.nu = d->nu, fp.nc = d->nc, fp.n = (int)n, fp.m = (int)m, fp.NP = np;
+    fp.has_ft = sp.q_wx, fp.q_wt = sp.q_wt, fp.q_wx = sp.q_wx;
+    fp.w_t = sp.w_t, fp.w_x = sp.w_x;
+    fp.P = f.P, fp.G = f.G, fp.Phi = f.Phi, fp.Psi = f.Psi, fp.phi_last = f.phi_last, fp.psi_last = f.psi_last;
+    fp.C = d->mode_C == QPMPC_B200_ABSENT ? nullptr : in->C;
+    fp.stepC = sp.op[OP_C].step;
+    fp.record = record;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d->dtype == QPMPC_B200_F64)
+        mpc_factor_kernel<double><<<1, 128, FACTOR_SMEM_BYTES, s>>>(fp);
+    else
+        mpc_factor_kernel<float><<<1, 128, FACTOR_SMEM_BYTES, s>>>(fp);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int qpmpc_b200_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                              const qpmpc_b200_outputs *out, void *stream) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    if (!record || !out || !out->U || !out->status) return QPMPC_B200_EINVAL;
+    const int np = factor_np(d);
+    if (!np) return QPMPC_B200_EUNSUPPORTED;
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.U = out->U;
+    p.status = out->status;
+    p.iters = out->iters;
+    p.Z = out->Z;
+    p.record = record;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool f64 = d->dtype == QPMPC_B200_F64;
+    if (np == 8) return f64 ? launch_solve_pre<double, 8>(p, s) : launch_solve_pre<float, 8>(p, s);
+    if (np == 16) return f64 ? launch_solve_pre<double, 16>(p, s) : launch_solve_pre<float, 16>(p, s);
+    return f64 ? launch_solve_pre<double, 32>(p, s) : launch_solve_pre<float, 32>(p, s);
+}
+
 int qpmpc_b200_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *U, void *X,
                          void *stream) {
     if (!d || !in || !U || !X || !in->A || !in->B || !in->x0) return QPMPC_B200_EINVAL;
@@ -428,10 +525,14 @@ int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_o
     pp.goal = const_cast<void *>(in->goal);
     pp.targets = const_cast<void *>(in->targets);
     pp.unsolved = loop->unsolved;
+    pp.upright = loop->upright;
+    pp.iters = out->iters;
+    pp.iter_sum = nullptr;
     const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
     const int threads = 128, grid = (d->batch + threads - 1) / threads;
     auto step = [&](int substeps, int slot) {
         pp.substeps = substeps;
+        pp.iter_sum = (loop->iterations && out->iters && slot > 0) ? reinterpret_cast<long long *>(loop->iterations) + (slot - 1) : nullptr;
         pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 4 * es : nullptr;
         if (d->dtype == QPMPC_B200_F64)
             pendulum_step_kernel<double><<<grid, threads, 0, s>>>(pp);
@@ -441,7 +542,8 @@ int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_o
     };
     step(0, 0);  // targets of the first cycle from the initial state
     for (int c = 0; c < loop->cycles; ++c) {
-        int rc = qpmpc_b200_solve(d, in, out, stream);
+        int rc = loop->record ? qpmpc_b200_solve_factored(d, in, loop->record, out, stream)
+                              : qpmpc_b200_solve(d, in, out, stream);
         if (rc) return rc;
         step(loop->substeps, c + 1);
     }

@@ -218,6 +218,25 @@ class EmulatedLibrary:
         with _Checked() as lib:
             return lib.emu_integrate(desc, ops, U, X)
 
+    def qpmpc_b200_factor_bytes(self, desc):
+        self.lib.emu_factor_bytes.restype = ctypes.c_size_t
+        return self.lib.emu_factor_bytes(desc)
+
+    def qpmpc_b200_factor(self, desc, ops, record, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_factor(desc, ops, record)
+
+    def qpmpc_b200_solve_factored(self, desc, ops, record, outs, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_solve_factored(desc, ops, record, outs, 0)
+
+    def qpmpc_b200_pendulum_closed_loop(self, desc, ops, outs, loop, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_pendulum_closed_loop(desc, ops, outs, loop)
+
     def qpmpc_b200_strerror(self, code):
         return f"emulated engine: error {code}".encode()
 

@@ -19,6 +19,7 @@
 #include "qpmpc_b200/csrc/mpc_pdip.cuh"  // brings mpc_common.cuh and mpc_kernels.cuh
 #include "qpmpc_b200/csrc/mpc_cta_kernel.cuh"
 #include "qpmpc_b200/csrc/mpc_lr_kernel.cuh"
+#include "qpmpc_b200/csrc/mpc_factor.cuh"
 #include "qpmpc_b200/csrc/mpc_integrate.cuh"
 #include "qpmpc_b200/csrc/mpc_plant.cuh"
 
@@ -193,6 +194,47 @@ int solve_lr(SolveParams p) {
         case 4: launch(p.batch, NP, smem, [&]() { mpc_solve_lr_kernel<T, NP, 4>(p); }); return 0;
     }
     return QPMPC_B200_ESHAPE;
+}
+
+// launch_solve_pre (mpc_launch.cuh): shared-model fast path
+template <typename T, int NP>
+int solve_pre(SolveParams p, int wpc) {
+    using L = Lay<T, NP, 1, true, false, true, true>;
+    constexpr int IPW = 32 / NP;
+    for (int o : {OP_A, OP_B, OP_C, OP_D}) p.op[o] = OperandView{nullptr, 0, 0, 0, 0};
+    p.toeplitz = 0;
+    p.inst_stride = (L::fixed + 3) / 4 * 4;
+    p.gt_off = p.g_off = p.scr_off = 0;
+    const FactorLay F = factor_layout(NP, p.nx, p.N, p.q_wx != 0);
+    if (wpc <= 0) wpc = 8;
+    const int ipc = IPW * wpc;
+    int off = 0;
+    p.present_mask = 0;
+    for (int o = 0; o < OP_COUNT; ++o) {
+        OperandView &v = p.op[o];
+        if (!v.ptr) continue;
+        p.present_mask |= 1 << o;
+        v.smem_off = off;
+        off += (v.sz * (v.per_instance ? ipc : 1) + 3) / 4 * 4;
+    }
+    p.input_elems = off;
+    const size_t smem = 16 + ((size_t)ipc * p.inst_stride + off + F.total) * sizeof(T);
+    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    launch((p.batch + ipc - 1) / ipc, wpc * 32, smem, [&]() { mpc_solve_kernel<T, NP, 1, true, false, true, true>(p); });
+    return 0;
+}
+
+// factor_np / factor_has_ft of qpmpc_b200.cu
+int emu_factor_np(const qpmpc_b200_desc *d) {
+    auto shared = [](int mode, bool opt) {
+        return mode == QPMPC_B200_SHARED_LTI || mode == QPMPC_B200_SHARED_LTV || (opt && mode == QPMPC_B200_ABSENT);
+    };
+    if (!d || d->nc <= 0 || (d->nc & 1) || !d->paired || d->method != QPMPC_B200_ACTIVE_SET) return 0;
+    if (!shared(d->mode_A, false) || !shared(d->mode_B, false) || !shared(d->mode_C, true) || !shared(d->mode_D, true))
+        return 0;
+    Variant v;
+    if (!pick_variant(d->N * d->nu, d->N * d->nc, &v, true) || !v.paired) return 0;
+    return v.np;
 }
 
 // the active-set kernels of one dtype: warp kernel variants, or the CTA kernel
@@ -385,6 +427,68 @@ int emu_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const
 
 // qpmpc_b200_pendulum_closed_loop with host pointers: pendulum_step_kernel and the
 // fused solve alternate exactly as in qpmpc_b200.cu.
+// qpmpc_b200_factor_bytes / _factor / _solve_factored with host pointers (double only)
+size_t emu_factor_bytes(const qpmpc_b200_desc *d) {
+    const int np = emu_factor_np(d);
+    if (!np || d->dtype != QPMPC_B200_F64) return 0;
+    SolveParams sp;
+    qpmpc_b200_operands none = {};
+    fill_params(d, &none, &sp);
+    const size_t n = (size_t)d->N * d->nu, m = (size_t)d->N * d->nc, nx = d->nx, N = d->N;
+    return ((size_t)factor_layout(np, d->nx, d->N, sp.q_wx != 0).total + n * n + m * n + N * nx * nx + N * nx * n +
+            nx * nx + nx * n + 16) * 8;
+}
+int emu_factor(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, void *record) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    const int np = emu_factor_np(d);
+    if (!np || d->dtype != QPMPC_B200_F64 || !record) return QPMPC_B200_EUNSUPPORTED;
+    SolveParams sp;
+    fill_params(d, in, &sp);
+    const FactorLay F = factor_layout(np, d->nx, d->N, sp.q_wx != 0);
+    const size_t n = (size_t)d->N * d->nu, m = (size_t)d->N * d->nc, nx = d->nx, N = d->N;
+    double *scr = static_cast<double *>(record) + F.total;
+    qpmpc_b200_qp_fields f;
+    f.P = scr, scr += n * n;
+    f.G = scr, scr += m * n;
+    f.Phi = scr, scr += N * nx * nx;
+    f.Psi = scr, scr += N * nx * n;
+    f.phi_last = scr, scr += nx * nx;
+    f.psi_last = scr;
+    f.q = f.h = nullptr;
+    qpmpc_b200_desc d1 = *d;
+    d1.batch = 1;
+    if ((rc = emu_condense(&d1, in, &f)) != 0) return rc;
+    FactorParams fp;
+    fp.N = d->N, fp.nx = d->nx, fp.nu = d->nu, fp.nc = d->nc, fp.n = (int)n, fp.m = (int)m, fp.NP = np;
+    fp.has_ft = sp.q_wx, fp.q_wt = sp.q_wt, fp.q_wx = sp.q_wx;
+    fp.w_t = sp.w_t, fp.w_x = sp.w_x;
+    fp.P = f.P, fp.G = f.G, fp.Phi = f.Phi, fp.Psi = f.Psi, fp.phi_last = f.phi_last, fp.psi_last = f.psi_last;
+    fp.C = d->mode_C == QPMPC_B200_ABSENT ? nullptr : in->C;
+    fp.stepC = sp.op[OP_C].step;
+    fp.record = record;
+    launch(1, 128, FACTOR_SMEM_BYTES, [&]() { mpc_factor_kernel<double>(fp); });
+    return 0;
+}
+int emu_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                       const qpmpc_b200_outputs *out, int wpc) {
+    int rc = check_desc(d, in);
+    if (rc) return rc;
+    const int np = emu_factor_np(d);
+    if (!np || d->dtype != QPMPC_B200_F64 || !record || !out || !out->U || !out->status) return QPMPC_B200_EUNSUPPORTED;
+    if (d->batch == 0) return 0;
+    SolveParams p;
+    fill_params(d, in, &p);
+    p.U = out->U;
+    p.status = out->status;
+    p.iters = out->iters;
+    p.Z = out->Z;
+    p.record = record;
+    if (np == 8) return solve_pre<double, 8>(p, wpc);
+    if (np == 16) return solve_pre<double, 16>(p, wpc);
+    return solve_pre<double, 32>(p, wpc);
+}
+
 int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
                              const qpmpc_b200_closed_loop *loop) {
     if (!d || !in || !out || !loop || d->nx != 4 || d->nu != 1 || d->dtype != QPMPC_B200_F64) return QPMPC_B200_EINVAL;
@@ -403,15 +507,19 @@ int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands
     pp.goal = const_cast<void *>(in->goal);
     pp.targets = const_cast<void *>(in->targets);
     pp.unsolved = loop->unsolved;
+    pp.upright = loop->upright;
+    pp.iters = out->iters;
+    pp.iter_sum = nullptr;
     const int threads = 128, grid = (d->batch + threads - 1) / threads;
     auto step = [&](int substeps, int slot) {
         pp.substeps = substeps;
+        pp.iter_sum = (loop->iterations && out->iters && slot > 0) ? (long long *)loop->iterations + (slot - 1) : nullptr;
         pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 4 * 8 : nullptr;
         launch(grid, threads, 0, [&]() { pendulum_step_kernel<double>(pp); });
     };
     step(0, 0);
     for (int c = 0; c < loop->cycles; ++c) {
-        const int rc = emu_solve(d, in, out, 0);
+        const int rc = loop->record ? emu_solve_factored(d, in, loop->record, out, 0) : emu_solve(d, in, out, 0);
         if (rc) return rc;
         step(loop->substeps, c + 1);
     }

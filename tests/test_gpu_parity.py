@@ -293,7 +293,7 @@ def test_fp32_humanoid_within_stated_tolerance():
     assert err.max() <= 1e-4, err.max()
 
 
-def _cpu_closed_loop(w, cycles, substeps=15):
+def _cpu_closed_loop(w, cycles, substeps=15, return_iters=False):
     """The loop of examples/wheeled_inverted_pendulum.py:99-118 on the CPU: the
     oracle solves, the host mirror of the plant integrates."""
     import oracle
@@ -303,21 +303,33 @@ def _cpu_closed_loop(w, cycles, substeps=15):
     pend = WheeledInvertedPendulum()
     B, N, T = w["batch"], w["N"], w["T"]
     state = w["x0"].copy()
-    traj = [state.copy()]
+    traj, iters = [state.copy()], []
     w = dict(w)
     for _ in range(cycles):
         w["x0"] = state
         w["targets"], w["goal"] = pendulum_targets(state, w["v_target"], N, T)
         ref = oracle.solve_batch(B, N, 4, 1, 2, oracle_ops(w), w["w_t"], w["w_x"], w["w_u"])
         assert (ref["status"] == 0).all()
-        new = np.empty_like(state)
-        for b in range(B):
-            x = state[b]
+        if B <= 64:
+            new = np.empty_like(state)
+            for b in range(B):
+                x = state[b]
+                for _s in range(substeps):
+                    x = pend.integrate(x, ref["U"][b, 0], T / substeps)
+                new[b] = x
+            state = new
+        else:
+            # the same Taylor step (systems/wheeled_inverted_pendulum.py:127-160), vectorised
+            u, dt, x = ref["U"][:, 0], T / substeps, state
             for _s in range(substeps):
-                x = pend.integrate(x, ref["U"][b, 0], T / substeps)
-            new[b] = x
-        state = new
+                pa = pend.omega**2 * (np.sin(x[:, 1]) - (u / pend.GRAVITY) * np.cos(x[:, 1]))
+                x = np.stack([x[:, 0] + dt * x[:, 2] + 0.5 * dt * dt * u, x[:, 1] + dt * x[:, 3] + 0.5 * dt * dt * pa,
+                              x[:, 2] + dt * u, x[:, 3] + dt * pa], axis=1)
+            state = x
+        iters.append(ref["iters"].copy())
         traj.append(state.copy())
+    if return_iters:
+        return np.stack(traj), np.stack(iters)
     return np.stack(traj)
 
 
@@ -491,3 +503,67 @@ def test_solve_host_paths_are_bit_identical(path, kind, monkeypatch):
         assert torch.equal(U, plan.inputs.reshape(B, n).cpu())
         assert torch.equal(st, plan.status.cpu()) and torch.equal(it, plan.iters.cpu())
         assert torch.equal(Z, plan.multipliers.cpu())
+
+
+@pytest.mark.parametrize("factored", [False, True])
+def test_pendulum_closed_loop_1024_instances_200_cycles_against_the_cpu_loop(factored):
+    """BASELINE config 3 at full length: 1 024 instances x 200 receding-horizon cycles on the
+    device (re-condensing every cycle, or with the model factored once: qpmpc_b200_factor +
+    qpmpc_b200_solve_factored) against the CPU loop (oracle + host plant), state by state for
+    every instance that stays upright; the per-cycle iteration counts (summed over the batch) and
+    the number of (instance, cycle) pairs solved from an upright state agree too."""
+    import torch
+
+    from qpmpc_b200 import factor_model, pendulum_closed_loop
+    from qpmpc_b200.workloads import pendulum_batch, pendulum_targets, to_batched
+
+    B, cycles = 1024, 200
+    w = pendulum_batch(B, seed=1)
+    ref, ref_iters = _cpu_closed_loop(w, cycles, return_iters=True)
+    prob = to_batched(w)
+    model = None
+    if factored:
+        tg, goal = pendulum_targets(w["x0"], w["v_target"], w["N"], w["T"])
+        prob.update_goal_state(goal)
+        prob.update_target_states(tg)
+        model = factor_model(prob)
+    plan, traj, unsolved, stats = pendulum_closed_loop(prob, w["v_target"], cycles, record=True, stats=True,
+                                                      factored=model)
+    torch.cuda.synchronize()
+    assert int(unsolved.item()) == 0
+    got = traj.cpu().numpy()
+    upright = np.abs(ref[:, :, 1]).max(axis=0) < 1.2
+    assert upright.mean() > 0.98
+    assert np.array_equal(np.abs(got[:, :, 1]).max(axis=0) < 1.2, upright)
+    assert np.abs(got[:, upright] - ref[:, upright]).max() <= 1e-6
+    assert int(stats["upright"].item()) == int((np.abs(ref[:-1, :, 1]) <= 1.2).sum())
+    it = stats["iterations"].cpu().numpy()
+    # the iteration histogram: identical while every instance is upright, and the loop is mostly
+    # unconstrained once it has converged (the bound is active in the first cycles only)
+    first_fall = int(np.argmax((np.abs(ref[:, :, 1]) > 1.2).any(axis=1))) if (~upright).any() else cycles
+    assert np.array_equal(it[:first_fall], ref_iters.sum(axis=1)[:first_fall])
+    assert it[0] > it[-1]
+
+
+def test_factored_model_matches_the_full_path_on_the_device():
+    """qpmpc_b200_factor + qpmpc_b200_solve_factored against qpmpc_b200_solve and the oracle:
+    pendulum (stage cost, D rows), humanoid (per-instance per-step e_k), shared triple integrator
+    at N = 8 / 32."""
+    import torch
+
+    from qpmpc_b200 import factor_model, solve_mpc_batch
+    from qpmpc_b200.workloads import humanoid_batch, pendulum_batch, to_batched, triple_integrator_batch
+
+    ti32 = triple_integrator_batch(300, N=32, seed=5, per_instance_model=False)
+    for w in (pendulum_batch(4099, seed=3), pendulum_batch(515, seed=4, ltv_model=True), humanoid_batch(2050, seed=6),
+              triple_integrator_batch(1000, N=8, seed=7, per_instance_model=False), ti32):
+        prob = to_batched(w)
+        full = solve_mpc_batch(prob, return_multipliers=True)
+        fast = solve_mpc_batch(prob, return_multipliers=True, factored=factor_model(prob))
+        torch.cuda.synchronize()
+        ref = _oracle(w)
+        ok = ref["status"] == 0
+        assert np.array_equal(fast.status.cpu().numpy() == 0, ok) and torch.equal(fast.status, full.status)
+        assert torch.equal(fast.iters, full.iters)
+        U = fast.inputs.reshape(w["batch"], -1).cpu().numpy()
+        assert np.abs(U[ok] - ref["U"][ok]).max() <= U_TOL

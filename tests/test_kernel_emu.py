@@ -447,3 +447,67 @@ def test_low_rank_kernel_is_only_used_where_it_applies(monkeypatch):
     _check(w)                                   # stage cost: P is not low rank
     _check(pendulum_batch(3, N=20, seed=4))     # D rows and a stage cost
     _check(triple_integrator_batch(2, N=24, seed=5), paired=False)
+
+
+# -- shared-model fast path: factor once, per solve only q and h (mpc_factor.cuh) -------------
+
+@pytest.mark.parametrize("kind", ["pendulum", "pendulum_ltv", "humanoid_shared", "ti8_shared", "ti32_shared", "no_targets"])
+def test_factored_model_path_matches_the_full_path(kind, emulated_engine, monkeypatch):
+    """``factor_model`` + ``solve_mpc_batch(..., factored=)``: the batched form of one MPCQP kept
+    across calls with update_cost_vector / update_constraint_vector (mpc_qp.py:129-163).  Same
+    answers, statuses and iteration counts as condensing every instance from scratch and as
+    the oracle; new initial / goal / target states reuse the record."""
+    import torch
+
+    from qpmpc_b200 import factor_model, solve_mpc_batch
+    from qpmpc_b200.workloads import to_batched
+
+    monkeypatch.setenv("QPMPC_B200_LR", "0")
+    if kind.startswith("pendulum") or kind == "no_targets":
+        w = pendulum_batch(37, seed=31, ltv_model=(kind == "pendulum_ltv"))
+        if kind == "no_targets":
+            w["targets"], w["w_x"] = None, None
+    elif kind == "humanoid_shared":
+        w = humanoid_batch(21, seed=32)  # per-instance per-step e_k, shared A, B, C
+    else:
+        N = 8 if kind == "ti8_shared" else 32
+        w = triple_integrator_batch(13, N=N, seed=33, per_instance_model=False)
+        w["e"] = np.tile(w["e"], (13, 1)) * (1.0 + 0.1 * np.arange(13))[:, None]  # per-instance bounds
+    prob = to_batched(w)
+    model = factor_model(prob)
+    full = solve_mpc_batch(prob, return_multipliers=True)
+    fast = solve_mpc_batch(prob, return_multipliers=True, factored=model)
+    ref = _oracle(w)
+    ok = ref["status"] == 0
+    assert np.array_equal(fast.status.numpy() == 0, ok) and torch.equal(fast.status, full.status)
+    assert torch.equal(fast.iters[torch.as_tensor(ok)], full.iters[torch.as_tensor(ok)])
+    U = fast.inputs.reshape(w["batch"], -1).numpy()
+    assert np.abs(U[ok] - ref["U"][ok]).max() <= U_TOL
+    assert np.abs(U[ok] - full.inputs.reshape(w["batch"], -1).numpy()[ok]).max() <= 1e-8
+    assert np.abs(fast.multipliers.numpy()[ok] - full.multipliers.numpy()[ok]).max() <= 1e-6 * max(
+        1.0, np.abs(full.multipliers.numpy()[ok]).max())
+    # new states, same record (what a receding-horizon loop does every cycle)
+    rng = np.random.default_rng(5)
+    w2 = dict(w)
+    w2["x0"] = w["x0"] + 0.05 * rng.standard_normal(w["x0"].shape)
+    w2["goal"] = w["goal"] + 0.05 * rng.standard_normal(w["goal"].shape)
+    prob.update_initial_state(w2["x0"])
+    prob.update_goal_state(w2["goal"])
+    again = solve_mpc_batch(prob, factored=model)
+    ref2 = _oracle(w2)
+    ok2 = ref2["status"] == 0
+    assert np.array_equal(again.status.numpy() == 0, ok2)
+    assert np.abs(again.inputs.reshape(w["batch"], -1).numpy()[ok2] - ref2["U"][ok2]).max() <= U_TOL
+
+
+def test_factored_model_is_refused_where_it_does_not_apply(emulated_engine):
+    from qpmpc_b200 import BackendError, ProblemDefinitionError, factor_model, solve_mpc_batch
+    from qpmpc_b200.workloads import to_batched
+
+    with pytest.raises(BackendError):
+        factor_model(to_batched(triple_integrator_batch(4, seed=1)))      # per-instance A, B, C
+    with pytest.raises(BackendError):
+        factor_model(to_batched(random_batch(3, 4, 3, 1, 2, ltv=False)))   # rows are not pairs
+    a, b = to_batched(pendulum_batch(5, seed=1)), to_batched(pendulum_batch(5, seed=2, T=0.12))
+    with pytest.raises(ProblemDefinitionError):
+        solve_mpc_batch(b, factored=factor_model(a))                       # another model's record
