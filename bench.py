@@ -55,8 +55,9 @@ ROTATE_BYTES = 160e6  # distinct input sets must exceed the 126 MB L2
 METRIC = "MPC solves/sec (batched)"
 UNIT = "solves/s"
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
-DEFAULTS = {2: (65536, 16), 3: (16384, 12), 4: (8192, 16), 5: (262144, 64)}  # config -> (batch/GPU, N)
+DEFAULTS = {2: (65536, 16), 3: (16384, 12), 4: (8192, 16), 5: (262144, 64), 6: (8192, 16)}  # config -> (batch/GPU, N)
 CYCLES = 200  # config 3
+WALK_CYCLES = 300  # config 6 (examples/lipm_walking_controller.py:306)
 
 
 def parse_args():
@@ -65,7 +66,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--horizon", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -77,9 +78,9 @@ def parse_args():
     args.batch = args.batch or b
     args.horizon = args.horizon or n
     if args.steps is None:
-        args.steps = {2: 1024, 3: 8, 4: 1024, 5: 64}[args.config] if args.impl == "b200" else 8
+        args.steps = {2: 1024, 3: 8, 4: 1024, 5: 64, 6: 8}[args.config] if args.impl == "b200" else 8
     if args.warmup is None:
-        args.warmup = {2: 16, 3: 3, 4: 16, 5: 4}[args.config] if args.impl == "b200" else 3
+        args.warmup = {2: 16, 3: 3, 4: 16, 5: 4, 6: 3}[args.config] if args.impl == "b200" else 3
     return args
 
 
@@ -87,8 +88,10 @@ def parse_args():
 # workloads
 # ---------------------------------------------------------------------------
 def make_workload(args, seed):
-    from qpmpc_b200.workloads import humanoid_batch, pendulum_batch, triple_integrator_batch
+    from qpmpc_b200.workloads import humanoid_batch, lipm_walking_batch, pendulum_batch, triple_integrator_batch
 
+    if args.config == 6:
+        return lipm_walking_batch(args.batch, N=args.horizon, seed=4 + seed)
     if args.config == 3:
         return pendulum_batch(args.batch, N=args.horizon, seed=1 + seed)
     if args.config == 4:
@@ -101,7 +104,7 @@ def dtype_of(args):
 
 
 def solves_per_step(args):
-    return args.batch * (CYCLES if args.config == 3 else 1)
+    return args.batch * (CYCLES if args.config == 3 else WALK_CYCLES if args.config == 6 else 1)
 
 
 def config_dict(args, world, rotate=None):
@@ -113,6 +116,10 @@ def config_dict(args, world, rotate=None):
            "(targets -> condense+solve -> 15 plant substeps per cycle), shared model (BASELINE configs[2])",
         4: f"humanoid/LIPM fp32 nx=3 nu=1 nc=2 N={N} batch={B}/GPU per-instance per-step e_k (BASELINE configs[3])",
         5: f"triple_integrator T=1/N fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU (BASELINE configs[4], one sweep point)",
+        6: f"lipm_walking_controller fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU, {WALK_CYCLES}-cycle walking loop: per "
+           "cycle the phase machine rewrites the per-step ZMP bounds e_k and the goal, condense+solve, 15 "
+           "integration substeps (the closed-loop form of BASELINE configs[3]'s LIPM LTV constraints; "
+           "examples/lipm_walking_controller.py)",
     }
     cfg = {
         "workload": names[args.config],
@@ -225,18 +232,39 @@ def cpu_closed_loop(workload, cycles, threads, substeps=15):
     return x
 
 
+def cpu_walking_loop(workload, cycles, threads):
+    """Config 6 on the host: examples/lipm_walking_controller.py:307-335 with the numpy phase
+    machine of qpmpc_b200.workloads and the oracle as the solver."""
+    from qpmpc_b200.workloads import lipm_advance, lipm_phase_vectors
+
+    w = dict(workload)
+    x, foot = w["x0"].copy(), w["support_foot"].copy()
+    pidx, sidx = w["phase_index"].copy(), w["stride_index"].copy()
+    for _ in range(cycles):
+        w["x0"] = x
+        w["e"], w["goal"] = lipm_phase_vectors(w, foot, pidx, sidx)
+        ref = cpu_solve(w, threads)
+        u0 = np.where(ref["status"] == 0, ref["U"][:, 0], 0.0)
+        x, foot, pidx, sidx = lipm_advance(w, x, u0, foot, pidx, sidx)
+    return x
+
+
+def cpu_loop(args, workload, cycles, threads):
+    return (cpu_closed_loop if args.config == 3 else cpu_walking_loop)(workload, cycles, threads)
+
+
 def cpu_arm(args, workload, seconds):
     """Time the oracle on a bounded sample of the workload for about `seconds`;
     returns (solves/s, threads, sample description)."""
     from qpmpc_b200.workloads import slice_workload
 
     threads = host_threads()
-    if args.config == 3:
+    if args.config in (3, 6):
         # the closed loop is sequential over cycles: a slice of the batch, fewer cycles
         k, cyc = min(workload["batch"], 16384), 20
         ws = slice_workload(workload, 0, k)
         t0 = time.perf_counter()
-        cpu_closed_loop(ws, cyc, threads)
+        cpu_loop(args, ws, cyc, threads)
         dt = time.perf_counter() - t0
         return k * cyc / dt, threads, (f"{k} instances x {cyc} closed-loop cycles (C oracle solve on {threads} "
                                        f"threads + NumPy plant step) in {dt:.1f} s")
@@ -261,15 +289,15 @@ def run_reference(args, rank, world):
     from qpmpc_b200.workloads import slice_workload
 
     threads = host_threads()
-    if args.config == 3:
+    if args.config in (3, 6):
         w = make_workload(args, 0)
         k, cyc = min(args.batch, 16384), 20
         ws = slice_workload(w, 0, k)
         for _ in range(min(args.warmup, 1)):
-            cpu_closed_loop(ws, 1, threads)
+            cpu_loop(args, ws, 1, threads)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_closed_loop(ws, cyc, threads)
+            cpu_loop(args, ws, cyc, threads)
         dt = time.perf_counter() - t0
         value, per_step = k * cyc * args.steps / dt, k * cyc
         sample = f"{args.steps} steps x ({k} instances x {cyc} closed-loop cycles): C oracle + NumPy plant"
@@ -313,6 +341,8 @@ def kernel_name(args):
     if args.method == "pdip":
         return f"mpc_pdip_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
     terminal_only = args.config != 3  # config 3 has a stage cost
+    if args.config in (3, 6):
+        return f"mpc_solve_kernel<{t},NP=16,paired rows,shared-model record>"
     if t == "double" and terminal_only and 16 < n <= 64:
         return f"mpc_solve_lr_kernel<double,NP={32 if n <= 32 else 64}>"  # structure-exploiting (rank-nx Hessian)
     if n > 32:
@@ -363,6 +393,8 @@ def flop_models(args, iters_mean):
     nc, n, m = 2, N * nu, 2 * N
     has_C = args.config != 3
     has_wx = args.config == 3
+    if args.config in (3, 6):
+        pass  # (the executed model below is replaced by the factored path's in run_b200)
     # dense, structure-agnostic condensing + K = 10 interior-point iterations
     f_cond = N * (2 * nx**3 + 2 * nx * nx * n + (2 * nc * nx * n + 2 * nc * nx * nx + 2 * nc * nx if has_C else 0)) \
         + 2 * nx * n * n + (2 * N * nx * n * n if has_wx else 0)
@@ -393,7 +425,7 @@ def run_b200(args, rank, local_rank, world):
 
     import torch
 
-    from qpmpc_b200 import _capi, factor_model, pendulum_closed_loop, solve_mpc_batch
+    from qpmpc_b200 import _capi, factor_model, lipm_walking_closed_loop, pendulum_closed_loop, solve_mpc_batch
     from qpmpc_b200.workloads import algorithmic_bytes_per_solve, to_batched
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -412,14 +444,15 @@ def run_b200(args, rank, local_rank, world):
     w0 = make_workload(args, 1000 * rank)
     bytes_per_solve = algorithmic_bytes_per_solve(w0, es)
     in_bytes = (bytes_per_solve - es * n - 4) * B
-    rotate = 1 if args.config == 3 else max(2, min(16, int(np.ceil(ROTATE_BYTES / max(in_bytes, 1)))))
+    loop_cfg = args.config in (3, 6)
+    rotate = 1 if loop_cfg else max(2, min(16, int(np.ceil(ROTATE_BYTES / max(in_bytes, 1)))))
     sets = [w0] + [make_workload(args, 1000 * rank + s) for s in range(1, rotate)]
     problems = [to_batched(w, dtype=tdtype, device=dev) for w in sets]
     U_out = torch.empty((B, n), dtype=tdtype, device=dev)
     U_all = torch.empty((world * B, n), dtype=tdtype, device=dev) if world > 1 else None
     mkw = {} if args.method == "active_set" else {"method": args.method}
     gather, gather_kind = None, "none"
-    if world > 1 and args.config != 3:
+    if world > 1 and not loop_cfg:
         gather_kind = "nccl all_gather_into_tensor"
         # (the fused gather exists for the active-set kernel only)
         if os.environ.get("QPMPC_B200_GATHER", "peer") == "peer" and args.method == "active_set" \
@@ -432,17 +465,29 @@ def run_b200(args, rank, local_rank, world):
             except Exception as exc:  # noqa: BLE001
                 gather_kind += f" (symmetric memory unavailable: {type(exc).__name__})"
 
-    x0_init = torch.as_tensor(w0["x0"]).to(dev) if args.config == 3 else None
+    x0_init = torch.as_tensor(w0["x0"]).to(dev) if loop_cfg else None
     v_dev = torch.as_tensor(w0["v_target"]).to(dev) if args.config == 3 else None
+    walk0 = {k: torch.as_tensor(w0[k]).to(dev) for k in ("support_foot", "strides", "phase_index", "stride_index")} \
+        if args.config == 6 else None
     loop_info = {}
     # config 3: the model (A, B, D, weights) is shared by the batch and constant over the loop --
     # factored once (qpmpc_b200_factor), every cycle then only rebuilds q and h.
     # QPMPC_B200_BENCH_FACTORED=0 re-condenses every instance every cycle instead.
     model = None
-    if args.config == 3 and os.environ.get("QPMPC_B200_BENCH_FACTORED", "1") != "0":
+    if loop_cfg and os.environ.get("QPMPC_B200_BENCH_FACTORED", "1") != "0":
         model = factor_model(problems[0])
 
+    def walk(prob, x0_src, phase_src):
+        prob.x0.copy_(x0_src, non_blocking=True)
+        return lipm_walking_closed_loop(prob, phase_src["support_foot"].clone(), phase_src["strides"],
+                                        phase_src["phase_index"].clone(), phase_src["stride_index"].clone(),
+                                        WALK_CYCLES, factored=model)
+
     def step(i):
+        if args.config == 6:
+            plan, _, unsolved, _ = walk(problems[0], x0_init, walk0)
+            loop_info["unsolved"] = unsolved
+            return plan
         if args.config == 3:
             problems[0].x0.copy_(x0_init)
             plan, _, unsolved, stats = pendulum_closed_loop(problems[0], v_dev, CYCLES, factored=model, stats=True)
@@ -465,7 +510,7 @@ def run_b200(args, rank, local_rank, world):
     for i in range(args.warmup):
         plan = step(i)
     barrier()
-    if args.config != 3:
+    if not loop_cfg:
         assert int((plan.status != 0).sum().item()) == 0, "warm-up batch has unsolved instances"
 
     sampler = ClockSampler(local_rank)
@@ -490,7 +535,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- N > 1: the gathered U equals a local re-solve of every other rank's shard ----------
     gather_check = None
-    if world > 1 and args.config != 3:
+    if world > 1 and not loop_cfg:
         last = step(0)
         barrier()
         got = (last.gathered if hasattr(last, "gathered") else U_all).clone()
@@ -509,7 +554,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- kernel-only duration (no collective): events around bare launches -----------------
     kernel_ms = None
-    if args.config != 3:
+    if not loop_cfg:
         ksteps = min(args.steps, 256)
         kev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * ksteps)]
         torch.cuda.synchronize()
@@ -533,7 +578,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- e2e: host buffers through the C ABI ----------------------------------------------
     lib = _capi.load()
     e2e = None
-    if args.config != 3:
+    if not loop_cfg:
         np_dtype = np.float32 if args.config == 4 else np.float64
         names = [k for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets") if sets[0][k] is not None]
         host_sets = []
@@ -605,6 +650,31 @@ def run_b200(args, rank, local_rank, world):
                        "reads the operands from host memory over PCIe and whose epilogue stores U / status into host "
                        "memory; sync per step)" + ("; ranks write their rows into one host array shared by the "
                                                    "job (the gather), barrier per step" if world > 1 else "")}
+    elif args.config == 6:
+        # the walking loop: initial states and the phase machine's state come from pinned host
+        # memory every step, the final states go back
+        x0_host = torch.from_numpy(np.ascontiguousarray(w0["x0"])).pin_memory()
+        ph_host = {k: torch.from_numpy(np.ascontiguousarray(w0[k])).pin_memory()
+                   for k in ("support_foot", "strides", "phase_index", "stride_index")}
+        xf_host = torch.empty_like(x0_host).pin_memory()
+        e2e_steps = max(2, min(args.steps, 8))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ph_dev = {k: v.to(dev, non_blocking=True) for k, v in ph_host.items()}
+            walk(problems[0], x0_host, ph_dev)
+            xf_host.copy_(problems[0].x0, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * solves_per_step(args) * e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": x0_host.numel() * 8 + sum(v.numel() * v.element_size() for v in ph_host.values()),
+               "d2h_bytes_per_step": xf_host.numel() * 8, "steps": e2e_steps,
+               "call": "lipm_walking_closed_loop -> qpmpc_b200_lipm_closed_loop: initial states, strides, support feet "
+                       "and phases from pinned host memory, final states read back; sync per step"}
     else:
         # config 3: the state lives on the device for the whole loop; a step uploads the initial
         # states / target velocities from pinned host memory and reads the final states back
@@ -663,7 +733,7 @@ def run_b200(args, rank, local_rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(args), "data": "synthetic",
         "config": config_dict(args, world,
                               f"inputs rotate over {rotate} distinct sets ({rotate}x{in_bytes / 1e6:.1f} MB > L2)"
-                              if rotate > 1 else "state resident on the device across the 200 cycles (the workload)"),
+                              if rotate > 1 else "state resident on the device across the cycles of the loop (the workload)"),
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -700,6 +770,11 @@ def run_b200(args, rank, local_rank, world):
                          f"(profiles/{prof['source']}), at this run's kernel time"}
     if gather_check is not None:
         line["gather_check"] = gather_check
+    if args.config == 6:
+        line["closed_loop"] = {"cycles": WALK_CYCLES, "unsolved": int(loop_info["unsolved"].item()),
+                               "model": "factored once (qpmpc_b200_factor), q and h per cycle" if model is not None
+                               else "condensed and factored per instance and cycle",
+                               "launches_per_step": 2 * WALK_CYCLES + 1}
     if args.config == 3:
         hist = loop_info["stats"]["iterations"].cpu().numpy().astype(float) / B
         useful = int(loop_info["stats"]["upright"].item())

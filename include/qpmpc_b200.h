@@ -241,6 +241,37 @@ int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *desc, const qpmpc_b20
                                     const qpmpc_b200_outputs *out, const qpmpc_b200_closed_loop *loop,
                                     void *stream);
 
+/* Walking loop of examples/lipm_walking_controller.py:307-335 for a batch, state resident on
+ * the device: per cycle { ZMP bounds e_k of the horizon and the goal from the phase machine
+ * (update_goal_and_constraints :175-205, PhaseStepper :104-172); condense + solve
+ * (qpmpc/solve_mpc.py:42-43); `substeps` constant-jerk integration steps under the first input
+ * (:208-226); phase advance and foot switch (:331-334) }.  The problem must have nx = 3,
+ * nu = 1, nc = 2 (C = [+zmp; -zmp]) with per-instance x0 [batch,3] (the state, read and
+ * overwritten), per-instance per-step e [batch,N,2] (mode_e = BATCH_LTV) and per-instance goal
+ * [batch,3]: both are work buffers the loop rewrites every cycle.  An instance without a plan
+ * in some cycle gets jerk 0 for that cycle and is counted in *unsolved.  2 * cycles + 1
+ * launches, asynchronous on `stream`. */
+typedef struct qpmpc_b200_lipm_loop {
+    int32_t cycles;          /* control cycles (300 in the reference example) */
+    int32_t substeps;        /* integration steps per cycle (15) */
+    int32_t nb_dsp_steps;    /* round(dsp_duration / sampling_period) */
+    int32_t nb_ssp_steps;    /* round(ssp_duration / sampling_period) */
+    double sampling_period;  /* T of the MPC model */
+    double foot_size;
+    double max_zmp_dist;     /* bound written where the ZMP is unconstrained (MAX_ZMP_DIST) */
+    void *support_foot;      /* [batch] position of the support foot, read and updated */
+    const void *strides;     /* [batch, 2] alternating strides */
+    int32_t *phase_index;    /* [batch] PhaseStepper.index, read and updated */
+    int32_t *stride_index;   /* [batch] PhaseStepper.stride_index, read and updated */
+    void *trajectory;        /* optional [cycles + 1, batch, 3] states after each cycle */
+    int32_t *unsolved;       /* optional device counter, incremented per missing plan */
+    const void *record;      /* optional: record of qpmpc_b200_factor for this model */
+} qpmpc_b200_lipm_loop;
+
+int qpmpc_b200_lipm_closed_loop(const qpmpc_b200_desc *desc, const qpmpc_b200_operands *in,
+                                const qpmpc_b200_outputs *out, const qpmpc_b200_lipm_loop *loop,
+                                void *stream);
+
 /* Scratch the device entry points need from the caller: none (0) today; kept
  * in the ABI so a future kernel can ask for it without a signature change. */
 size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *desc);

@@ -27,6 +27,7 @@ from .batched import (  # noqa: E402
     condense_batch,
     factor_model,
     integrate_batch,
+    lipm_walking_closed_loop,
     pendulum_closed_loop,
     problem_to_batch,
     solve_mpc_batch,
@@ -37,6 +38,6 @@ from .solve_mpc import solve_mpc  # noqa: E402  (rebinds the name from module to
 __all__ = [
     "BackendError", "BatchedMPCProblem", "BatchedPlan", "FactoredModel", "MPCProblem", "MPCQP",
     "Plan", "PlanError", "ProblemDefinitionError", "QPMPCException", "QPProblem",
-    "Solution", "StateError", "condense_batch", "factor_model", "integrate_batch", "pendulum_closed_loop",
+    "Solution", "StateError", "condense_batch", "factor_model", "integrate_batch", "lipm_walking_closed_loop", "pendulum_closed_loop",
     "solve_mpc", "solve_mpc_batch",
 ]

@@ -26,7 +26,7 @@ EXPORTS = (
     "qpmpc_b200_max_rows", "qpmpc_b200_launch_count", "qpmpc_b200_strerror",
     "qpmpc_b200_version", "qpmpc_b200_fp64_peak", "qpmpc_b200_pendulum_closed_loop",
     "qpmpc_b200_solve_scatter", "qpmpc_b200_factor_bytes", "qpmpc_b200_factor",
-    "qpmpc_b200_solve_factored",
+    "qpmpc_b200_solve_factored", "qpmpc_b200_lipm_closed_loop",
 )
 
 
@@ -93,6 +93,21 @@ class ClosedLoop(ctypes.Structure):
     ]
 
 
+class LipmLoop(ctypes.Structure):
+    """``qpmpc_b200_lipm_loop``."""
+
+    _fields_ = [
+        ("cycles", ctypes.c_int32), ("substeps", ctypes.c_int32),
+        ("nb_dsp_steps", ctypes.c_int32), ("nb_ssp_steps", ctypes.c_int32),
+        ("sampling_period", ctypes.c_double), ("foot_size", ctypes.c_double),
+        ("max_zmp_dist", ctypes.c_double),
+        ("support_foot", ctypes.c_void_p), ("strides", ctypes.c_void_p),
+        ("phase_index", ctypes.c_void_p), ("stride_index", ctypes.c_void_p),
+        ("trajectory", ctypes.c_void_p), ("unsolved", ctypes.c_void_p),
+        ("record", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -121,6 +136,9 @@ def load():
     lib.qpmpc_b200_factor_bytes.restype = ctypes.c_size_t
     lib.qpmpc_b200_factor.argtypes = [P(Desc), P(Operands), ctypes.c_void_p, ctypes.c_void_p]
     lib.qpmpc_b200_solve_factored.argtypes = [P(Desc), P(Operands), ctypes.c_void_p, P(Outputs), ctypes.c_void_p]
+    lib.qpmpc_b200_lipm_closed_loop.argtypes = [
+        P(Desc), P(Operands), P(Outputs), P(LipmLoop), ctypes.c_void_p]
+    lib.qpmpc_b200_lipm_closed_loop.restype = ctypes.c_int
     for name in ("solve", "solve_host", "condense", "integrate", "version", "factor", "solve_factored",
                  "max_vars", "max_rows", "pendulum_closed_loop", "solve_scatter"):
         getattr(lib, f"qpmpc_b200_{name}").restype = ctypes.c_int

@@ -605,3 +605,80 @@ def pendulum_closed_loop(
     if stats:
         return BatchedPlan(problem, U, status, iters), traj, unsolved, dict(upright=upright, iterations=iter_hist)
     return BatchedPlan(problem, U, status, iters), traj, unsolved
+
+
+def lipm_walking_closed_loop(
+    problem: BatchedMPCProblem,
+    support_foot,
+    strides,
+    phase_index,
+    stride_index,
+    cycles: int,
+    substeps: int = 15,
+    dsp_duration: float = 0.1,
+    ssp_duration: float = 0.7,
+    sampling_period: float = 0.1,
+    foot_size: float = 0.065,
+    max_zmp_dist: float = 100.0,
+    record: bool = False,
+    factored: Optional[FactoredModel] = None,
+):
+    """Walking loop of ``examples/lipm_walking_controller.py:307-335`` on the device, batched:
+    per cycle the phase machine writes the ZMP bounds ``e_k`` of the horizon and the goal, the
+    MPC is condensed and solved, the state advances ``substeps`` constant-jerk steps under the
+    first input, and the phase (and, at a foot switch, the support foot) advances.
+
+    ``problem.x0`` [B, 3] is the state and is updated in place; ``problem.e`` [B, N, 2] and
+    ``problem.goal`` [B, 3] are (re)allocated and rewritten every cycle.  ``support_foot`` [B],
+    ``phase_index`` [B] and ``stride_index`` [B] are the phase machine's state (updated in place
+    when given as device tensors), ``strides`` [B, 2] the alternating strides.
+
+    Returns ``(plan_of_last_cycle, trajectory or None, unsolved_count_tensor, phase_state)``
+    with ``phase_state = dict(support_foot, phase_index, stride_index)``.  Asynchronous.
+    """
+    lib = _capi.load()
+    B, N = problem.batch_size, problem.nb_timesteps
+    if problem.state_dim != 3 or problem.input_dim != 1 or problem.ineq_dim != 2:
+        raise ProblemDefinitionError("the walking loop needs state_dim 3, input_dim 1 and two rows per step")
+    dev, dt_ = problem.device, problem.dtype
+    if problem.x0 is None or problem.mode_x0 != _capi.VEC_BATCH:
+        raise ProblemDefinitionError("per-instance initial states [B, 3] are required")
+    with _device_guard(dev):
+        if problem.e is None or problem.mode_e != _capi.BATCH_LTV:
+            problem.e = torch.empty((B, N, 2), dtype=dt_, device=dev)
+            problem.mode_e = _capi.BATCH_LTV
+        if problem.goal is None or problem.mode_goal != _capi.VEC_BATCH:
+            problem.goal = torch.zeros((B, 3), dtype=dt_, device=dev)
+            problem.mode_goal = _capi.VEC_BATCH
+
+        def vec(v, dtype, shape):
+            t = torch.as_tensor(v).to(device=dev, dtype=dtype)
+            if t.numel() * B == int(np.prod(shape)):
+                t = t.expand(shape)
+            t = t.reshape(shape).contiguous()
+            return t
+
+        foot = vec(support_foot, dt_, (B,))
+        strd = vec(strides, dt_, (B, 2))
+        pidx = vec(phase_index, torch.int32, (B,))
+        sidx = vec(stride_index, torch.int32, (B,))
+        n = problem.nb_vars
+        U = torch.empty((B, n), dtype=dt_, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        iters = torch.zeros(B, dtype=torch.int32, device=dev)
+        traj = torch.empty((cycles + 1, B, 3), dtype=dt_, device=dev) if record else None
+        unsolved = torch.zeros(1, dtype=torch.int32, device=dev)
+        if factored is not None and factored.signature != _model_signature(problem):
+            raise ProblemDefinitionError("the factored model belongs to another problem")
+        desc = problem.desc()
+        ops = problem.operands()
+        outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), None)
+        loop = _capi.LipmLoop(int(cycles), int(substeps), int(round(dsp_duration / sampling_period)),
+                              int(round(ssp_duration / sampling_period)), float(sampling_period), float(foot_size),
+                              float(max_zmp_dist), _ptr(foot), _ptr(strd), _ptr(pidx), _ptr(sidx), _ptr(traj),
+                              _ptr(unsolved), _ptr(factored.record) if factored is not None else None)
+        rc = lib.qpmpc_b200_lipm_closed_loop(ctypes.byref(desc), ctypes.byref(ops), ctypes.byref(outs),
+                                             ctypes.byref(loop), _stream_ptr(dev))
+    _capi.check(rc, "qpmpc_b200_lipm_closed_loop")
+    return (BatchedPlan(problem, U, status, iters), traj, unsolved,
+            dict(support_foot=foot, phase_index=pidx, stride_index=sidx))

@@ -77,4 +77,109 @@ __global__ void __launch_bounds__(128) pendulum_step_kernel(const PendulumStepPa
     gl[3] = T(0);
 }
 
+// ---------------------------------------------------------------------------
+// The walking loop of examples/lipm_walking_controller.py:307-335 (reference tree), batched:
+// between two MPC solves the state is integrated under the first jerk of the plan
+// (integrate, :208-226), the phase machine advances (PhaseStepper.advance, :124-130, and the
+// foot switch of :331-334), and the next cycle's LTV constraint vector e_k and goal are written
+// (update_goal_and_constraints, :175-205, with PhaseStepper.get_nb_steps, :132-163).
+// One thread per instance; state is [batch, 3] = [pos, vel, accel].
+// ---------------------------------------------------------------------------
+struct LipmStepParams {
+    int batch, N, n;
+    int substeps;          // integration substeps per control cycle (0: only write e and the goal)
+    int nb_dsp, nb_ssp;    // steps of a double / single support phase
+    double dt;             // integration step = sampling period / substeps
+    double foot_size, max_zmp;
+    void *state;           // [batch, 3] in/out
+    const void *U;         // [batch, n] plan of the cycle that just ended
+    const int *status;     // [batch] 0 = solved; otherwise the jerk is 0
+    void *support_foot;    // [batch] in/out: position of the support foot
+    const void *strides;   // [batch, 2]
+    int *phase_index;      // [batch] in/out
+    int *stride_index;     // [batch] in/out
+    void *e;               // [batch, N, 2] out: ZMP bounds of the next cycle
+    void *goal;            // [batch, 3] out
+    void *traj;            // optional [batch, 3] slot of the recorded trajectory
+    int *unsolved;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) lipm_step_kernel(const LipmStepParams p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    T *st = static_cast<T *>(p.state) + (size_t)b * 3;
+    T pos = st[0], vel = st[1], acc = st[2];
+    int index = p.phase_index[b], sidx = p.stride_index[b];
+    T foot = static_cast<T *>(p.support_foot)[b];
+    const T *strides = static_cast<const T *>(p.strides) + (size_t)b * 2;
+    const int cyc = p.nb_dsp + p.nb_ssp;
+    if (p.substeps > 0) {
+        const bool ok = p.status[b] == 0;
+        const T jerk = ok ? static_cast<const T *>(p.U)[(size_t)b * p.n] : T(0);
+        if (!ok && p.unsolved) atomicAdd(p.unsolved, 1);
+        const T dt = (T)p.dt;
+        for (int s = 0; s < p.substeps; ++s) {
+            // constant-jerk integration (:219-225)
+            const T p1 = pos + dt * (vel + dt * (acc / T(2) + dt * jerk / T(6)));
+            const T v1 = vel + dt * (acc + dt * (jerk / T(2)));
+            acc = acc + dt * jerk;
+            pos = p1;
+            vel = v1;
+        }
+        st[0] = pos, st[1] = vel, st[2] = acc;
+        // PhaseStepper.advance and the foot switch (:331-334)
+        index = index + 1 >= cyc ? 0 : index + 1;
+        if (index == 0) {
+            foot = foot + strides[sidx];
+            sidx = (sidx + 1) % 2;
+            static_cast<T *>(p.support_foot)[b] = foot;
+            p.stride_index[b] = sidx;
+        }
+        p.phase_index[b] = index;
+    }
+    if (p.traj) {
+        T *tr = static_cast<T *>(p.traj) + (size_t)b * 3;
+        tr[0] = pos, tr[1] = vel, tr[2] = acc;
+    }
+    // get_nb_steps (:132-163): lengths of the six phases that cover the horizon
+    int off = index;
+    const int n0 = max(0, p.nb_dsp - off);
+    off = max(0, off - p.nb_dsp);
+    const int n1 = max(0, p.nb_ssp - off);
+    int rem = p.N - n0 - n1;
+    const int n2 = min(p.nb_dsp, rem);
+    rem = max(0, rem - p.nb_dsp);
+    const int n3 = min(p.nb_ssp, rem);
+    rem = max(0, rem - p.nb_ssp);
+    const int n4 = min(p.nb_dsp, rem);
+    rem = max(0, rem - p.nb_dsp);
+    // (the sixth phase takes what is left: at most nb_ssp steps for horizons of two steps)
+    // update_goal_and_constraints (:175-205)
+    const T next = foot + strides[sidx];
+    const T last = next + strides[(sidx + 1) % 2];
+    const T hf = T(0.5) * (T)p.foot_size, big = (T)p.max_zmp;
+    T *e = static_cast<T *>(p.e) + (size_t)b * p.N * 2;
+    for (int k = 0; k < p.N; ++k) {
+        T hi = big, lo = big;
+        int j = k;
+        if (j < n0) {
+        } else if ((j -= n0) < n1) {
+            hi = foot + hf, lo = -(foot - hf);
+        } else if ((j -= n1) < n2) {
+        } else if ((j -= n2) < n3) {
+            hi = next + hf, lo = -(next - hf);
+        } else if ((j -= n3) < n4) {
+        } else {
+            hi = last + hf, lo = -(last - hf);
+        }
+        e[2 * k] = hi;
+        e[2 * k + 1] = lo;
+    }
+    T *gl = static_cast<T *>(p.goal) + (size_t)b * 3;
+    gl[0] = n4 > 0 ? last : next;
+    gl[1] = T(0);
+    gl[2] = T(0);
+}
+
 }  // namespace qpmpc

@@ -550,6 +550,52 @@ int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_o
     return (int)cudaGetLastError();
 }
 
+int qpmpc_b200_lipm_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in,
+                                const qpmpc_b200_outputs *out, const qpmpc_b200_lipm_loop *loop, void *stream) {
+    if (!d || !in || !out || !loop) return QPMPC_B200_EINVAL;
+    if (d->nx != 3 || d->nu != 1 || d->nc != 2) return QPMPC_B200_ESHAPE;
+    if (d->mode_x0 != QPMPC_B200_VEC_BATCH || d->mode_goal != QPMPC_B200_VEC_BATCH || d->mode_e != QPMPC_B200_BATCH_LTV)
+        return QPMPC_B200_EINVAL;
+    if (!in->x0 || !in->goal || !in->e || !loop->support_foot || !loop->strides || !loop->phase_index ||
+        !loop->stride_index || !out->U || !out->status)
+        return QPMPC_B200_EINVAL;
+    if (loop->cycles < 0 || loop->substeps <= 0 || !(loop->sampling_period > 0.0) || loop->nb_dsp_steps < 0 ||
+        loop->nb_ssp_steps <= 0 || 2 * (loop->nb_dsp_steps + loop->nb_ssp_steps) < d->N)
+        return QPMPC_B200_EINVAL;  // more than two steps in the receding horizon (:108-111)
+    if (d->batch == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LipmStepParams pp;
+    pp.batch = d->batch, pp.N = d->N, pp.n = d->N * d->nu;
+    pp.nb_dsp = loop->nb_dsp_steps, pp.nb_ssp = loop->nb_ssp_steps;
+    pp.dt = loop->sampling_period / loop->substeps;
+    pp.foot_size = loop->foot_size, pp.max_zmp = loop->max_zmp_dist;
+    pp.state = const_cast<void *>(in->x0);
+    pp.U = out->U, pp.status = out->status;
+    pp.support_foot = loop->support_foot, pp.strides = loop->strides;
+    pp.phase_index = loop->phase_index, pp.stride_index = loop->stride_index;
+    pp.e = const_cast<void *>(in->e), pp.goal = const_cast<void *>(in->goal);
+    pp.unsolved = loop->unsolved;
+    const size_t es = d->dtype == QPMPC_B200_F64 ? 8 : 4;
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    auto step = [&](int substeps, int slot) {
+        pp.substeps = substeps;
+        pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 3 * es : nullptr;
+        if (d->dtype == QPMPC_B200_F64)
+            lipm_step_kernel<double><<<grid, threads, 0, s>>>(pp);
+        else
+            lipm_step_kernel<float><<<grid, threads, 0, s>>>(pp);
+        count_launch();
+    };
+    step(0, 0);  // bounds and goal of the first cycle
+    for (int c = 0; c < loop->cycles; ++c) {
+        int rc = loop->record ? qpmpc_b200_solve_factored(d, in, loop->record, out, stream)
+                              : qpmpc_b200_solve(d, in, out, stream);
+        if (rc) return rc;
+        step(loop->substeps, c + 1);
+    }
+    return (int)cudaGetLastError();
+}
+
 int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
                           int device) {
     int rc = check_desc(d, in);

@@ -132,6 +132,78 @@ def pendulum_batch(batch: int, N: int = 12, seed: int = 1, T: float = 0.1, max_a
                 v_target=v, T=T)
 
 
+def lipm_walking_batch(batch: int, N: int = 16, seed: int = 4, T: float = 0.1, com_height: float = 0.84) -> Dict:
+    """The walking controller of ``examples/lipm_walking_controller.py`` (reference tree) for a
+    batch: shared triple-integrator model with T = 0.1 s and ZMP rows C = [+zmp; -zmp]
+    (:62-101), per-instance strides, initial support foot and initial phase.  e (per instance
+    and step) and the goal are rewritten every cycle by the phase machine; the arrays here are
+    those of the first cycle (:func:`lipm_phase_vectors`).  Parameters of :31-59."""
+    rng = np.random.default_rng(seed)
+    A = np.array([[1.0, T, T**2 / 2.0], [0.0, 1.0, T], [0.0, 0.0, 1.0]])
+    B = np.array([[T**3 / 6.0], [T**2 / 2.0], [T]])
+    omega2 = GRAVITY / com_height
+    zmp = np.array([1.0, 0.0, -1.0 / omega2])
+    C = np.array([+zmp, -zmp])
+    stride = rng.uniform(0.12, 0.24, batch)
+    strides = np.stack([-stride, stride], axis=1)           # :47  strides = [-0.18, 0.18]
+    foot = rng.uniform(0.07, 0.11, batch)                   # :42  init_support_foot_pos = 0.09
+    phase_index = rng.integers(3, 7, batch).astype(np.int32)  # :116 initial_index = 5
+    stride_index = np.zeros(batch, dtype=np.int32)
+    # initial ZMP at the centre of the initial foothold, DCM halfway (:296-299)
+    omega = np.sqrt(omega2)
+    x0 = np.stack([np.zeros(batch), 0.5 * omega * foot, -omega2 * foot], axis=1)
+    w = dict(name="lipm_walking", batch=batch, N=N, nx=3, nu=1, nc=2, A=A, B=B, C=C, D=None, e=None, x0=x0,
+             goal=None, targets=None, w_t=1.0, w_x=None, w_u=1e-3, ltv=(), T=T, strides=strides,
+             support_foot=foot, phase_index=phase_index, stride_index=stride_index, foot_size=0.065,
+             nb_dsp=int(round(0.1 / T)), nb_ssp=int(round(0.7 / T)), max_zmp=100.0)
+    w["e"], w["goal"] = lipm_phase_vectors(w, foot, phase_index, stride_index)
+    return w
+
+
+def lipm_phase_vectors(w: Dict, foot, phase_index, stride_index):
+    """(e [B, N, 2], goal [B, 3]) of one control cycle: ``update_goal_and_constraints``
+    (``examples/lipm_walking_controller.py:175-205``) with ``PhaseStepper.get_nb_steps``
+    (:132-163), vectorised over the instances."""
+    N, nd, ns, B = w["N"], w["nb_dsp"], w["nb_ssp"], len(foot)
+    off = phase_index.astype(np.int64)
+    n0 = np.maximum(0, nd - off)
+    off = np.maximum(0, off - nd)
+    n1 = np.maximum(0, ns - off)
+    rem = N - n0 - n1
+    n2 = np.minimum(nd, rem)
+    rem = np.maximum(0, rem - nd)
+    n3 = np.minimum(ns, rem)
+    rem = np.maximum(0, rem - ns)
+    n4 = np.minimum(nd, rem)
+    rows = np.arange(B)
+    nxt = foot + w["strides"][rows, stride_index]
+    last = nxt + w["strides"][rows, (stride_index + 1) % 2]
+    hf, big = 0.5 * w["foot_size"], w["max_zmp"]
+    k = np.arange(N)[None, :]
+    c0, c1, c2, c3, c4 = (np.cumsum([n0, n1, n2, n3, n4], axis=0)[i][:, None] for i in range(5))
+    centre = np.where(k < c1, foot[:, None], np.where(k < c3, nxt[:, None], last[:, None]))
+    free = (k < c0) | ((k >= c1) & (k < c2)) | ((k >= c3) & (k < c4))
+    e = np.stack([np.where(free, big, centre + hf), np.where(free, big, -(centre - hf))], axis=2)
+    goal = np.stack([np.where(n4 > 0, last, nxt), np.zeros(B), np.zeros(B)], axis=1)
+    return e, goal
+
+
+def lipm_advance(w: Dict, x, u, foot, phase_index, stride_index, substeps: int = 15):
+    """State, support foot and phase after one control cycle under jerk u: ``integrate``
+    (``examples/lipm_walking_controller.py:208-226``), ``PhaseStepper.advance`` (:124-130) and
+    the foot switch (:331-334), vectorised."""
+    dt = w["T"] / substeps
+    p, v, a = x[:, 0].copy(), x[:, 1].copy(), x[:, 2].copy()
+    for _ in range(substeps):
+        p, v, a = (p + dt * (v + dt * (a / 2 + dt * u / 6)), v + dt * (a + dt * (u / 2)), a + dt * u)
+    index = np.where(phase_index + 1 >= w["nb_dsp"] + w["nb_ssp"], 0, phase_index + 1).astype(np.int32)
+    switch = index == 0
+    rows = np.arange(len(foot))
+    foot = np.where(switch, foot + w["strides"][rows, stride_index], foot)
+    stride_index = np.where(switch, (stride_index + 1) % 2, stride_index).astype(np.int32)
+    return np.stack([p, v, a], axis=1), foot, index, stride_index
+
+
 def random_batch(batch: int, N: int, nx: int, nu: int, nc: int, seed: int = 0, with_C: bool = True,
                  with_D: bool = True, w_t: Optional[float] = 0.7, w_x: Optional[float] = 0.3,
                  w_u: float = 1e-2, ltv: bool = True) -> Dict:

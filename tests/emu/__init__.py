@@ -237,6 +237,11 @@ class EmulatedLibrary:
         with _Checked() as lib:
             return lib.emu_pendulum_closed_loop(desc, ops, outs, loop)
 
+    def qpmpc_b200_lipm_closed_loop(self, desc, ops, outs, loop, stream):
+        self.calls += 1
+        with _Checked() as lib:
+            return lib.emu_lipm_closed_loop(desc, ops, outs, loop)
+
     def qpmpc_b200_strerror(self, code):
         return f"emulated engine: error {code}".encode()
 

@@ -526,4 +526,34 @@ int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands
     return 0;
 }
 
+int emu_lipm_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
+                         const qpmpc_b200_lipm_loop *loop) {
+    if (!d || !in || !out || !loop || d->nx != 3 || d->nu != 1 || d->nc != 2 || d->dtype != QPMPC_B200_F64)
+        return QPMPC_B200_EINVAL;
+    LipmStepParams pp;
+    pp.batch = d->batch, pp.N = d->N, pp.n = d->N * d->nu;
+    pp.nb_dsp = loop->nb_dsp_steps, pp.nb_ssp = loop->nb_ssp_steps;
+    pp.dt = loop->sampling_period / loop->substeps;
+    pp.foot_size = loop->foot_size, pp.max_zmp = loop->max_zmp_dist;
+    pp.state = const_cast<void *>(in->x0);
+    pp.U = out->U, pp.status = out->status;
+    pp.support_foot = loop->support_foot, pp.strides = loop->strides;
+    pp.phase_index = loop->phase_index, pp.stride_index = loop->stride_index;
+    pp.e = const_cast<void *>(in->e), pp.goal = const_cast<void *>(in->goal);
+    pp.unsolved = loop->unsolved;
+    const int threads = 128, grid = (d->batch + threads - 1) / threads;
+    auto step = [&](int substeps, int slot) {
+        pp.substeps = substeps;
+        pp.traj = loop->trajectory ? static_cast<char *>(loop->trajectory) + (size_t)slot * d->batch * 3 * 8 : nullptr;
+        launch(grid, threads, 0, [&]() { lipm_step_kernel<double>(pp); });
+    };
+    step(0, 0);
+    for (int c = 0; c < loop->cycles; ++c) {
+        const int rc = loop->record ? emu_solve_factored(d, in, loop->record, out, 0) : emu_solve(d, in, out, 0);
+        if (rc) return rc;
+        step(loop->substeps, c + 1);
+    }
+    return 0;
+}
+
 }  // extern "C"

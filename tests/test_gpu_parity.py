@@ -567,3 +567,41 @@ def test_factored_model_matches_the_full_path_on_the_device():
         assert torch.equal(fast.iters, full.iters)
         U = fast.inputs.reshape(w["batch"], -1).cpu().numpy()
         assert np.abs(U[ok] - ref["U"][ok]).max() <= U_TOL
+
+
+@pytest.mark.parametrize("factored", [False, True])
+def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored):
+    """The walking controller of examples/lipm_walking_controller.py:307-335 (LTV constraint
+    vector rewritten every cycle by the phase machine, goal update, 300 cycles), 256 instances
+    on the device against the CPU loop (numpy phase machine + oracle): states of every cycle,
+    support foot and phase at the end."""
+    import torch
+
+    from qpmpc_b200 import factor_model, lipm_walking_closed_loop
+    from qpmpc_b200.workloads import lipm_advance, lipm_phase_vectors, lipm_walking_batch, to_batched
+
+    B, cycles = 256, 300
+    w = lipm_walking_batch(B, seed=4)
+    x, foot = w["x0"].copy(), w["support_foot"].copy()
+    pidx, sidx = w["phase_index"].copy(), w["stride_index"].copy()
+    ref, wc, active = [x.copy()], dict(w), 0
+    for _ in range(cycles):
+        wc["x0"] = x
+        wc["e"], wc["goal"] = lipm_phase_vectors(wc, foot, pidx, sidx)
+        sol = _oracle(wc)
+        assert (sol["status"] == 0).all()
+        active += int((sol["iters"] > 0).sum())
+        x, foot, pidx, sidx = lipm_advance(wc, x, sol["U"][:, 0], foot, pidx, sidx)
+        ref.append(x.copy())
+    ref = np.stack(ref)
+    prob = to_batched(w)
+    model = factor_model(prob) if factored else None
+    plan, traj, unsolved, phase = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
+                                                           w["stride_index"], cycles, record=True, factored=model)
+    torch.cuda.synchronize()
+    assert int(unsolved.item()) == 0
+    assert np.abs(traj.cpu().numpy() - ref).max() <= 1e-6
+    assert np.abs(phase["support_foot"].cpu().numpy() - foot).max() <= 1e-12
+    assert np.array_equal(phase["phase_index"].cpu().numpy(), pidx)
+    assert np.array_equal(phase["stride_index"].cpu().numpy(), sidx)
+    assert active > 0.5 * B * cycles  # the ZMP bounds bind in most cycles: not a degenerate workload

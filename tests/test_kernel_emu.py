@@ -511,3 +511,61 @@ def test_factored_model_is_refused_where_it_does_not_apply(emulated_engine):
     a, b = to_batched(pendulum_batch(5, seed=1)), to_batched(pendulum_batch(5, seed=2, T=0.12))
     with pytest.raises(ProblemDefinitionError):
         solve_mpc_batch(b, factored=factor_model(a))                       # another model's record
+
+
+# -- LIPM walking controller: closed loop with per-cycle rewritten LTV constraints --------------
+
+def _cpu_walking_loop(w, cycles):
+    """examples/lipm_walking_controller.py:307-335 on the CPU: numpy phase machine, oracle solve."""
+    from qpmpc_b200.workloads import lipm_advance, lipm_phase_vectors
+
+    x, foot = w["x0"].copy(), w["support_foot"].copy()
+    pidx, sidx = w["phase_index"].copy(), w["stride_index"].copy()
+    traj, w = [x.copy()], dict(w)
+    for _ in range(cycles):
+        w["x0"] = x
+        w["e"], w["goal"] = lipm_phase_vectors(w, foot, pidx, sidx)
+        ref = _oracle(w)
+        assert (ref["status"] == 0).all()
+        x, foot, pidx, sidx = lipm_advance(w, x, ref["U"][:, 0], foot, pidx, sidx)
+        traj.append(x.copy())
+    return np.stack(traj), foot, pidx, sidx
+
+
+@pytest.mark.parametrize("factored", [False, True])
+def test_lipm_walking_closed_loop_matches_the_cpu_loop(factored, emulated_engine, monkeypatch):
+    """The walking loop (phase machine + solve + constant-jerk integration) on the emulated
+    device against the CPU loop: states, support foot and phase after 40 cycles (five foot
+    switches), with the model re-condensed every cycle or factored once."""
+    from qpmpc_b200 import factor_model, lipm_walking_closed_loop
+    from qpmpc_b200.workloads import lipm_walking_batch, to_batched
+
+    monkeypatch.setenv("QPMPC_B200_LR", "0")
+    w = lipm_walking_batch(6, seed=4)
+    ref, foot, pidx, sidx = _cpu_walking_loop(w, 40)
+    prob = to_batched(w)
+    model = factor_model(prob) if factored else None
+    plan, traj, unsolved, phase = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
+                                                           w["stride_index"], 40, record=True, factored=model)
+    assert int(unsolved.item()) == 0
+    assert np.abs(traj.numpy() - ref).max() <= 1e-6
+    assert np.abs(phase["support_foot"].numpy() - foot).max() <= 1e-12
+    assert np.array_equal(phase["phase_index"].numpy(), pidx) and np.array_equal(phase["stride_index"].numpy(), sidx)
+    # lateral sway (the strides alternate in sign): the centre of mass moves and stays between the feet
+    pos = traj[:, :, 0].numpy()
+    assert np.abs(pos).max() < 0.3 and np.abs(pos).max(axis=0).min() > 0.01
+
+
+def test_lipm_phase_vectors_follow_the_reference_pattern():
+    """e_k and the goal of the first cycle for the reference's own parameters (index 5, foot
+    0.09, strides -+0.18): 3 steps of the current single support, 1 free, 7 on the next foot,
+    1 free, 4 on the last foot; goal on the last foot."""
+    from qpmpc_b200.workloads import lipm_phase_vectors, lipm_walking_batch
+
+    w = lipm_walking_batch(1)
+    w["strides"] = np.array([[-0.18, 0.18]])
+    e, goal = lipm_phase_vectors(w, np.array([0.09]), np.array([5], dtype=np.int32), np.array([0], dtype=np.int32))
+    big, hf = 100.0, 0.0325
+    expect = [(0.09 + hf, -(0.09 - hf))] * 3 + [(big, big)] + [(-0.09 + hf, 0.09 + hf)] * 7 + [(big, big)] \
+        + [(0.09 + hf, -(0.09 - hf))] * 4
+    assert np.allclose(e[0], np.array(expect)) and np.allclose(goal[0], [0.09, 0.0, 0.0])
