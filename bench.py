@@ -356,7 +356,7 @@ def measured_profile(args):
     launch executed (opcode counts of the profiler) per solve.  Missing entries are None --
     never a constant."""
     want = kernel_name(args).split("<")[0]
-    tag = {2: "ti16", 3: "pend", 4: "hum", 5: f"ti{args.horizon}"}[args.config]
+    tag = {2: "ti16", 3: "pend", 4: "hum", 5: f"ti{args.horizon}", 6: "walk"}[args.config]
     best = {"traffic": None, "flops_per_solve": None, "source": None}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_*.txt"))):
         base = os.path.basename(path)
