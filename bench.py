@@ -253,6 +253,59 @@ def cpu_loop(args, workload, cycles, threads):
     return (cpu_closed_loop if args.config == 3 else cpu_walking_loop)(workload, cycles, threads)
 
 
+def reference_python_condense(seconds=2.0):
+    """the reference's OWN condensing (qpmpc.MPCQP, pure Python /
+    NumPy) on one core, timed when the reference tree is importable (the development container);
+    elsewhere (the GPU box has no copy of it) the container measurement of BASELINE.md is quoted.
+    The solver half of the reference (qpsolvers wheels) is not installable offline."""
+    ref_root = os.environ.get("QPMPC_REFERENCE", "/root/reference")
+    quoted = {"mpcqp_build_us": 553.0, "builds_per_s_per_core": 1.0e6 / 553.0,
+              "source": "quoted: BASELINE.md section 2 (measured in the development container; the reference "
+                        "tree is not present on this machine)"}
+    if not os.path.isdir(os.path.join(ref_root, "qpmpc")):
+        return quoted
+    try:
+        import importlib
+        import types
+
+        stub = types.ModuleType("qpsolvers")
+        stub.Problem = lambda *a, **k: None
+        stub.Solution = object
+        stub.solve_problem = lambda *a, **k: None
+        saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "qpsolvers" or k.split(".")[0] == "qpmpc"}
+        for k in list(saved):
+            sys.modules.pop(k, None)
+        sys.modules["qpsolvers"] = stub
+        sys.path.insert(0, ref_root)
+        try:
+            ref = importlib.import_module("qpmpc")
+            T = 1.0 / 16
+            prob = ref.MPCProblem(
+                transition_state_matrix=np.array([[1.0, T, T**2 / 2.0], [0.0, 1.0, T], [0.0, 0.0, 1.0]]),
+                transition_input_matrix=np.array([T**3 / 6.0, T**2 / 2.0, T]).reshape((3, 1)),
+                ineq_state_matrix=np.array([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0]]), ineq_input_matrix=None,
+                ineq_vector=np.array([3.0, 3.0]), initial_state=np.zeros(3), goal_state=np.array([1.0, 0.0, 0.0]),
+                nb_timesteps=16, terminal_cost_weight=1.0, stage_state_cost_weight=None, stage_input_cost_weight=1e-6)
+            ref.MPCQP(prob)
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < seconds:
+                ref.MPCQP(prob)
+                n += 1
+            us = (time.perf_counter() - t0) / n * 1e6
+        finally:
+            sys.path.remove(ref_root)
+            for k in [k for k in sys.modules if k == "qpsolvers" or k.split(".")[0] == "qpmpc"]:
+                sys.modules.pop(k, None)
+            for k, v in saved.items():
+                if v is not None:
+                    sys.modules[k] = v
+        return {"mpcqp_build_us": us, "builds_per_s_per_core": 1e6 / us,
+                "source": f"measured here: {n} x qpmpc.MPCQP(triple integrator N=16) from {ref_root}, one core"}
+    except Exception as exc:  # noqa: BLE001
+        quoted["source"] += f" [import failed: {type(exc).__name__}]"
+        return quoted
+
+
 def cpu_arm(args, workload, seconds):
     """Time the oracle on a bounded sample of the workload for about `seconds`;
     returns (solves/s, threads, sample description)."""
@@ -322,7 +375,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_of(args),
         "data": "synthetic", "config": config_dict(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "reference_python": reference_python_condense()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "instances_per_step": per_step,
         "note": "reference is pure Python over qpsolvers/proxqp wheels that are not installable "
@@ -793,7 +847,8 @@ def run_b200(args, rank, local_rank, world):
             "launches_per_step": 2 * CYCLES + 1}
     if not args.no_cpu_baseline:
         v, threads, sample = cpu_arm(args, sets[0], args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                "reference_python": reference_python_condense()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

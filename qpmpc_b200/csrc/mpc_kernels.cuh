@@ -45,6 +45,10 @@
 #ifndef QPMPC_MINB_PAIRED
 #define QPMPC_MINB_PAIRED 2
 #endif
+// ... and the largest CTA they are launched with (threads)
+#ifndef QPMPC_THREADS_PAIRED
+#define QPMPC_THREADS_PAIRED 256
+#endif
 #ifndef QPMPC_SYNC_TAIL
 #define QPMPC_SYNC_TAIL 1
 #endif
@@ -662,9 +666,10 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 //     step (x += t J2 d2), as in the textbook method.
 // ---------------------------------------------------------------------------
 template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false, bool PRE = false>  // @phase kernel prologue
-__global__ void __launch_bounds__(256, (NP <= 16 && MREG)
-                                           ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : (PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
-                                           : 1)
+__global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8) ? QPMPC_THREADS_PAIRED : 256,
+                                  (NP <= 16 && MREG)
+                                      ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : (PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
+                                      : 1)
     mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, MREG, RS, PAIRED, PRE>;
     using T2 = typename Pair<T>::type;
