@@ -143,9 +143,15 @@ __device__ __forceinline__ void inv_lower_small(const T (&l)[NX * NX], T (&out)[
 #ifndef QPMPC_LR_MINB
 #define QPMPC_LR_MINB 4
 #endif
+// the same for the one-warp variant (NP = 32): 16 one-warp CTAs per SM at 128 registers -- measured
+// 39 -> 62 M solves/s at N = 32 against 8 CTAs at 196 registers (latency-bound: occupancy pays);
+// a packed triangular R^-1 (more CTAs by shared memory) was measured slower at equal occupancy
+#ifndef QPMPC_LR_MINB32
+#define QPMPC_LR_MINB32 16
+#endif
 
 template <typename T, int NP, int NX>  // @phase LR kernel
-__global__ void __launch_bounds__(NP, NP == 32 ? 8 : QPMPC_LR_MINB) mpc_solve_lr_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(NP, NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB) mpc_solve_lr_kernel(const SolveParams p) {
     using L = LrLay<T, NP>;
     using T2 = typename Pair<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
