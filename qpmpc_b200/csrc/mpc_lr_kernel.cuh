@@ -487,14 +487,17 @@ __global__ void __launch_bounds__(NP, NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB
         if (NP == 32) __syncwarp();
         const T a2 = a2v[0];
         // -G z = M2 m2 for the owned row
-        T gz0 = T(0), gz1 = T(0);
+        T gz0 = T(0), gz1 = T(0), gz2 = T(0), gz3 = T(0);  // four chains: the kernel is latency-bound
 #pragma unroll
-        for (int c = 0; c < NP; c += 2) {
+        for (int c = 0; c < NP; c += 4) {
             const T2 v = *reinterpret_cast<const T2 *>(d2 + c);
+            const T2 w = *reinterpret_cast<const T2 *>(d2 + c + 2);
             gz0 += Mrow[c] * v.x;
             gz1 += Mrow[c + 1] * v.y;
+            gz2 += Mrow[c + 2] * w.x;
+            gz3 += Mrow[c + 3] * w.y;
         }
-        const T gz = gz0 + gz1;
+        const T gz = (gz0 + gz1) + (gz2 + gz3);
         // -r = R^-1 m1 (component l; zero on threads >= na)
         T rv = T(0);
         {
