@@ -58,6 +58,8 @@ struct SolveParams {
     void *P, *q, *G, *h, *Phi, *Psi, *phi_last, *psi_last;
     // shared-model fast path (mpc_factor.cuh): the record of the model, staged once per CTA
     const void *record;
+    // condense-only CTA kernel: 1 = do not accumulate P (the tensor-core kernel computes it)
+    int skip_P;
 };
 
 template <typename T> struct Pair;

@@ -260,7 +260,7 @@ __device__ void cta_condense(const SolveParams &p, const CtaLay &L, T *sm, long 
         const T *xb = xbar + cur * nx;
         const bool last = (k == N);
         const T w = last ? w_t : w_x;
-        const bool inP = last ? p.has_wt : p.has_wx;
+        const bool inP = !p.skip_P && (last ? p.has_wt : p.has_wx);
         const bool inq = last ? p.q_wt : p.q_wx;
         const T *ref = last ? goal : (tgt ? tgt + k * nx : nullptr);
         if (!last) {

@@ -12,6 +12,7 @@
 
 #include "mpc_cta_kernel.cuh"
 #include "mpc_factor.cuh"
+#include "mpc_hessian_tc.cuh"
 #include "mpc_host_params.h"
 #include "mpc_integrate.cuh"
 #include "mpc_launch.cuh"
@@ -363,8 +364,30 @@ int qpmpc_b200_condense(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in,
     p.psi_last = out->psi_last;
     Variant v;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (use_cta(p.n, p.m, &v))
-        return d->dtype == QPMPC_B200_F64 ? launch_condense_cta<double>(p, s) : launch_condense_cta<float>(p, s);
+    if (use_cta(p.n, p.m, &v)) {
+        // Single precision, a horizon that fills a tensor-core tile (32 < n <= 64) and a stage cost:
+        // the Psi' Q Psi contraction of P runs on tcgen05 (mpc_hessian_tc.cuh) from the Psi stack
+        // the condensing kernel has just written.  QPMPC_B200_HESSIAN_TC=0 keeps the SIMT sum.
+        const bool tc = d->dtype == QPMPC_B200_F32 && p.n > 32 && p.n <= 64 && p.has_wx && out->P && out->Psi &&
+                        (out->psi_last || !p.has_wt) && env_int("QPMPC_B200_HESSIAN_TC", 1) != 0;
+        if (tc) p.P = nullptr, p.skip_P = 1;
+        rc = d->dtype == QPMPC_B200_F64 ? launch_condense_cta<double>(p, s) : launch_condense_cta<float>(p, s);
+        if (rc || !tc) return rc;
+        HessianTcParams hp;
+        hp.batch = d->batch, hp.N = d->N, hp.nx = d->nx, hp.n = p.n;
+        hp.has_wt = p.has_wt, hp.has_wx = p.has_wx;
+        hp.w_t = (float)p.w_t, hp.w_x = (float)p.w_x, hp.w_u = (float)p.w_u;
+        hp.Psi = static_cast<const float *>(out->Psi);
+        hp.psi_last = static_cast<const float *>(out->psi_last);
+        hp.P = static_cast<float *>(out->P);
+        const size_t smem = hessian_tc_smem_bytes(d->N, d->nx, p.has_wt, p.has_wx);
+        if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+        cudaError_t err = cudaFuncSetAttribute(mpc_hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        mpc_hessian_tc_kernel<<<d->batch, 128, smem, s>>>(hp);
+        count_launch();
+        return (int)cudaGetLastError();
+    }
     return d->dtype == QPMPC_B200_F64 ? dispatch_condense<double>(p, v, s) : dispatch_condense<float>(p, v, s);
 }
 

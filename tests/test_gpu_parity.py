@@ -605,3 +605,49 @@ def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored):
     assert np.array_equal(phase["phase_index"].cpu().numpy(), pidx)
     assert np.array_equal(phase["stride_index"].cpu().numpy(), sidx)
     assert active > 0.5 * B * cycles  # the ZMP bounds bind in most cycles: not a degenerate workload
+
+
+@pytest.mark.parametrize("N,ltv", [(64, False), (64, True), (40, True), (33, False)])
+def test_tensor_core_hessian_matches_the_simt_sum_and_the_oracle(N, ltv, monkeypatch):
+    """Single precision, 32 < n <= 64, stage cost: P = w_u I + w_x Psi'Psi + w_t psi_N'psi_N of
+    ``condense_batch`` comes from tcgen05.mma.kind::tf32 with a hi/lo split of the operands
+    (mpc_hessian_tc.cuh).  Bar: 2e-6 relative to max|P| against the fp64 oracle -- the SIMT fp32
+    sum (QPMPC_B200_HESSIAN_TC=0) is held to the same bar -- i.e. the split recovers full fp32
+    accuracy from TF32 products; the other fields are untouched."""
+    import torch
+
+    import oracle
+    from qpmpc_b200 import _capi, condense_batch
+    from qpmpc_b200.workloads import oracle_ops, to_batched, triple_integrator_batch
+
+    B = 70
+    # a model whose powers stay bounded over the horizon: triple integrator, 1 s horizon, stage cost
+    w = triple_integrator_batch(B, N=N, seed=N, per_instance_model=False)
+    w["w_x"], w["w_t"], w["w_u"] = 0.5, 2.0, 1e-3
+    w["targets"] = np.random.default_rng(N).standard_normal((B, N * 3))
+    if ltv:
+        w["A"], w["B"] = np.tile(w["A"], (N, 1, 1)), np.tile(w["B"], (N, 1, 1))
+        w["ltv"] = ("A", "B")
+    fields = ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last")
+    prob = to_batched(w, dtype=torch.float32)
+    before = _capi.launch_count()
+    tc = condense_batch(prob, fields)
+    torch.cuda.synchronize()
+    launches_tc = _capi.launch_count() - before
+    monkeypatch.setenv("QPMPC_B200_HESSIAN_TC", "0")
+    before = _capi.launch_count()
+    simt = condense_batch(prob, fields)
+    torch.cuda.synchronize()
+    assert launches_tc == (_capi.launch_count() - before) + 1  # the extra launch is the tensor-core kernel
+    ops = oracle_ops(w)
+    worst_tc = worst_simt = 0.0
+    for b in (0, 1, B - 1):
+        pick = lambda k: None if ops[k][0] is None else (ops[k][0][b] if ops[k][1] else ops[k][0])  # noqa: E731
+        ref = oracle.condense(w["N"], 3, 1, 2, pick("A"), pick("B"), pick("C"), None, pick("e"), w["x0"][b], w["goal"][b],
+                              w["targets"][b], w["w_t"], w["w_x"], w["w_u"])
+        scale = np.abs(ref["P"]).max()
+        worst_tc = max(worst_tc, np.abs(tc["P"][b].double().cpu().numpy() - ref["P"]).max() / scale)
+        worst_simt = max(worst_simt, np.abs(simt["P"][b].double().cpu().numpy() - ref["P"]).max() / scale)
+    assert worst_tc <= 2e-6 and worst_simt <= 1e-5, (worst_tc, worst_simt)
+    for k in fields[1:]:
+        assert torch.equal(tc[k], simt[k]), k
