@@ -24,6 +24,7 @@ int launch_solve_lr(SolveParams p, cudaStream_t stream) {
     return QPMPC_B200_ESHAPE;
 }
 
+template int launch_solve_lr<double, 16>(SolveParams, cudaStream_t);
 template int launch_solve_lr<double, 32>(SolveParams, cudaStream_t);
 template int launch_solve_lr<double, 64>(SolveParams, cudaStream_t);
 

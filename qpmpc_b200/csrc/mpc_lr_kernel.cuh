@@ -41,12 +41,16 @@ struct LrLay {
     static constexpr int fixed = oSc + 8 + 16;      // the staged inputs follow
 };
 
-// ---- reductions over the NP threads of the CTA (one or two warps) -----------------------------
+// ---- reductions over the NP threads of the CTA (half a warp, one warp or two) ------------------
 // `red` holds two sets of slots used alternately (parity), so one barrier per call is enough.
 template <int NP>
+struct LrMask {  // the lanes of a warp that exist: a CTA of 16 threads is half a warp
+    static constexpr unsigned value = NP >= 32 ? FULL_MASK : ((1u << (NP & 31)) - 1u);
+};
+template <int NP>
 __device__ __forceinline__ unsigned lr_max_u32(unsigned key, unsigned long long *red, int &par) {
-    key = __reduce_max_sync(FULL_MASK, key);  // REDUX
-    if (NP == 32) return key;
+    key = __reduce_max_sync(LrMask<NP>::value, key);  // REDUX
+    if (NP <= 32) return key;
     unsigned *slot = reinterpret_cast<unsigned *>(red + (par & 1) * 4);
     par ^= 1;
     if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = key;
@@ -58,10 +62,10 @@ template <int NP>
 __device__ __forceinline__ unsigned long long lr_min_u64(unsigned long long key, unsigned long long *red, int &par) {
     // two REDUX: the high words, then the low words of those that tie
     const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned mh = __reduce_min_sync(FULL_MASK, hi);
-    const unsigned ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xffffffffu);
+    const unsigned mh = __reduce_min_sync(LrMask<NP>::value, hi);
+    const unsigned ml = __reduce_min_sync(LrMask<NP>::value, hi == mh ? lo : 0xffffffffu);
     key = ((unsigned long long)mh << 32) | ml;
-    if (NP == 32) return key;
+    if (NP <= 32) return key;
     unsigned long long *slot = red + (par & 1) * 4;
     par ^= 1;
     if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = key;
@@ -72,11 +76,11 @@ __device__ __forceinline__ unsigned long long lr_min_u64(unsigned long long key,
 template <typename T, int NP, int NV>
 __device__ __forceinline__ void lr_sum(T (&v)[NV], T *red, int &par) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
+    for (int off = (NP >= 32 ? 16 : NP / 2); off > 0; off >>= 1) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(FULL_MASK, v[i], off);
+        for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(LrMask<NP>::value, v[i], off);
     }
-    if (NP == 32) return;
+    if (NP <= 32) return;
     static_assert(2 * NV <= 24, "reduction slots");
     T *slot = red + (par & 1) * 24;
     par ^= 1;
@@ -90,8 +94,8 @@ __device__ __forceinline__ void lr_sum(T (&v)[NV], T *red, int &par) {
 }
 template <int NP>
 __device__ __forceinline__ void lr_sync() {
-    if (NP == 32)
-        __syncwarp();
+    if (NP <= 32)
+        __syncwarp(LrMask<NP>::value);
     else
         __syncthreads();
 }
@@ -149,9 +153,14 @@ __device__ __forceinline__ void inv_lower_small(const T (&l)[NX * NX], T (&out)[
 #ifndef QPMPC_LR_MINB32
 #define QPMPC_LR_MINB32 16
 #endif
+// NP = 16: a CTA is HALF a warp (16 threads) -- lanes idle, but no second instance in lockstep,
+// no CTA tail and every branch uniform; a row of M is 32 registers, so more CTAs fit
+#ifndef QPMPC_LR_MINB16
+#define QPMPC_LR_MINB16 24
+#endif
 
 template <typename T, int NP, int NX>  // @phase LR kernel
-__global__ void __launch_bounds__(NP, NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB) mpc_solve_lr_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(NP, NP == 16 ? QPMPC_LR_MINB16 : NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB) mpc_solve_lr_kernel(const SolveParams p) {
     using L = LrLay<T, NP>;
     using T2 = typename Pair<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(NP, NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB
         d2[l] = d2l;  // the part of d outside the working set, zero-padded; the rest is read from draw
         T a2v[1] = {d2l * d2l};
         lr_sum<T, NP, 1>(a2v, redv, par);  // (its barrier also publishes d2)
-        if (NP == 32) __syncwarp();
+        if (NP <= 32) __syncwarp(LrMask<NP>::value);
         const T a2 = a2v[0];
         // -G z = M2 m2 for the owned row
         T gz0 = T(0), gz1 = T(0), gz2 = T(0), gz3 = T(0);  // four chains: the kernel is latency-bound
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(NP, NP == 32 ? QPMPC_LR_MINB32 : QPMPC_LR_MINB
         // smallest ratio, ties to the lowest position: the low 6 bits of the key carry the position
         unsigned long long kmin = ((unsigned long long)__double_as_longlong((double)cand) & ~63ull) | (unsigned)l;
         kmin = lr_min_u64<NP>(kmin, redk, par);  // (two warps: its barrier also publishes cands)
-        if (NP == 32) __syncwarp();
+        if (NP <= 32) __syncwarp(LrMask<NP>::value);
         const int lidx = (int)(kmin & 63ull);
         const T t1 = cands[lidx];
         const T violp = sc[0], dn2 = sc[1];
@@ -688,6 +697,10 @@ size_t lr_layout_smem(SolveParams *p) {
     p->input_elems = off;
     return 16 + ((size_t)L::fixed + off) * sizeof(T);
 }
+
+// Whether horizons 8 < n <= 16 take this kernel (half-warp CTAs) or the warp kernel
+// (QPMPC_B200_LR16 overrides).
+constexpr int LR16_DEFAULT = 0;
 
 // The shape the kernel handles (see the header of this file).
 inline bool lr_applicable(const SolveParams &p, bool paired) {

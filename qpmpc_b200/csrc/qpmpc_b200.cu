@@ -328,8 +328,10 @@ static int solve_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, c
     // Toeplitz G, one CTA of n threads per instance); QPMPC_B200_LR=0 switches it off.
     const int lr = env_int("QPMPC_B200_LR", -1);
     if (d->dtype == QPMPC_B200_F64 && lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 &&
-        lr_applicable(p, rows_paired(d)) && p.n > 16)
-        return p.n <= 32 ? launch_solve_lr<double, 32>(p, s) : launch_solve_lr<double, 64>(p, s);
+        lr_applicable(p, rows_paired(d)) && (p.n > 16 || (p.n > 8 && env_int("QPMPC_B200_LR16", LR16_DEFAULT) != 0)))
+        return p.n <= 16   ? launch_solve_lr<double, 16>(p, s)
+               : p.n <= 32 ? launch_solve_lr<double, 32>(p, s)
+                           : launch_solve_lr<double, 64>(p, s);
     if (use_cta(p.n, p.m, &v, rows_paired(d)))
         return d->dtype == QPMPC_B200_F64 ? launch_solve_cta<double>(p, s) : launch_solve_cta<float>(p, s);
     return d->dtype == QPMPC_B200_F64 ? dispatch_solve<double>(p, v, s) : dispatch_solve<float>(p, v, s);

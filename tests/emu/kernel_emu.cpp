@@ -245,8 +245,9 @@ int emu_solve_t(const qpmpc_b200_desc *d, SolveParams &p, int wpc) {
     const bool paired = d->paired != 0 && d->nc > 0 && (d->nc & 1) == 0 && env_int("QPMPC_B200_NO_PAIRED", 0) == 0;
     if constexpr (sizeof(T) == 8) {
         const int lr = env_int("QPMPC_B200_LR", -1);
-        if (lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 && lr_applicable(p, paired) && p.n > 16)
-            return p.n <= 32 ? solve_lr<T, 32>(p) : solve_lr<T, 64>(p);
+        if (lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 && lr_applicable(p, paired) &&
+            (p.n > 16 || (p.n > 8 && env_int("QPMPC_B200_LR16", LR16_DEFAULT) != 0)))
+            return p.n <= 16 ? solve_lr<T, 16>(p) : p.n <= 32 ? solve_lr<T, 32>(p) : solve_lr<T, 64>(p);
     }
     const bool warp_ok = pick_variant(p.n, p.m, &v, paired);
     if (!warp_ok || env_int("QPMPC_B200_FORCE_CTA", 0) != 0) {

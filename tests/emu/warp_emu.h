@@ -339,7 +339,11 @@ inline int emu_reduce_max_sync(int line, unsigned m, int v) {
 inline int emu_reduce_min_sync(int line, unsigned m, int v) {
     return emu::fold(line, m, v, [](int a, int b) { return a < b ? a : b; });
 }
-#define __syncwarp() emu_syncwarp(__LINE__)
+struct EmuSyncWarpAt {  // __syncwarp() and __syncwarp(mask) through one macro without GNU extensions
+    int line;
+    void operator()(unsigned mask = 0xffffffffu) const { emu_syncwarp(line, mask); }
+};
+#define __syncwarp(...) EmuSyncWarpAt{__LINE__}(__VA_ARGS__)
 #define __shfl_sync(...) emu_shfl_sync(__LINE__, __VA_ARGS__)
 #define __shfl_xor_sync(...) emu_shfl_xor_sync(__LINE__, __VA_ARGS__)
 #define __shfl_down_sync(...) emu_shfl_down_sync(__LINE__, __VA_ARGS__)

@@ -407,18 +407,25 @@ def test_unpaired_rows_are_not_taken_for_pairs():
 
 # -- structure-exploiting long-horizon kernel (mpc_lr_kernel.cuh) -----------------------------
 
-@pytest.mark.parametrize("kind", ["ti64", "ti48", "ti33", "humanoid40", "ti24_forced", "ti32_forced", "infeasible"])
+@pytest.mark.parametrize("kind", ["ti64", "ti48", "ti33", "humanoid40", "ti24_forced", "ti32_forced", "infeasible",
+                                  "ti16_half", "ti11_half", "humanoid16_half"])
 def test_low_rank_hessian_kernel(kind, monkeypatch):
     """Terminal-cost problems with n > 32 (and, with QPMPC_B200_LR=1, n > 16) run on the kernel
     that never factors the n x n Hessian: P = w_u I + w_t psi' psi, J from 3 x 3 algebra, rows of
     M in O(n nx).  Same exact answers and iteration counts as the oracle; multipliers too."""
     if kind.endswith("forced"):
         monkeypatch.setenv("QPMPC_B200_LR", "1")
+    if kind.endswith("half"):  # 8 < n <= 16: CTAs of 16 threads, half a warp
+        monkeypatch.setenv("QPMPC_B200_LR", "1")
+        monkeypatch.setenv("QPMPC_B200_LR16", "1")
     w = {"ti64": lambda: triple_integrator_batch(5, N=64, seed=21), "ti48": lambda: triple_integrator_batch(3, N=48, seed=22),
          "ti33": lambda: triple_integrator_batch(3, N=33, seed=23), "humanoid40": lambda: humanoid_batch(4, N=40, seed=24),
          "ti24_forced": lambda: triple_integrator_batch(4, N=24, seed=25),
          "ti32_forced": lambda: triple_integrator_batch(4, N=32, seed=26),
-         "infeasible": lambda: humanoid_batch(3, N=36, seed=27)}[kind]()
+         "infeasible": lambda: humanoid_batch(3, N=36, seed=27),
+         "ti16_half": lambda: triple_integrator_batch(9, N=16, seed=28),
+         "ti11_half": lambda: triple_integrator_batch(5, N=11, seed=29),
+         "humanoid16_half": lambda: humanoid_batch(5, N=16, seed=30)}[kind]()
     if kind == "infeasible":
         w["e"][1, 0, :] = [-0.5, -0.5]      # the k = 0 rows cannot be repaired (no D)
         w["e"][2, 20, :] = [0.05, -0.06]    # a pair that admits no point
