@@ -474,6 +474,35 @@ def flop_models(args, iters_mean):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: keep this rank's threads -- and so, by first touch, the host buffers it
+    allocates -- on the NUMA node its GPU hangs off (sysfs; None when the box does not say).
+    QPMPC_B200_BENCH_NUMA=0 switches it off."""
+    if os.environ.get("QPMPC_B200_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def run_b200(args, rank, local_rank, world):
     import ctypes
 
@@ -486,9 +515,11 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    numa_node = None
     if world > 1:
         import torch.distributed as dist
 
+        numa_node = bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     B, N = args.batch, args.horizon
@@ -644,6 +675,10 @@ def run_b200(args, rank, local_rank, world):
         if world > 1:
             U_job = torch.from_file(shm_path + "_U", shared=True, size=world * B * n, dtype=tdtype)
             st_job = torch.from_file(shm_path + "_st", shared=True, size=world * B, dtype=torch.int32)
+            # first touch: every rank faults its own rows in (on its NUMA node) before anybody pins
+            U_job[rank * B * n:(rank + 1) * B * n].zero_()
+            st_job[rank * B:(rank + 1) * B].zero_()
+            dist.barrier()
             cudart = torch.cuda.cudart()
             for t in (U_job, st_job):
                 rc = cudart.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
@@ -796,7 +831,7 @@ def run_b200(args, rank, local_rank, world):
                      "bytes_per_solve": bytes_per_solve,
                      "note": "latency/FP64-issue bound by design (SURVEY 8d): HBM fraction is "
                              "necessarily tiny; see fp64"},
-        "iters_mean": iters_mean, "gather": gather_kind,
+        "iters_mean": iters_mean, "gather": gather_kind, "numa_node": numa_node,
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }

@@ -272,11 +272,13 @@ int qpmpc_b200_lipm_closed_loop(const qpmpc_b200_desc *desc, const qpmpc_b200_op
                                 const qpmpc_b200_outputs *out, const qpmpc_b200_lipm_loop *loop,
                                 void *stream);
 
-/* Scratch the device entry points need from the caller: none (0) today; kept
- * in the ABI so a future kernel can ask for it without a signature change. */
+/* Scratch the device entry points need from the caller: none (0).  Shapes whose
+ * matrices exceed shared memory (n > 72 in fp64 with m = 2 n) take a workspace
+ * the library allocates and frees in stream order (cudaMallocAsync) itself. */
 size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *desc);
 
-/* Largest n = N*nu and m = N*nc the compiled kernels accept for this dtype. */
+/* Largest n = N*nu and m = N*nc the kernels accept for this dtype (n <= 512,
+ * m <= 4096; beyond 227 KB of matrices the CTA kernel works out of global memory). */
 int qpmpc_b200_max_vars(int dtype);
 int qpmpc_b200_max_rows(int dtype, int n);
 

@@ -60,6 +60,8 @@ struct SolveParams {
     const void *record;
     // condense-only CTA kernel: 1 = do not accumulate P (the tensor-core kernel computes it)
     int skip_P;
+    // CTA kernels, shapes beyond shared memory: global-memory home of the matrices (nullptr: shared memory)
+    void *workspace;
 };
 
 template <typename T> struct Pair;

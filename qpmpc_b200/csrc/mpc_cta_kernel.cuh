@@ -125,13 +125,13 @@ __device__ __forceinline__ const T *operand(const SolveParams &p, int o, long lo
 // Scratch: W, XB in the R^-1 region, the prefix-sum table in the J region.
 // ---------------------------------------------------------------------------
 template <typename T>  // @phase CTA condense (time-invariant model)
-__device__ void cta_condense_lti(const SolveParams &p, const CtaLay &L, T *sm, long long inst) {
+__device__ void cta_condense_lti(const SolveParams &p, const CtaLay &L, T *mat, T *vec, long long inst) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nx = p.nx, nu = p.nu, nc = p.nc, N = p.N, n = p.n, m = p.m, ld = L.ld;
-    T *M = sm + L.oM, *PL = sm + L.oPL, *Tt = sm + L.oJ;
-    T *W = sm + L.oRi;            // [nx][n]
+    T *M = mat + L.oM, *PL = mat + L.oPL, *Tt = mat + L.oJ;
+    T *W = mat + L.oRi;           // [nx][n]
     T *XB = W + nx * n;           // [N + 1][nx]
-    T *hs = sm + L.o_hs, *q = sm + L.o_q;
+    T *hs = vec + L.o_hs, *q = vec + L.o_q;
     const T *A = operand<T>(p, OP_A, inst), *B = operand<T>(p, OP_B, inst);
     const T *C = operand<T>(p, OP_C, inst), *D = operand<T>(p, OP_D, inst);
     const T *e = operand<T>(p, OP_E, inst), *x0 = operand<T>(p, OP_X0, inst);
@@ -232,11 +232,11 @@ __device__ void cta_condense_lti(const SolveParams &p, const CtaLay &L, T *sm, l
 }
 
 template <typename T, bool DUMP>  // @phase CTA condense
-__device__ void cta_condense(const SolveParams &p, const CtaLay &L, T *sm, long long inst) {
+__device__ void cta_condense(const SolveParams &p, const CtaLay &L, T *mat, T *vec, long long inst) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nx = p.nx, nu = p.nu, nc = p.nc, N = p.N, n = p.n, ld = L.ld;
-    T *M = sm + L.oM, *PL = sm + L.oPL, *scr = sm + L.oRi;
-    T *hs = sm + L.o_hs, *q = sm + L.o_q;
+    T *M = mat + L.oM, *PL = mat + L.oPL, *scr = mat + L.oRi;
+    T *hs = vec + L.o_hs, *q = vec + L.o_q;
     T *psi = scr;                   // [2][nx][n]
     T *xbar = psi + 2 * nx * n;     // [2][nx]
     T *phi = xbar + 2 * nx;         // [2][nx][nx]
@@ -372,32 +372,50 @@ __device__ __forceinline__ void row_fsolve(const T *PL, const T *dv, int ld, int
     }
 }
 
+// Where the matrices (M, J, L / R, R^-1) and the vectors of one CTA live.  Shapes whose matrices
+// fit keep everything in shared memory; larger ones (n > 72 in fp64 with m = 2 n) keep the
+// vectors there and the matrices in a slice of a global-memory workspace the launcher
+// allocates (p.workspace, one slice of L.oV elements per CTA) -- slower, but no horizon is
+// refused for size.  The vector offsets of CtaLay count from the start of the matrices.
+template <typename T>
+__device__ __forceinline__ void cta_bases(const SolveParams &p, const CtaLay &L, T *sm, T *&mat, T *&vec) {
+    if (p.workspace) {
+        mat = static_cast<T *>(p.workspace) + (size_t)blockIdx.x * L.oV;
+        vec = sm - L.oV;
+    } else {
+        mat = vec = sm;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p) {  // @phase CTA prologue
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int tid = threadIdx.x, nt = blockDim.x;
-    const long long inst = blockIdx.x;
     const int n = p.n, m = p.m;
     const CtaLay L = cta_layout(n, m, p.nx, (int)sizeof(T));
     const int ld = L.ld;
-    T *M = sm + L.oM, *J = sm + L.oJ, *PL = sm + L.oPL, *Rc = sm + L.oPL, *Ri = sm + L.oRi;
-    T *hs = sm + L.o_hs, *viol = sm + L.o_viol, *vtol = sm + L.o_vtol, *ginv = sm + L.o_ginv;
-    T *mn2 = sm + L.o_mn2, *gzv = sm + L.o_gz;
-    T *q = sm + L.o_q, *x = sm + L.o_x, *z = sm + L.o_z, *dd = sm + L.o_dd, *d2 = sm + L.o_d2;
-    T *lam = sm + L.o_lam, *rv = sm + L.o_rv, *dv = sm + L.o_dv, *tq = sm + L.o_tq;
-    T *cand = sm + L.o_cand, *cs = sm + L.o_cs, *sn = sm + L.o_sn;
-    int *aidx = reinterpret_cast<int *>(sm + L.o_aidx);
-    int *actf = reinterpret_cast<int *>(sm + L.o_actf);
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(sm + L.o_red);
-    T *sc = sm + L.o_sc;
+    T *mat, *vec;
+    cta_bases<T>(p, L, sm, mat, vec);
+    T *M = mat + L.oM, *J = mat + L.oJ, *PL = mat + L.oPL, *Rc = mat + L.oPL, *Ri = mat + L.oRi;
+    T *hs = vec + L.o_hs, *viol = vec + L.o_viol, *vtol = vec + L.o_vtol, *ginv = vec + L.o_ginv;
+    T *mn2 = vec + L.o_mn2, *gzv = vec + L.o_gz;
+    T *q = vec + L.o_q, *x = vec + L.o_x, *z = vec + L.o_z, *dd = vec + L.o_dd, *d2 = vec + L.o_d2;
+    T *lam = vec + L.o_lam, *rv = vec + L.o_rv, *dv = vec + L.o_dv, *tq = vec + L.o_tq;
+    T *cand = vec + L.o_cand, *cs = vec + L.o_cs, *sn = vec + L.o_sn;
+    int *aidx = reinterpret_cast<int *>(vec + L.o_aidx);
+    int *actf = reinterpret_cast<int *>(vec + L.o_actf);
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(vec + L.o_red);
+    T *sc = vec + L.o_sc;
 
+    // one instance per CTA, or (workspace mode: the grid is bounded) a stride over the batch
+    for (long long inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
     {
         const bool lti = p.op[OP_A].step == 0 && p.op[OP_B].step == 0 && (!p.op[OP_C].ptr || p.op[OP_C].step == 0);
         if (lti && p.nc > 0 && p.nx <= 8 && p.nu < 32 && (!p.has_wx || p.nu == 1) && p.toeplitz)
-            cta_condense_lti<T>(p, L, sm, inst);
+            cta_condense_lti<T>(p, L, mat, vec, inst);
         else
-            cta_condense<T, false>(p, L, sm, inst);
+            cta_condense<T, false>(p, L, mat, vec, inst);
     }
 
     // ---- Cholesky in place on PL (lower triangle)  // @phase CTA cholesky
@@ -680,6 +698,8 @@ __global__ void __launch_bounds__(256) mpc_solve_cta_kernel(const SolveParams p)
         if (st == 0)
             for (int l = tid; l < na; l += nt) Zb[aidx[l]] = lam[l];
     }
+    __syncthreads();  // the next instance of this CTA reuses every buffer
+    }  // instances
 }
 
 // Condense-only CTA kernel (MPCQP fields for n > 32).
@@ -688,21 +708,25 @@ __global__ void __launch_bounds__(256) mpc_condense_cta_kernel(const SolveParams
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     const int tid = threadIdx.x, nt = blockDim.x;
-    const long long inst = blockIdx.x;
     const int n = p.n, m = p.m;
     const CtaLay L = cta_layout(n, m, p.nx, (int)sizeof(T));
-    cta_condense<T, true>(p, L, sm, inst);
-    const T *M = sm + L.oM, *PL = sm + L.oPL;
-    if (p.P)
-        for (int idx = tid; idx < n * n; idx += nt)
-            static_cast<T *>(p.P)[(size_t)inst * n * n + idx] = PL[(idx / n) * L.ld + idx % n];
-    if (p.q)
-        for (int c = tid; c < n; c += nt) static_cast<T *>(p.q)[(size_t)inst * n + c] = sm[L.o_q + c];
-    if (p.G)
-        for (int idx = tid; idx < m * n; idx += nt)
-            static_cast<T *>(p.G)[(size_t)inst * m * n + idx] = M[(idx / n) * L.ld + idx % n];
-    if (p.h)
-        for (int r = tid; r < m; r += nt) static_cast<T *>(p.h)[(size_t)inst * m + r] = sm[L.o_hs + r];
+    T *mat, *vec;
+    cta_bases<T>(p, L, sm, mat, vec);
+    for (long long inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
+        cta_condense<T, true>(p, L, mat, vec, inst);
+        const T *M = mat + L.oM, *PL = mat + L.oPL;
+        if (p.P)
+            for (int idx = tid; idx < n * n; idx += nt)
+                static_cast<T *>(p.P)[(size_t)inst * n * n + idx] = PL[(idx / n) * L.ld + idx % n];
+        if (p.q)
+            for (int c = tid; c < n; c += nt) static_cast<T *>(p.q)[(size_t)inst * n + c] = vec[L.o_q + c];
+        if (p.G)
+            for (int idx = tid; idx < m * n; idx += nt)
+                static_cast<T *>(p.G)[(size_t)inst * m * n + idx] = M[(idx / n) * L.ld + idx % n];
+        if (p.h)
+            for (int r = tid; r < m; r += nt) static_cast<T *>(p.h)[(size_t)inst * m + r] = vec[L.o_hs + r];
+        __syncthreads();
+    }
 }
 
 }  // namespace qpmpc

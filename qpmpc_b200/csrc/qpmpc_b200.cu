@@ -33,38 +33,78 @@ int env_int(const char *name, int dflt) {
 namespace {
 
 
-// One CTA per instance (mpc_cta_kernel.cuh): any shape whose matrices fit in
-// 227 KB of shared memory.
+// One CTA per instance (mpc_cta_kernel.cuh).  Shapes whose matrices fit in 227 KB of shared
+// memory keep everything there; larger ones keep the vectors in shared memory and the matrices
+// in a stream-ordered global-memory workspace (one slice per CTA, a bounded grid striding over
+// the batch), so no horizon is refused for its size until the VECTORS outgrow shared memory.
 template <typename T>
 size_t cta_smem_bytes(int n, int m, int nx) {
     return (size_t)cta_layout(n, m, nx, (int)sizeof(T)).total * sizeof(T);
+}
+constexpr size_t CTA_SMEM_MAX = 227 * 1024;
+constexpr int CTA_MAX_ROWS = 4096;  // the row index field of the pivot key
+constexpr int CTA_MAX_VARS = 512;   // largest n accepted (tested up to 256 on the device)
+
+struct CtaPlan {
+    size_t smem = 0, ws_bytes = 0;
+    int grid = 0;
+    void *ws = nullptr;
+};
+template <typename T>
+int plan_cta(const SolveParams &p, cudaStream_t stream, CtaPlan *plan) {
+    const CtaLay L = cta_layout(p.n, p.m, p.nx, (int)sizeof(T));
+    plan->smem = (size_t)L.total * sizeof(T);
+    plan->grid = p.batch;
+    const bool forced = env_int("QPMPC_B200_CTA_WORKSPACE", 0) != 0;  // tests: the workspace path on small shapes
+    if (plan->smem <= CTA_SMEM_MAX && !forced) return 0;
+    plan->smem = (size_t)(L.total - L.oV) * sizeof(T);
+    if (plan->smem > CTA_SMEM_MAX || p.m > CTA_MAX_ROWS || p.n > CTA_MAX_VARS) return QPMPC_B200_ESHAPE;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)(CTA_SMEM_MAX / (plan->smem + 1024));
+    const int resident = sms * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    plan->grid = p.batch < resident ? p.batch : resident;
+    plan->ws_bytes = (size_t)plan->grid * L.oV * sizeof(T);
+    cudaError_t err = cudaMallocAsync(&plan->ws, plan->ws_bytes, stream);
+    return err == cudaSuccess ? 0 : (int)err;
 }
 
 template <typename T>
 int launch_solve_cta(SolveParams p, cudaStream_t stream) {
     p.toeplitz = env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0;  // the time-invariant condensing path may be used
-    const size_t smem = cta_smem_bytes<T>(p.n, p.m, p.nx);
-    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+    CtaPlan plan;
+    int rc = plan_cta<T>(p, stream, &plan);
+    if (rc) return rc;
+    p.workspace = plan.ws;
     auto kern = mpc_solve_cta_kernel<T>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
-    int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
-    threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
-    kern<<<p.batch, threads, smem, stream>>>(p);
-    count_launch();
-    return (int)cudaGetLastError();
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (err == cudaSuccess) {
+        int threads = env_int("QPMPC_B200_CTA_THREADS", 256);
+        threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
+        kern<<<plan.grid, threads, plan.smem, stream>>>(p);
+        count_launch();
+        err = cudaGetLastError();
+    }
+    if (plan.ws) cudaFreeAsync(plan.ws, stream);
+    return (int)err;
 }
 
 template <typename T>
-int launch_condense_cta(const SolveParams &p, cudaStream_t stream) {
-    const size_t smem = cta_smem_bytes<T>(p.n, p.m, p.nx);
-    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
+int launch_condense_cta(SolveParams p, cudaStream_t stream) {
+    CtaPlan plan;
+    int rc = plan_cta<T>(p, stream, &plan);
+    if (rc) return rc;
+    p.workspace = plan.ws;
     auto kern = mpc_condense_cta_kernel<T>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
-    kern<<<p.batch, 256, smem, stream>>>(p);
-    count_launch();
-    return (int)cudaGetLastError();
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (err == cudaSuccess) {
+        kern<<<plan.grid, 256, plan.smem, stream>>>(p);
+        count_launch();
+        err = cudaGetLastError();
+    }
+    if (plan.ws) cudaFreeAsync(plan.ws, stream);
+    return (int)err;
 }
 
 // desc.paired is honoured when the rows really split into two halves per step (nc even)
@@ -256,21 +296,24 @@ long long qpmpc_b200_launch_count(void) { return g_launches.load(); }
 
 size_t qpmpc_b200_workspace_bytes(const qpmpc_b200_desc *) { return 0; }
 
-// Capacity of the CTA kernel (shared memory bound), assuming nx <= 8.
-static size_t cta_bytes(int dtype, int n, int m) {
-    return dtype == QPMPC_B200_F64 ? cta_smem_bytes<double>(n, m, 8) : cta_smem_bytes<float>(n, m, 8);
+// Capacity of the CTA kernel, assuming nx <= 8: its VECTORS must fit in shared memory (the
+// matrices move to a global-memory workspace beyond 227 KB) and a row index in 12 bits.
+static size_t cta_vector_bytes(int dtype, int n, int m) {
+    const int es = dtype == QPMPC_B200_F64 ? 8 : 4;
+    const CtaLay L = cta_layout(n, m, 8, es);
+    return (size_t)(L.total - L.oV) * es;
 }
 
 int qpmpc_b200_max_vars(int dtype) {
     int n = 32;
-    while (cta_bytes(dtype, n + 1, 2 * (n + 1)) <= 227 * 1024) ++n;  // with m = 2 n rows
+    while (n + 1 <= CTA_MAX_VARS && 2 * (n + 1) <= CTA_MAX_ROWS && cta_vector_bytes(dtype, n + 1, 2 * (n + 1)) <= CTA_SMEM_MAX) ++n;  // m = 2 n rows
     return n;
 }
 
 int qpmpc_b200_max_rows(int dtype, int n) {
-    if (n <= 0 || cta_bytes(dtype, n, 0) > 227 * 1024) return -1;
+    if (n <= 0 || n > CTA_MAX_VARS || cta_vector_bytes(dtype, n, 0) > CTA_SMEM_MAX) return -1;
     int m = 0;
-    while (cta_bytes(dtype, n, m + 8) <= 227 * 1024) m += 8;
+    while (m + 8 <= CTA_MAX_ROWS && cta_vector_bytes(dtype, n, m + 8) <= CTA_SMEM_MAX) m += 8;
     return m;
 }
 
@@ -278,7 +321,7 @@ const char *qpmpc_b200_strerror(int code) {
     switch (code) {
         case 0: return "success";
         case QPMPC_B200_EINVAL: return "invalid argument (null pointer, bad mode or dimension)";
-        case QPMPC_B200_ESHAPE: return "N*nu or N*nc exceeds the compiled kernel variants";
+        case QPMPC_B200_ESHAPE: return "N*nu or N*nc exceeds what the kernels hold (see qpmpc_b200_max_vars / _max_rows)";
         case QPMPC_B200_EWEIGHT: return "weights: need w_u > 0 and at least one of w_t, w_x";
         case QPMPC_B200_ENODEVICE: return "no usable CUDA device";
         case QPMPC_B200_EUNSUPPORTED: return "combination not implemented";

@@ -118,21 +118,33 @@ int condense(SolveParams p, int wpc) {
 }
 
 
-// launch_solve_cta / launch_condense_cta (qpmpc_b200.cu): one CTA per instance
-template <typename T>
-int solve_cta(SolveParams p, int threads) {
-    p.toeplitz = env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0;
-    const size_t smem = (size_t)cta_layout(p.n, p.m, p.nx, (int)sizeof(T)).total * sizeof(T);
-    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
-    launch(p.batch, threads, smem, [&]() { mpc_solve_cta_kernel<T>(p); });
+// launch_solve_cta / launch_condense_cta (qpmpc_b200.cu): one CTA per instance, or -- matrices
+// beyond 227 KB, or QPMPC_B200_CTA_WORKSPACE=1 -- a bounded grid (3 CTAs here, so that the stride
+// over the batch is exercised) with the matrices in a workspace outside shared memory
+template <typename T, typename K>
+int run_cta(SolveParams p, int threads, K kernel) {
+    const CtaLay L = cta_layout(p.n, p.m, p.nx, (int)sizeof(T));
+    size_t smem = (size_t)L.total * sizeof(T);
+    int grid = p.batch;
+    std::vector<T> ws;
+    if (smem > 227 * 1024 || env_int("QPMPC_B200_CTA_WORKSPACE", 0) != 0) {
+        smem = (size_t)(L.total - L.oV) * sizeof(T);
+        if (smem > 227 * 1024 || p.m > 4096 || p.n > 512) return QPMPC_B200_ESHAPE;
+        grid = p.batch < 3 ? p.batch : 3;
+        ws.assign((size_t)grid * L.oV, std::numeric_limits<T>::quiet_NaN());
+        p.workspace = ws.data();
+    }
+    launch(grid, threads, smem, [&]() { kernel(p); });
     return 0;
 }
 template <typename T>
+int solve_cta(SolveParams p, int threads) {
+    p.toeplitz = env_int("QPMPC_B200_NO_TOEPLITZ", 0) == 0;
+    return run_cta<T>(p, threads, [](const SolveParams &q) { mpc_solve_cta_kernel<T>(q); });
+}
+template <typename T>
 int condense_cta(const SolveParams &p) {
-    const size_t smem = (size_t)cta_layout(p.n, p.m, p.nx, (int)sizeof(T)).total * sizeof(T);
-    if (smem > 227 * 1024) return QPMPC_B200_ESHAPE;
-    launch(p.batch, 256, smem, [&]() { mpc_condense_cta_kernel<T>(p); });
-    return 0;
+    return run_cta<T>(p, 256, [](const SolveParams &q) { mpc_condense_cta_kernel<T>(q); });
 }
 
 // ---- pdip_core() on explicit QPs (P, q, G, h given), one emulated warp ------

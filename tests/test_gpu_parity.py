@@ -181,6 +181,66 @@ def test_cta_kernel_matches_oracle(kind, monkeypatch):
     _check_against_oracle(w)
 
 
+@pytest.mark.parametrize("kind", ["forced_ti16", "forced_pendulum", "forced_random", "humanoid_N100", "ti_stage_N96",
+                                  "random_n80_nu2", "ti_N128", "ti_N256"])
+def test_cta_kernel_beyond_shared_memory(kind, monkeypatch):
+    """Horizons whose matrices do not fit in 227 KB (n > 72 with m = 2 n in fp64): the CTA kernel
+    with its matrices in the stream-ordered global-memory workspace (qpmpc_b200.cu: plan_cta), a
+    bounded grid striding over the batch -- forced onto small shapes with more instances than
+    CTAs, and on horizons that need it, up to N = 256 (n = 256, m = 512)."""
+    import time
+
+    import torch
+
+    from qpmpc_b200 import solve_mpc_batch
+    from qpmpc_b200.workloads import (humanoid_batch, pendulum_batch, random_batch, to_batched,
+                                      triple_integrator_batch)
+
+    if kind.startswith("forced"):
+        monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+        monkeypatch.setenv("QPMPC_B200_CTA_WORKSPACE", "1")
+    w = {"forced_ti16": lambda: triple_integrator_batch(3000, N=16, seed=61),
+         "forced_pendulum": lambda: pendulum_batch(2000, seed=62),
+         "forced_random": lambda: random_batch(1500, 7, 5, 2, 3, seed=63, ltv=True),
+         "humanoid_N100": lambda: humanoid_batch(600, N=100, seed=64),
+         "ti_stage_N96": lambda: triple_integrator_batch(300, N=96, seed=65),
+         "random_n80_nu2": lambda: random_batch(300, 40, 4, 2, 3, seed=66, ltv=True, w_u=1.0),
+         "ti_N128": lambda: triple_integrator_batch(64, N=128, seed=67),
+         "ti_N256": lambda: triple_integrator_batch(8, N=256, seed=68)}[kind]()
+    if kind == "ti_stage_N96":
+        w["w_x"], w["targets"] = 0.5, np.zeros((w["batch"], 96 * 3))
+    prob = to_batched(w)
+    t0 = time.perf_counter()
+    plan = solve_mpc_batch(prob)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    import oracle
+    from qpmpc_b200.workloads import oracle_ops
+
+    ref = oracle.solve_batch(w["batch"], w["N"], w["nx"], w["nu"], w["nc"], oracle_ops(w), w["w_t"], w["w_x"], w["w_u"])
+    st = plan.status.cpu().numpy()
+    U = plan.inputs.reshape(w["batch"], -1).cpu().numpy()
+    assert np.array_equal(st == 0, ref["status"] == 0), (st[:16], ref["status"][:16])
+    ok = st == 0
+    assert ok.mean() > 0.5
+    assert np.array_equal(plan.iters.cpu().numpy()[ok], ref["iters"][ok])
+    err = np.abs(U[ok] - ref["U"][ok]).max()
+    assert err <= U_TOL, f"|dU|_inf = {err:.3e}"
+    print(f"{kind}: {w['batch']} instances in {dt * 1e3:.1f} ms, |dU| {err:.2e}")
+    if kind == "ti_N128":  # the MPCQP fields of a horizon this long, against the oracle's condensing
+        from qpmpc_b200 import condense_batch
+
+        fields = condense_batch(prob, ("P", "q", "G", "h"))
+        ops = oracle_ops(w)
+        pick = lambda a, flag: None if a is None else (a[3] if flag else a)  # noqa: E731
+        c = oracle.condense(w["N"], w["nx"], w["nu"], w["nc"], *[pick(*ops[k][:2]) for k in ("A", "B", "C", "D", "e")],
+                            w["x0"][3], w["goal"][3], None, w["w_t"], w["w_x"], w["w_u"])
+        for field in ("P", "q", "G", "h"):
+            ref_f = np.asarray(c[field])
+            got = fields[field][3].cpu().numpy().reshape(ref_f.shape)
+            assert np.abs(got - ref_f).max() <= 1e-12 * max(1.0, np.abs(ref_f).max()), field
+
+
 def test_cta_kernel_condense_fields(monkeypatch):
     """mpc_condense_cta_kernel reproduces the reference MPCQP fields."""
     from qpmpc_b200 import MPCQP

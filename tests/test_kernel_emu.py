@@ -223,6 +223,54 @@ def test_cta_kernel_long_horizon_and_forced_small_shapes(monkeypatch):
     _check(inf)
 
 
+def test_cta_kernel_beyond_shared_memory(monkeypatch):
+    """Shapes whose matrices do not fit in 227 KB (n > 72 in fp64 with m = 2 n) keep them in a
+    global-memory workspace, one slice per CTA of a bounded grid striding over the batch: the
+    same kernel forced onto small shapes (more instances than CTAs, so slices are reused), and a
+    horizon that needs it -- N = 96 with a stage cost, n = 80 with nu = 2 and D rows, N = 100."""
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    monkeypatch.setenv("QPMPC_B200_CTA_WORKSPACE", "1")
+    for w in (triple_integrator_batch(7, seed=51), pendulum_batch(5, seed=52), humanoid_batch(4, seed=53),
+              random_batch(5, 7, 5, 2, 3, seed=54, ltv=True)):
+        _check(w)
+        _check(w, descending=True)
+    monkeypatch.delenv("QPMPC_B200_FORCE_CTA")
+    monkeypatch.delenv("QPMPC_B200_CTA_WORKSPACE")
+    w = triple_integrator_batch(2, N=96, seed=55)
+    w["w_x"], w["targets"] = 0.5, np.zeros((2, 96 * 3))
+    got = _check(w)
+    assert (got["status"] == 0).all()
+    _check(random_batch(2, 40, 4, 2, 3, seed=56, ltv=True, w_u=1.0))   # n = 80, m = 120, D rows
+    _check(random_batch(2, 40, 4, 2, 3, seed=56, ltv=False, w_u=1.0))
+    _check(humanoid_batch(2, N=100, seed=3))
+
+
+def test_cta_condense_kernel_beyond_shared_memory(monkeypatch):
+    """mpc_condense_cta_kernel out of the workspace: the golden fixtures through the forced path,
+    and the MPCQP fields of an N = 96 horizon against the oracle's condensing."""
+    monkeypatch.setenv("QPMPC_B200_FORCE_CTA", "1")
+    monkeypatch.setenv("QPMPC_B200_CTA_WORKSPACE", "1")
+    for name in ("pendulum", "random_ltv_cd"):
+        g = load_golden(name)
+        out = emu.condense(_golden_workload(g))
+        for field in ("P", "q", "G", "h", "Phi", "Psi", "phi_last", "psi_last"):
+            ref = g[f"ref_{field}"]
+            got = out[field][0].reshape(ref.shape)
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (name, field)
+    monkeypatch.delenv("QPMPC_B200_FORCE_CTA")
+    monkeypatch.delenv("QPMPC_B200_CTA_WORKSPACE")
+    w = triple_integrator_batch(2, N=96, seed=57)
+    out = emu.condense(w)
+    ops = oracle_ops(w)
+    pick = lambda a, flag: None if a is None else (a[1] if flag else a)
+    c = oracle.condense(w["N"], w["nx"], w["nu"], w["nc"], *[pick(*ops[k][:2]) for k in ("A", "B", "C", "D", "e")],
+                        w["x0"][1], w["goal"][1], None, w["w_t"], w["w_x"], w["w_u"])
+    for field in ("P", "q", "G", "h"):
+        ref = np.asarray(c[field])
+        got = out[field][1].reshape(ref.shape)
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), field
+
+
 def test_cta_condense_kernel_matches_reference_fields(monkeypatch):
     """mpc_condense_cta_kernel against the reference's MPCQP fields (N = 64 golden
     fixture natively, two more through QPMPC_B200_FORCE_CTA)."""

@@ -11,3 +11,6 @@ echo "rc=$?"; cat $OUT/${TAG}_bench_${N}gpu.json; tail -5 $OUT/${TAG}_bench_${N}
 echo "== reference arm under torchrun"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 4 --warmup 1 > $OUT/${TAG}_bench_ref_${N}gpu.json 2>> $OUT/${TAG}_bench_${N}gpu.err
 cat $OUT/${TAG}_bench_ref_${N}gpu.json | cut -c1-400
+echo "== host<->device copy ceiling of the box, all ranks at once"
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/pcie_probe.py 2>> $OUT/${TAG}_bench_${N}gpu.err | grep '^{' > $OUT/${TAG}_pcie_${N}gpu.json
+cat $OUT/${TAG}_pcie_${N}gpu.json
