@@ -308,6 +308,20 @@ def pack_problem(problem: MPCProblem) -> dict:
     N = problem.nb_timesteps
     if problem.initial_state is None:
         raise ProblemDefinitionError("initial state is undefined")  # mpc_qp.py:49-51
+    if not isinstance(problem.ineq_vector, list):
+        # time-invariant rows (the common case, and the one a control loop calls every cycle):
+        # nothing is ragged, nothing needs stacking
+        e0 = np.asarray(problem.ineq_vector, dtype=float).reshape(-1)
+        nc = e0.shape[0]
+        nx, nu = problem.state_dim, problem.input_dim
+        A, B = problem.transition_state_matrix, problem.transition_input_matrix
+        C, D = problem.ineq_state_matrix, problem.ineq_input_matrix
+        if not any(isinstance(op, list) for op in (A, B, C, D)):
+            return dict(A=np.asarray(A, dtype=float), B=np.asarray(B, dtype=float).reshape(nx, nu),
+                        C=None if C is None else np.asarray(C, dtype=float).reshape(-1, nx),
+                        D=None if D is None else np.asarray(D, dtype=float).reshape(-1, nu),
+                        e=e0, x0=problem.initial_state, goal=problem.goal_state, targets=problem.target_states,
+                        nc=nc, row_map=list(range(N * nc)))
     e_steps = [np.asarray(problem.get_ineq_vector(k), dtype=float).reshape(-1) for k in range(N)]
     ncs = [ek.shape[0] for ek in e_steps]
     nc = max(ncs)

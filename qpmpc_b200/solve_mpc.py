@@ -25,11 +25,13 @@ import warnings
 
 import torch
 
-from .batched import problem_to_batch, solve_mpc_batch
-from .exceptions import BackendError
+from . import _capi
+from .batched import pack_problem, problem_to_batch, solve_mpc_batch
+from .exceptions import BackendError, ProblemDefinitionError
 from .mpc_problem import MPCProblem
 from .mpc_qp import MPCQP  # noqa: F401  (reference tests import it from here)
 from .plan import Plan
+from .single import solve_single
 from .solution import Solution
 
 NATIVE_SOLVERS = ("b200", "cuda", "b200_pdip")
@@ -122,21 +124,30 @@ def solve_mpc(
         warnings.warn(
             f"solve_mpc: keyword(s) {dropped} do not apply to the CUDA engine's {method} method "
             "and were ignored", stacklevel=2)
-    batch = problem_to_batch(problem, dtype=kwargs.get("dtype", torch.float64))
-    plan = solve_mpc_batch(
-        batch,
-        method=method,
-        max_iter=int(kwargs.get("max_iter", 0)),
-        tol=tol,
-        return_multipliers=True,
-    )
-    status = int(plan.status[0].item())
+    dtype = kwargs.get("dtype", torch.float64)
+    max_iter = int(kwargs.get("max_iter", 0))
+    if os.environ.get("QPMPC_B200_SINGLE_ZEROCOPY", "1") != "0":
+        # one launch, no copy call: operands and results in one page-locked block (single.py)
+        code = {"active_set": _capi.ACTIVE_SET, "pdip": _capi.PDIP}.get(method)
+        if code is None or dtype not in (torch.float64, torch.float32):
+            raise ProblemDefinitionError(f"unknown method {method!r}" if code is None else
+                                         "dtype must be torch.float64 or torch.float32")
+        pk = pack_problem(problem)
+        x, z, status, iters = solve_single(problem, pk, code, max_iter, tol, dtype)
+        rows = pk["row_map"]
+    else:
+        # through device tensors, as a batch of one (the path the batched surface takes)
+        batch = problem_to_batch(problem, dtype=dtype)
+        plan = solve_mpc_batch(batch, method=method, max_iter=max_iter, tol=tol, return_multipliers=True)
+        status, iters = int(plan.status[0].item()), int(plan.iters[0].item())
+        x = plan.inputs[0].reshape(-1).double().cpu().numpy()
+        z = plan.multipliers[0].double().cpu().numpy()
+        rows = batch.row_map
     found = status == 0
-    rows = batch.row_map
     qpsol = Solution(
         found=found,
-        x=plan.inputs[0].reshape(-1).double().cpu().numpy() if found else None,
-        z=plan.multipliers[0].double().cpu().numpy()[rows] if found and rows else None,
-        extras={"status": status, "iters": int(plan.iters[0].item()), "method": method},
+        x=x if found else None,
+        z=z[rows] if found and rows else None,
+        extras={"status": status, "iters": iters, "method": method},
     )
     return Plan(problem, qpsol)

@@ -208,6 +208,10 @@ class EmulatedLibrary:
         with _Checked() as lib:
             return lib.emu_solve(desc, ops, outs, 0)
 
+    def qpmpc_b200_solve_host(self, desc, ops, outs, device):
+        # host buffers are all the emulator has: the host entry is the device entry
+        return self.qpmpc_b200_solve(desc, ops, outs, None)
+
     def qpmpc_b200_condense(self, desc, ops, fields, stream):
         self.calls += 1
         with _Checked() as lib:

@@ -711,3 +711,23 @@ def test_tensor_core_hessian_matches_the_simt_sum_and_the_oracle(N, ltv, monkeyp
     assert worst_tc <= 2e-6 and worst_simt <= 1e-5, (worst_tc, worst_simt)
     for k in fields[1:]:
         assert torch.equal(tc[k], simt[k]), k
+
+
+def test_solve_mpc_single_path_matches_batch_path_on_the_device(monkeypatch):
+    """``solve_mpc`` of ONE problem: the zero-copy host entry (qpmpc_b200/single.py) against the
+    device-tensor path, bit for bit; and what a control loop pays per cycle."""
+    import time
+
+    from qpmpc_b200 import solve_mpc
+    from test_host import single_path_matches_batch_path
+
+    single_path_matches_batch_path(monkeypatch)
+    problem = golden_problem(load_golden("triple_integrator"))
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QPMPC_B200_SINGLE_ZEROCOPY", mode)
+        for _ in range(20):
+            solve_mpc(problem, "b200")
+        t0 = time.perf_counter()
+        for _ in range(200):
+            solve_mpc(problem, "b200")
+        print(f"solve_mpc latency, QPMPC_B200_SINGLE_ZEROCOPY={mode}: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")

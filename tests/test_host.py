@@ -321,3 +321,49 @@ def test_batched_front_end_validates_its_arguments(emulated_engine):
     both = BatchedMPCProblem.from_problems([a, golden_problem(load_golden("triple_integrator"))])
     plan = solve_mpc_batch(both)
     assert torch.equal(plan.inputs[0], plan.inputs[1]) and int(plan.status.sum()) == 0
+
+
+def _ragged_problem():
+    A, B = np.array([[1.0, 0.1], [0.0, 1.0]]), np.array([[0.005], [0.1]])
+    C = [np.array([[0.0, 1.0]]), np.array([[0.0, 1.0], [0.0, -1.0], [1.0, 0.0]]), None, np.array([[1.0, 0.0]])]
+    e = [np.array([0.3]), np.array([0.3, 0.3, 2.0]), np.array([1.0, 1.0]), np.array([0.8])]
+    D = [None, None, np.array([[1.0], [-1.0]]), None]
+    return MPCProblem(A, B, C, D, e, 4, 1.0, 0.1, 1e-2, initial_state=np.array([0.0, 0.0]),
+                      goal_state=np.array([1.0, 0.0]), target_states=np.zeros(8))
+
+
+def single_path_matches_batch_path(monkeypatch):
+    """``solve_mpc`` through the page-locked staging block + host entry (single.py) and through
+    device tensors as a batch of one (QPMPC_B200_SINGLE_ZEROCOPY=0): same plan, multipliers,
+    status and iteration count -- time-invariant, time-varying and ragged problems, both methods,
+    both precisions, an infeasible problem, and a second solve that reuses the cached block."""
+    import torch
+
+    from qpmpc_b200 import solve_mpc
+
+    problems = [golden_problem(load_golden(name)) for name in ("triple_integrator", "humanoid", "pendulum", "random_ltv_cd")]
+    problems.append(_ragged_problem())
+    infeasible = golden_problem(load_golden("triple_integrator"))
+    infeasible.update_initial_state(np.array([0.0, 0.0, 5.0]))
+    problems.append(infeasible)
+    for problem in problems + problems[:2]:
+        for kw in ({}, {"method": "pdip"}, {"dtype": torch.float32}):
+            if kw.get("dtype") is torch.float32 and problem is infeasible:
+                continue
+            monkeypatch.setenv("QPMPC_B200_SINGLE_ZEROCOPY", "1")
+            a = solve_mpc(problem, "b200", **kw)
+            monkeypatch.setenv("QPMPC_B200_SINGLE_ZEROCOPY", "0")
+            b = solve_mpc(problem, "b200", **kw)
+            assert a.is_empty == b.is_empty
+            assert a.qpsol.extras == b.qpsol.extras
+            if not a.is_empty:
+                assert np.array_equal(a.qpsol.x, b.qpsol.x)
+                assert (a.qpsol.z is None) == (b.qpsol.z is None)
+                if a.qpsol.z is not None:
+                    assert np.array_equal(a.qpsol.z, b.qpsol.z)
+    assert problems[-1] is infeasible and solve_mpc(infeasible, "b200").is_empty
+
+
+def test_solve_mpc_single_path_matches_batch_path_on_the_emulator(emulated_engine, monkeypatch):
+    single_path_matches_batch_path(monkeypatch)
+    assert emulated_engine.calls > 0
