@@ -32,7 +32,10 @@ def _rows_paired(pk: dict, nc: int) -> bool:
     if nc == 0 or nc % 2 or (pk["C"] is None and pk["D"] is None):
         return False
     h = nc // 2
-    return all(np.array_equal(t[..., :h, :], -t[..., h:, :]) for t in (pk["C"], pk["D"]) if t is not None)
+    for t in (pk["C"], pk["D"]):
+        if t is not None and (t[..., :h, :] != -t[..., h:, :]).any():
+            return False
+    return True
 
 
 class _Slot:
