@@ -503,6 +503,33 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def single_call_latency(calls=300):
+    """BASELINE configs[0]: ONE triple-integrator problem through the reference-facing call,
+    ``solve_mpc(problem)`` -> Plan (what a control loop pays per cycle; host objects in, host
+    arrays out).  Outside the timed region of the headline."""
+    from qpmpc_b200 import MPCProblem, solve_mpc
+
+    T = 1.0 / 16
+    problem = MPCProblem(
+        transition_state_matrix=np.array([[1.0, T, T**2 / 2.0], [0.0, 1.0, T], [0.0, 0.0, 1.0]]),
+        transition_input_matrix=np.array([T**3 / 6.0, T**2 / 2.0, T]).reshape((3, 1)),
+        ineq_state_matrix=np.array([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0]]), ineq_input_matrix=None,
+        ineq_vector=np.array([3.0, 3.0]), nb_timesteps=16, terminal_cost_weight=1.0,
+        stage_state_cost_weight=None, stage_input_cost_weight=1e-6,
+        initial_state=np.array([0.0, 0.0, 0.0]), goal_state=np.array([1.0, 0.0, 0.0]))
+    for _ in range(20):
+        plan = solve_mpc(problem, "b200")
+    t0 = time.perf_counter()
+    for i in range(calls):
+        problem.update_initial_state(np.array([0.001 * i, 0.0, 0.0]))
+        plan = solve_mpc(problem, "b200")
+    us = (time.perf_counter() - t0) / calls * 1e6
+    assert not plan.is_empty
+    return {"solve_mpc_us": us, "calls": calls,
+            "path": "qpmpc_b200.solve_mpc -> page-locked staging block -> qpmpc_b200_solve_host (zero-copy, one launch)",
+            "workload": "triple_integrator N=16, one instance (BASELINE configs[0]), new initial state every call"}
+
+
 def run_b200(args, rank, local_rank, world):
     import ctypes
 
@@ -884,6 +911,8 @@ def run_b200(args, rank, local_rank, world):
         v, threads, sample = cpu_arm(args, sets[0], args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                 "reference_python": reference_python_condense()}
+    if world == 1 and args.config == 2 and args.method == "active_set":
+        line["single_call"] = single_call_latency()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
