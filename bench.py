@@ -503,6 +503,12 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def loop_kind(model):
+    fused = model is not None and os.environ.get("QPMPC_B200_LOOP_FUSED", "1") != "0"
+    return ("all cycles inside ONE launch of the shared-model solve kernel (each lane group solves, moves its plant "
+            "and rewrites its vectors in shared memory)") if fused else "one solve launch and one plant launch per cycle"
+
+
 def single_call_latency(calls=300):
     """BASELINE configs[0]: ONE triple-integrator problem through the reference-facing call,
     ``solve_mpc(problem)`` -> Plan (what a control loop pays per cycle; host objects in, host
@@ -890,7 +896,8 @@ def run_b200(args, rank, local_rank, world):
         line["closed_loop"] = {"cycles": WALK_CYCLES, "unsolved": int(loop_info["unsolved"].item()),
                                "model": "factored once (qpmpc_b200_factor), q and h per cycle" if model is not None
                                else "condensed and factored per instance and cycle",
-                               "launches_per_step": 2 * WALK_CYCLES + 1}
+                               "launches_per_step": launches / args.steps,
+                               "loop": loop_kind(model)}
     if args.config == 3:
         hist = loop_info["stats"]["iterations"].cpu().numpy().astype(float) / B
         useful = int(loop_info["stats"]["upright"].item())
@@ -906,7 +913,7 @@ def run_b200(args, rank, local_rank, world):
                                           "cycles_50_199": float(hist[50:].mean())},
             "model": "factored once (qpmpc_b200_factor), q and h per cycle" if model is not None
                      else "condensed and factored per instance and cycle",
-            "launches_per_step": 2 * CYCLES + 1}
+            "launches_per_step": launches / args.steps, "loop": loop_kind(model)}
     if not args.no_cpu_baseline:
         v, threads, sample = cpu_arm(args, sets[0], args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,

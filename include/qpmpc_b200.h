@@ -216,8 +216,11 @@ int qpmpc_b200_integrate(const qpmpc_b200_desc *desc, const qpmpc_b200_operands 
  * (read and overwritten), in->goal [batch,4] and in->targets [batch,N*4] are
  * work buffers the loop rewrites every cycle; out->U / status / iters hold the
  * plan of the last cycle.  An instance without a plan in some cycle gets input
- * 0 for that cycle and is counted in *unsolved.  2 * cycles + 1 launches,
- * asynchronous on `stream`. */
+ * 0 for that cycle and is counted in *unsolved.  With loop->record the whole
+ * loop is 2 launches (the instances are independent: each lane group of the
+ * shared-model kernel runs all its cycles -- solve, plant, next targets -- without
+ * leaving the SM; QPMPC_B200_LOOP_FUSED=0: 2 per cycle); without, 2 * cycles + 1.
+ * Asynchronous on `stream`. */
 typedef struct qpmpc_b200_closed_loop {
     int32_t cycles;          /* control cycles (200 in BASELINE config 3) */
     int32_t substeps;        /* plant steps per cycle (NB_SUBSTEPS = 15) */

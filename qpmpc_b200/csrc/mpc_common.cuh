@@ -29,6 +29,27 @@ struct OperandView {
     int smem_off;      // element offset inside the CTA's input region
 };
 
+// A whole receding-horizon loop inside ONE launch of the shared-model solve kernel
+// (mpc_kernels.cuh, PRE): the instances are independent, so each lane group runs all its cycles
+// -- solve, apply the first input to the plant, write the next cycle's vectors into the staged
+// inputs in shared memory -- without leaving the SM (mpc_plant.cuh has the plant pieces).
+struct LoopDev {
+    int kind;                         // 0: a single solve; 1: wheeled inverted pendulum; 2: LIPM walking
+    int cycles, substeps;
+    double dt, T, omega2, g;          // plant step; pendulum: MPC sampling period, g / length, g
+    int nb_dsp, nb_ssp;               // walking: steps of a double / single support phase
+    double foot_size, max_zmp;
+    void *state;                      // [batch, nx] in/out
+    const void *v_target;             // pendulum [batch]
+    void *support_foot;               // walking [batch] in/out
+    const void *strides;              // walking [batch, 2]
+    int *phase_index, *stride_index;  // walking [batch] in/out
+    void *goal, *targets, *e;         // vectors of the NEXT cycle, written back after the last one
+    void *traj;                       // optional [cycles + 1, batch, nx] (slot 0 is the caller's)
+    int *unsolved, *upright;          // optional counters
+    long long *iter_sum;              // optional [cycles]
+};
+
 struct SolveParams {
     int batch, N, nx, nu, nc, n, m;
     OperandView op[OP_COUNT];
@@ -62,6 +83,8 @@ struct SolveParams {
     int skip_P;
     // CTA kernels, shapes beyond shared memory: global-memory home of the matrices (nullptr: shared memory)
     void *workspace;
+    // shared-model kernel: the closed loop it runs (kind 0: none)
+    LoopDev loop;
 };
 
 template <typename T> struct Pair;
@@ -70,6 +93,8 @@ template <> struct Pair<float> { using type = float2; };
 
 __device__ __forceinline__ double rsqrt_(double v) { return rsqrt(v); }
 __device__ __forceinline__ float rsqrt_(float v) { return rsqrtf(v); }
+__device__ __forceinline__ void sincos_(double a, double *s, double *c) { sincos(a, s, c); }
+__device__ __forceinline__ void sincos_(float a, float *s, float *c) { sincosf(a, s, c); }
 __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
 __device__ __forceinline__ float sqrt_(float v) { return sqrtf(v); }
 // Branch-free reciprocal and reciprocal square root for well-scaled positive

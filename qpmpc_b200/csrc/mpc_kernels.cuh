@@ -30,6 +30,7 @@
 #pragma once
 
 #include "mpc_common.cuh"
+#include "mpc_plant.cuh"
 #include "mpc_factor.cuh"  // FactorLay: the record of the shared-model fast path (PRE)
 
 // Resident CTAs of 128 threads per SM the register-resident variants are
@@ -714,8 +715,10 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
 #pragma unroll
     for (int o = 0; o < OP_COUNT; ++o) {
         const OperandView &v = p.op[o];
-        // Invalid tail slots read instance 0 of the CTA: defined data, results discarded.
-        in[o] = v.ptr ? inbase + v.smem_off + (v.per_instance ? (valid ? iic : 0) * v.sz : 0) : nullptr;
+        // Invalid tail slots read instance 0 of the CTA: defined data, results discarded.  (In a
+        // fused loop the slots are rewritten every cycle: there they keep their own, unused one.)
+        const bool own = valid || (PRE && p.loop.kind != 0);
+        in[o] = v.ptr ? inbase + v.smem_off + (v.per_instance ? (own ? iic : 0) * v.sz : 0) : nullptr;
     }
 
     // ---- shared-model fast path: the record of the model, once per CTA -------  // @phase PRE record
@@ -729,6 +732,26 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
         __syncthreads();
     }
 
+    // ---- fused closed loop (shared-model kernel only): every cycle runs the code below on the
+    // inputs staged in shared memory, then the plant moves and rewrites them in place
+    const int ncyc = (PRE && p.loop.kind != 0) ? p.loop.cycles : 1;
+    const bool looping = PRE && p.loop.kind != 0;
+    // loop-carried state of the walking pattern (uniform over the lanes of an instance)
+    int wk_index = 0, wk_sidx = 0;
+    T wk_foot = T(0), wk_s0 = T(0), wk_s1 = T(0), pend_v = T(0);
+    if (PRE && looping && valid) {
+        if (p.loop.kind == 1) {
+            pend_v = static_cast<const T *>(p.loop.v_target)[inst];
+        } else {
+            wk_index = p.loop.phase_index[inst];
+            wk_sidx = p.loop.stride_index[inst];
+            wk_foot = static_cast<const T *>(p.loop.support_foot)[inst];
+            wk_s0 = static_cast<const T *>(p.loop.strides)[2 * inst];
+            wk_s1 = static_cast<const T *>(p.loop.strides)[2 * inst + 1];
+        }
+    }
+#pragma unroll 1
+    for (int cyc = 0; cyc < ncyc; ++cyc) {
     // ---- phase A -----------------------------------------------------------
     T Prow[PRE ? 1 : NP];
     T qj;
@@ -1336,7 +1359,7 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
     // The warps of the CTA leave the iteration at different times but hold the
     // CTA's resources until the last one is done: let them run the (unrolled,
     // one-shot) recovery code together so that they share instruction fetches.
-    if (!HASJ && QPMPC_SYNC_TAIL) __syncthreads();
+    if (!HASJ && QPMPC_SYNC_TAIL && !looping) __syncthreads();  // (a fused loop would pay the wait every cycle)
     // ---- x from the multipliers (J not kept): x = -P^-1 (q + G_A' lambda)  // @phase D x from multipliers
     if (!HASJ) {
         // w_l = q_l + sum_i lambda_i G[a_i, l]
@@ -1388,7 +1411,7 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
         const unsigned nonfinite = __ballot_sync(FULL_MASK, !(abs_(x) < Num<T>::inf())) & segmask;  // all lanes vote
         if (st == 0 && nonfinite) st = 3;
     }
-    if (valid) {
+    if (valid && cyc + 1 == ncyc) {
         const T xo = (st == 0) ? x : Num<T>::nan();
         if (l < n && p.U) static_cast<T *>(p.U)[(size_t)inst * n + l] = xo;
         if (l == 0) {
@@ -1410,6 +1433,82 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
     } else if (p.Z) {
         __syncwarp();
     }
+    if constexpr (PRE) {
+        if (looping) {  // @phase PRE loop: plant and next cycle's vectors
+            // first input of the plan (nu = 1: variable 0), zero when the cycle has no plan
+            const T u0 = __shfl_sync(FULL_MASK, (st == 0) ? x : T(0), 0, NP);
+            T *xm = const_cast<T *>(in[OP_X0]);
+            T *gm = const_cast<T *>(in[OP_GOAL]);
+            const LoopDev &lp = p.loop;
+            const int nxs = p.nx;
+            __syncwarp();
+            if (valid && l == 0) {
+                if (st != 0 && lp.unsolved) atomicAdd(lp.unsolved, 1);
+                if (lp.iter_sum) atomicAdd(reinterpret_cast<unsigned long long *>(lp.iter_sum + cyc), (unsigned long long)it);
+            }
+            if (lp.kind == 1) {
+                if (valid && l == 0) {
+                    T r = xm[0], th = xm[1], rd = xm[2], thd = xm[3];
+                    // the MPC of this cycle was solved from the state before the plant moves
+                    if (lp.upright && abs_(th) <= T(1.2)) atomicAdd(lp.upright, 1);
+                    pendulum_integrate<T>(r, th, rd, thd, u0, lp.substeps, (T)lp.dt, (T)lp.omega2, (T)lp.g);
+                    xm[0] = r, xm[1] = th, xm[2] = rd, xm[3] = thd;
+                }
+                __syncwarp();
+                if (valid) {
+                    T *tg = const_cast<T *>(in[OP_TGT]);
+                    const T r = xm[0];
+                    for (int k = l; k < p.N; k += NP) pendulum_target<T>(tg + k * 4, r, pend_v, k, (T)lp.T);
+                    if (l == 0) pendulum_target<T>(gm, r, pend_v, p.N, (T)lp.T);
+                }
+            } else {
+                if (valid && l == 0) {
+                    T pos = xm[0], vel = xm[1], acc = xm[2];
+                    lipm_integrate<T>(pos, vel, acc, u0, lp.substeps, (T)lp.dt);
+                    xm[0] = pos, xm[1] = vel, xm[2] = acc;
+                }
+                // PhaseStepper.advance and the foot switch (:331-334), every lane for itself
+                wk_index = wk_index + 1 >= lp.nb_dsp + lp.nb_ssp ? 0 : wk_index + 1;
+                if (wk_index == 0) {
+                    wk_foot = wk_foot + (wk_sidx ? wk_s1 : wk_s0);
+                    wk_sidx = (wk_sidx + 1) % 2;
+                }
+                if (valid) {
+                    const LipmPhases ph = lipm_phases(wk_index, lp.nb_dsp, lp.nb_ssp, p.N);
+                    const T next = wk_foot + (wk_sidx ? wk_s1 : wk_s0);
+                    const T last = next + (wk_sidx ? wk_s0 : wk_s1);
+                    const T hf = T(0.5) * (T)lp.foot_size, big = (T)lp.max_zmp;
+                    T *em = const_cast<T *>(in[OP_E]);
+                    for (int k = l; k < p.N; k += NP) lipm_bounds<T>(ph, k, wk_foot, next, last, hf, big, em[2 * k], em[2 * k + 1]);
+                    if (l == 0) gm[0] = ph.n4 > 0 ? last : next, gm[1] = T(0), gm[2] = T(0);
+                }
+            }
+            __syncwarp();
+            if (valid && lp.traj && l < nxs)
+                static_cast<T *>(lp.traj)[((size_t)(cyc + 1) * p.batch + inst) * nxs + l] = xm[l];
+            if (valid && cyc + 1 == ncyc) {
+                // what the step kernel leaves behind after the last cycle: state and next vectors
+                if (l < nxs) {
+                    static_cast<T *>(lp.state)[(size_t)inst * nxs + l] = xm[l];
+                    static_cast<T *>(lp.goal)[(size_t)inst * nxs + l] = gm[l];
+                }
+                if (lp.kind == 1) {
+                    const T *tg = in[OP_TGT];
+                    for (int k = l; k < p.N * nxs; k += NP) static_cast<T *>(lp.targets)[(size_t)inst * p.N * nxs + k] = tg[k];
+                } else {
+                    const T *em = in[OP_E];
+                    for (int k = l; k < 2 * p.N; k += NP) static_cast<T *>(lp.e)[(size_t)inst * p.N * 2 + k] = em[k];
+                    if (l == 0) {
+                        lp.phase_index[inst] = wk_index;
+                        lp.stride_index[inst] = wk_sidx;
+                        static_cast<T *>(lp.support_foot)[inst] = wk_foot;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    }  // cycles
 }
 
 // ---------------------------------------------------------------------------

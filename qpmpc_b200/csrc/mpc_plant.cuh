@@ -13,6 +13,79 @@
 
 namespace qpmpc {
 
+// ---- the plant pieces as device functions: the step kernels below and the fused loop of the
+// shared-model solve kernel (mpc_kernels.cuh, SolveParams::loop) run the same code ------------
+
+// NB substeps of the second-order Taylor step of the nonlinear dynamics (systems/...:150-160)
+template <typename T>
+__device__ __forceinline__ void pendulum_integrate(T &r, T &th, T &rd, T &thd, T u, int substeps, T dt, T w2, T g) {
+    for (int s = 0; s < substeps; ++s) {
+        const T rdd = u;
+        T sn, cs;
+        sincos_(th, &sn, &cs);  // one argument reduction for both
+        const T thdd = w2 * (sn - (rdd / g) * cs);
+        r = r + dt * (rd + dt * (rdd / T(2)));
+        rd = rd + dt * rdd;
+        th = th + dt * (thd + dt * (thdd / T(2)));
+        thd = thd + dt * thdd;
+    }
+}
+// get_target_states: position ramp r + k T v, velocity v, zero pitch (examples/...:77-82)
+template <typename T>
+__device__ __forceinline__ void pendulum_target(T *tg, T r, T v, int k, T Ts) {
+    tg[0] = r + ((T)k * Ts) * v;
+    tg[1] = T(0);
+    tg[2] = v;
+    tg[3] = T(0);
+}
+// constant-jerk integration (examples/lipm_walking_controller.py:219-225)
+template <typename T>
+__device__ __forceinline__ void lipm_integrate(T &pos, T &vel, T &acc, T jerk, int substeps, T dt) {
+    for (int s = 0; s < substeps; ++s) {
+        const T p1 = pos + dt * (vel + dt * (acc / T(2) + dt * jerk / T(6)));
+        const T v1 = vel + dt * (acc + dt * (jerk / T(2)));
+        acc = acc + dt * jerk;
+        pos = p1;
+        vel = v1;
+    }
+}
+// get_nb_steps (:132-163): lengths of the first five phases that cover the horizon (the sixth
+// takes what is left: at most nb_ssp steps for horizons of two steps)
+struct LipmPhases {
+    int n0, n1, n2, n3, n4;
+};
+__device__ __forceinline__ LipmPhases lipm_phases(int index, int nb_dsp, int nb_ssp, int N) {
+    LipmPhases q;
+    int off = index;
+    q.n0 = max(0, nb_dsp - off);
+    off = max(0, off - nb_dsp);
+    q.n1 = max(0, nb_ssp - off);
+    int rem = N - q.n0 - q.n1;
+    q.n2 = min(nb_dsp, rem);
+    rem = max(0, rem - nb_dsp);
+    q.n3 = min(nb_ssp, rem);
+    rem = max(0, rem - nb_ssp);
+    q.n4 = min(nb_dsp, rem);
+    return q;
+}
+// update_goal_and_constraints (:175-205): ZMP bounds of step k (hi: z <= hi, lo: -z <= lo)
+template <typename T>
+__device__ __forceinline__ void lipm_bounds(const LipmPhases &q, int k, T foot, T next, T last, T hf, T big, T &hi,
+                                            T &lo) {
+    hi = big, lo = big;
+    int j = k;
+    if (j < q.n0) {
+    } else if ((j -= q.n0) < q.n1) {
+        hi = foot + hf, lo = -(foot - hf);
+    } else if ((j -= q.n1) < q.n2) {
+    } else if ((j -= q.n2) < q.n3) {
+        hi = next + hf, lo = -(next - hf);
+    } else if ((j -= q.n3) < q.n4) {
+    } else {
+        hi = last + hf, lo = -(last - hf);
+    }
+}
+
 struct PendulumStepParams {
     int batch, N, n;      // instances, horizon, N * nu (row stride of U)
     int substeps;         // plant steps per control cycle (0: only write targets)
@@ -45,16 +118,7 @@ __global__ void __launch_bounds__(128) pendulum_step_kernel(const PendulumStepPa
         if (p.upright && abs_(th) <= T(1.2)) atomicAdd(p.upright, 1);
         if (p.iter_sum && p.iters) atomicAdd(reinterpret_cast<unsigned long long *>(p.iter_sum),
                                              (unsigned long long)p.iters[b]);
-        const T dt = (T)p.dt, w2 = (T)p.omega2, g = (T)p.g;
-        for (int s = 0; s < p.substeps; ++s) {
-            // second-order Taylor step of the nonlinear dynamics (systems/...:150-160)
-            const T rdd = u;
-            const T thdd = w2 * (sin(th) - (rdd / g) * cos(th));
-            r = r + dt * (rd + dt * (rdd / T(2)));
-            rd = rd + dt * rdd;
-            th = th + dt * (thd + dt * (thdd / T(2)));
-            thd = thd + dt * thdd;
-        }
+        pendulum_integrate<T>(r, th, rd, thd, u, p.substeps, (T)p.dt, (T)p.omega2, (T)p.g);
         st[0] = r, st[1] = th, st[2] = rd, st[3] = thd;
     }
     if (p.traj) {
@@ -64,17 +128,8 @@ __global__ void __launch_bounds__(128) pendulum_step_kernel(const PendulumStepPa
     // get_target_states: position ramp r + k T v, velocity v, zero pitch (examples/...:77-82)
     const T v = static_cast<const T *>(p.v_target)[b];
     T *tg = static_cast<T *>(p.targets) + (size_t)b * p.N * 4;
-    for (int k = 0; k < p.N; ++k) {
-        tg[k * 4 + 0] = r + ((T)k * (T)p.T) * v;
-        tg[k * 4 + 1] = T(0);
-        tg[k * 4 + 2] = v;
-        tg[k * 4 + 3] = T(0);
-    }
-    T *gl = static_cast<T *>(p.goal) + (size_t)b * 4;
-    gl[0] = r + ((T)p.N * (T)p.T) * v;
-    gl[1] = T(0);
-    gl[2] = v;
-    gl[3] = T(0);
+    for (int k = 0; k < p.N; ++k) pendulum_target<T>(tg + k * 4, r, v, k, (T)p.T);
+    pendulum_target<T>(static_cast<T *>(p.goal) + (size_t)b * 4, r, v, p.N, (T)p.T);
 }
 
 // ---------------------------------------------------------------------------
@@ -118,15 +173,7 @@ __global__ void __launch_bounds__(128) lipm_step_kernel(const LipmStepParams p) 
         const bool ok = p.status[b] == 0;
         const T jerk = ok ? static_cast<const T *>(p.U)[(size_t)b * p.n] : T(0);
         if (!ok && p.unsolved) atomicAdd(p.unsolved, 1);
-        const T dt = (T)p.dt;
-        for (int s = 0; s < p.substeps; ++s) {
-            // constant-jerk integration (:219-225)
-            const T p1 = pos + dt * (vel + dt * (acc / T(2) + dt * jerk / T(6)));
-            const T v1 = vel + dt * (acc + dt * (jerk / T(2)));
-            acc = acc + dt * jerk;
-            pos = p1;
-            vel = v1;
-        }
+        lipm_integrate<T>(pos, vel, acc, jerk, p.substeps, (T)p.dt);
         st[0] = pos, st[1] = vel, st[2] = acc;
         // PhaseStepper.advance and the foot switch (:331-334)
         index = index + 1 >= cyc ? 0 : index + 1;
@@ -142,42 +189,14 @@ __global__ void __launch_bounds__(128) lipm_step_kernel(const LipmStepParams p) 
         T *tr = static_cast<T *>(p.traj) + (size_t)b * 3;
         tr[0] = pos, tr[1] = vel, tr[2] = acc;
     }
-    // get_nb_steps (:132-163): lengths of the six phases that cover the horizon
-    int off = index;
-    const int n0 = max(0, p.nb_dsp - off);
-    off = max(0, off - p.nb_dsp);
-    const int n1 = max(0, p.nb_ssp - off);
-    int rem = p.N - n0 - n1;
-    const int n2 = min(p.nb_dsp, rem);
-    rem = max(0, rem - p.nb_dsp);
-    const int n3 = min(p.nb_ssp, rem);
-    rem = max(0, rem - p.nb_ssp);
-    const int n4 = min(p.nb_dsp, rem);
-    rem = max(0, rem - p.nb_dsp);
-    // (the sixth phase takes what is left: at most nb_ssp steps for horizons of two steps)
-    // update_goal_and_constraints (:175-205)
+    const LipmPhases ph = lipm_phases(index, p.nb_dsp, p.nb_ssp, p.N);
     const T next = foot + strides[sidx];
     const T last = next + strides[(sidx + 1) % 2];
     const T hf = T(0.5) * (T)p.foot_size, big = (T)p.max_zmp;
     T *e = static_cast<T *>(p.e) + (size_t)b * p.N * 2;
-    for (int k = 0; k < p.N; ++k) {
-        T hi = big, lo = big;
-        int j = k;
-        if (j < n0) {
-        } else if ((j -= n0) < n1) {
-            hi = foot + hf, lo = -(foot - hf);
-        } else if ((j -= n1) < n2) {
-        } else if ((j -= n2) < n3) {
-            hi = next + hf, lo = -(next - hf);
-        } else if ((j -= n3) < n4) {
-        } else {
-            hi = last + hf, lo = -(last - hf);
-        }
-        e[2 * k] = hi;
-        e[2 * k + 1] = lo;
-    }
+    for (int k = 0; k < p.N; ++k) lipm_bounds<T>(ph, k, foot, next, last, hf, big, e[2 * k], e[2 * k + 1]);
     T *gl = static_cast<T *>(p.goal) + (size_t)b * 3;
-    gl[0] = n4 > 0 ? last : next;
+    gl[0] = ph.n4 > 0 ? last : next;
     gl[1] = T(0);
     gl[2] = T(0);
 }

@@ -510,8 +510,8 @@ int qpmpc_b200_factor(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, v
     return (int)cudaGetLastError();
 }
 
-int qpmpc_b200_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
-                              const qpmpc_b200_outputs *out, void *stream) {
+static int solve_factored_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                               const qpmpc_b200_outputs *out, const LoopDev *loop, void *stream) {
     int rc = check_desc(d, in);
     if (rc) return rc;
     if (!record || !out || !out->U || !out->status) return QPMPC_B200_EINVAL;
@@ -525,11 +525,23 @@ int qpmpc_b200_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operand
     p.iters = out->iters;
     p.Z = out->Z;
     p.record = record;
+    if (loop) p.loop = *loop;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool f64 = d->dtype == QPMPC_B200_F64;
     if (np == 8) return f64 ? launch_solve_pre<double, 8>(p, s) : launch_solve_pre<float, 8>(p, s);
     if (np == 16) return f64 ? launch_solve_pre<double, 16>(p, s) : launch_solve_pre<float, 16>(p, s);
     return f64 ? launch_solve_pre<double, 32>(p, s) : launch_solve_pre<float, 32>(p, s);
+}
+
+int qpmpc_b200_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                              const qpmpc_b200_outputs *out, void *stream) {
+    return solve_factored_impl(d, in, record, out, nullptr, stream);
+}
+
+// The closed loops with a factored model run as ONE launch of the shared-model kernel
+// (SolveParams::loop); QPMPC_B200_LOOP_FUSED=0 keeps two launches per cycle.
+static bool loop_fused(const void *record, int cycles) {
+    return record && cycles > 0 && env_int("QPMPC_B200_LOOP_FUSED", 1) != 0;
 }
 
 int qpmpc_b200_integrate(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *U, void *X,
@@ -609,6 +621,18 @@ int qpmpc_b200_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_o
         count_launch();
     };
     step(0, 0);  // targets of the first cycle from the initial state
+    if (loop_fused(loop->record, loop->cycles)) {
+        LoopDev ld;
+        std::memset(&ld, 0, sizeof(ld));
+        ld.kind = 1, ld.cycles = loop->cycles, ld.substeps = loop->substeps;
+        ld.dt = pp.dt, ld.T = pp.T, ld.omega2 = pp.omega2, ld.g = pp.g;
+        ld.state = pp.state, ld.v_target = pp.v_target, ld.goal = pp.goal, ld.targets = pp.targets;
+        ld.traj = loop->trajectory;
+        ld.unsolved = loop->unsolved, ld.upright = loop->upright;
+        ld.iter_sum = (loop->iterations && out->iters) ? reinterpret_cast<long long *>(loop->iterations) : nullptr;
+        int rc = solve_factored_impl(d, in, loop->record, out, &ld, stream);
+        return rc ? rc : (int)cudaGetLastError();
+    }
     for (int c = 0; c < loop->cycles; ++c) {
         int rc = loop->record ? qpmpc_b200_solve_factored(d, in, loop->record, out, stream)
                               : qpmpc_b200_solve(d, in, out, stream);
@@ -655,6 +679,20 @@ int qpmpc_b200_lipm_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_opera
         count_launch();
     };
     step(0, 0);  // bounds and goal of the first cycle
+    if (loop_fused(loop->record, loop->cycles)) {
+        LoopDev ld;
+        std::memset(&ld, 0, sizeof(ld));
+        ld.kind = 2, ld.cycles = loop->cycles, ld.substeps = loop->substeps;
+        ld.dt = pp.dt, ld.nb_dsp = pp.nb_dsp, ld.nb_ssp = pp.nb_ssp;
+        ld.foot_size = pp.foot_size, ld.max_zmp = pp.max_zmp;
+        ld.state = pp.state, ld.goal = pp.goal, ld.e = pp.e;
+        ld.support_foot = pp.support_foot, ld.strides = pp.strides;
+        ld.phase_index = pp.phase_index, ld.stride_index = pp.stride_index;
+        ld.traj = loop->trajectory;
+        ld.unsolved = loop->unsolved;
+        int rc = solve_factored_impl(d, in, loop->record, out, &ld, stream);
+        return rc ? rc : (int)cudaGetLastError();
+    }
     for (int c = 0; c < loop->cycles; ++c) {
         int rc = loop->record ? qpmpc_b200_solve_factored(d, in, loop->record, out, stream)
                               : qpmpc_b200_solve(d, in, out, stream);

@@ -483,8 +483,8 @@ int emu_factor(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, void *re
     launch(1, 128, FACTOR_SMEM_BYTES, [&]() { mpc_factor_kernel<double>(fp); });
     return 0;
 }
-int emu_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
-                       const qpmpc_b200_outputs *out, int wpc) {
+static int emu_solve_factored_impl(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                                   const qpmpc_b200_outputs *out, const LoopDev *loop, int wpc) {
     int rc = check_desc(d, in);
     if (rc) return rc;
     const int np = emu_factor_np(d);
@@ -497,9 +497,18 @@ int emu_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, 
     p.iters = out->iters;
     p.Z = out->Z;
     p.record = record;
+    if (loop) p.loop = *loop;
     if (np == 8) return solve_pre<double, 8>(p, wpc);
     if (np == 16) return solve_pre<double, 16>(p, wpc);
     return solve_pre<double, 32>(p, wpc);
+}
+int emu_solve_factored(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const void *record,
+                       const qpmpc_b200_outputs *out, int wpc) {
+    return emu_solve_factored_impl(d, in, record, out, nullptr, wpc);
+}
+// (qpmpc_b200.cu: loop_fused)
+static bool emu_loop_fused(const void *record, int cycles) {
+    return record && cycles > 0 && env_int("QPMPC_B200_LOOP_FUSED", 1) != 0;
 }
 
 int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in, const qpmpc_b200_outputs *out,
@@ -531,6 +540,17 @@ int emu_pendulum_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands
         launch(grid, threads, 0, [&]() { pendulum_step_kernel<double>(pp); });
     };
     step(0, 0);
+    if (emu_loop_fused(loop->record, loop->cycles)) {
+        LoopDev ld;
+        std::memset(&ld, 0, sizeof(ld));
+        ld.kind = 1, ld.cycles = loop->cycles, ld.substeps = loop->substeps;
+        ld.dt = pp.dt, ld.T = pp.T, ld.omega2 = pp.omega2, ld.g = pp.g;
+        ld.state = pp.state, ld.v_target = pp.v_target, ld.goal = pp.goal, ld.targets = pp.targets;
+        ld.traj = loop->trajectory;
+        ld.unsolved = loop->unsolved, ld.upright = loop->upright;
+        ld.iter_sum = (loop->iterations && out->iters) ? (long long *)loop->iterations : nullptr;
+        return emu_solve_factored_impl(d, in, loop->record, out, &ld, 0);
+    }
     for (int c = 0; c < loop->cycles; ++c) {
         const int rc = loop->record ? emu_solve_factored(d, in, loop->record, out, 0) : emu_solve(d, in, out, 0);
         if (rc) return rc;
@@ -561,6 +581,19 @@ int emu_lipm_closed_loop(const qpmpc_b200_desc *d, const qpmpc_b200_operands *in
         launch(grid, threads, 0, [&]() { lipm_step_kernel<double>(pp); });
     };
     step(0, 0);
+    if (emu_loop_fused(loop->record, loop->cycles)) {
+        LoopDev ld;
+        std::memset(&ld, 0, sizeof(ld));
+        ld.kind = 2, ld.cycles = loop->cycles, ld.substeps = loop->substeps;
+        ld.dt = pp.dt, ld.nb_dsp = pp.nb_dsp, ld.nb_ssp = pp.nb_ssp;
+        ld.foot_size = pp.foot_size, ld.max_zmp = pp.max_zmp;
+        ld.state = pp.state, ld.goal = pp.goal, ld.e = pp.e;
+        ld.support_foot = pp.support_foot, ld.strides = pp.strides;
+        ld.phase_index = pp.phase_index, ld.stride_index = pp.stride_index;
+        ld.traj = loop->trajectory;
+        ld.unsolved = loop->unsolved;
+        return emu_solve_factored_impl(d, in, loop->record, out, &ld, 0);
+    }
     for (int c = 0; c < loop->cycles; ++c) {
         const int rc = loop->record ? emu_solve_factored(d, in, loop->record, out, 0) : emu_solve(d, in, out, 0);
         if (rc) return rc;

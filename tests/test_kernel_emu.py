@@ -587,7 +587,7 @@ def _cpu_walking_loop(w, cycles):
     return np.stack(traj), foot, pidx, sidx
 
 
-@pytest.mark.parametrize("factored", [False, True])
+@pytest.mark.parametrize("factored", [False, True, "two_launches_per_cycle"])
 def test_lipm_walking_closed_loop_matches_the_cpu_loop(factored, emulated_engine, monkeypatch):
     """The walking loop (phase machine + solve + constant-jerk integration) on the emulated
     device against the CPU loop: states, support foot and phase after 40 cycles (five foot
@@ -596,6 +596,8 @@ def test_lipm_walking_closed_loop_matches_the_cpu_loop(factored, emulated_engine
     from qpmpc_b200.workloads import lipm_walking_batch, to_batched
 
     monkeypatch.setenv("QPMPC_B200_LR", "0")
+    if factored == "two_launches_per_cycle":  # (True: the whole loop is ONE launch of the shared-model kernel)
+        monkeypatch.setenv("QPMPC_B200_LOOP_FUSED", "0")
     w = lipm_walking_batch(6, seed=4)
     ref, foot, pidx, sidx = _cpu_walking_loop(w, 40)
     prob = to_batched(w)
@@ -609,6 +611,40 @@ def test_lipm_walking_closed_loop_matches_the_cpu_loop(factored, emulated_engine
     # lateral sway (the strides alternate in sign): the centre of mass moves and stays between the feet
     pos = traj[:, :, 0].numpy()
     assert np.abs(pos).max() < 0.3 and np.abs(pos).max(axis=0).min() > 0.01
+
+
+def test_pendulum_closed_loop_in_one_launch_matches_two_launches_per_cycle(emulated_engine, monkeypatch):
+    """The receding-horizon loop of BASELINE config 3 with a factored model: all cycles inside
+    ONE launch of the shared-model kernel (SolveParams::loop -- each lane group solves, moves its
+    plant and rewrites its targets in shared memory) against a solve and a plant launch per
+    cycle.  Same trajectory, final plan, counters and per-cycle iteration sums; a batch that
+    leaves lane groups of the last CTA without an instance."""
+    import torch
+
+    from qpmpc_b200 import factor_model, pendulum_closed_loop
+    from qpmpc_b200.workloads import pendulum_targets, to_batched
+
+    def run(fused):
+        monkeypatch.setenv("QPMPC_B200_LOOP_FUSED", fused)
+        w = pendulum_batch(19, seed=7)
+        prob = to_batched(w)
+        tg, goal = pendulum_targets(w["x0"], w["v_target"], w["N"], w["T"])
+        prob.update_goal_state(goal)
+        prob.update_target_states(tg)
+        model = factor_model(prob)
+        plan, traj, unsolved, stats = pendulum_closed_loop(prob, w["v_target"], 25, record=True, stats=True, factored=model)
+        return plan, traj, unsolved, stats, prob
+
+    a = run("1")
+    b = run("0")
+    assert int(a[2].item()) == int(b[2].item()) == 0
+    assert np.abs(a[1].numpy() - b[1].numpy()).max() <= 1e-12
+    assert np.abs(a[0].inputs.numpy() - b[0].inputs.numpy()).max() <= 1e-10
+    assert torch.equal(a[0].status, b[0].status) and torch.equal(a[0].iters, b[0].iters)
+    assert torch.equal(a[3]["iterations"], b[3]["iterations"]) and int(a[3]["upright"].item()) == int(b[3]["upright"].item())
+    # what the loop leaves in the problem: the state and the next cycle's vectors
+    for name in ("x0", "goal", "targets"):
+        assert np.abs(getattr(a[4], name).numpy() - getattr(b[4], name).numpy()).max() <= 1e-12, name
 
 
 def test_lipm_phase_vectors_follow_the_reference_pattern():
