@@ -565,8 +565,8 @@ def test_solve_host_paths_are_bit_identical(path, kind, monkeypatch):
         assert torch.equal(Z, plan.multipliers.cpu())
 
 
-@pytest.mark.parametrize("factored", [False, True])
-def test_pendulum_closed_loop_1024_instances_200_cycles_against_the_cpu_loop(factored):
+@pytest.mark.parametrize("factored", [False, True, "two_launches_per_cycle"])
+def test_pendulum_closed_loop_1024_instances_200_cycles_against_the_cpu_loop(factored, monkeypatch):
     """BASELINE config 3 at full length: 1 024 instances x 200 receding-horizon cycles on the
     device (re-condensing every cycle, or with the model factored once: qpmpc_b200_factor +
     qpmpc_b200_solve_factored) against the CPU loop (oracle + host plant), state by state for
@@ -577,6 +577,8 @@ def test_pendulum_closed_loop_1024_instances_200_cycles_against_the_cpu_loop(fac
     from qpmpc_b200 import factor_model, pendulum_closed_loop
     from qpmpc_b200.workloads import pendulum_batch, pendulum_targets, to_batched
 
+    if factored == "two_launches_per_cycle":  # (True: the whole loop inside ONE launch of the shared-model kernel)
+        monkeypatch.setenv("QPMPC_B200_LOOP_FUSED", "0")
     B, cycles = 1024, 200
     w = pendulum_batch(B, seed=1)
     ref, ref_iters = _cpu_closed_loop(w, cycles, return_iters=True)
@@ -629,8 +631,8 @@ def test_factored_model_matches_the_full_path_on_the_device():
         assert np.abs(U[ok] - ref["U"][ok]).max() <= U_TOL
 
 
-@pytest.mark.parametrize("factored", [False, True])
-def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored):
+@pytest.mark.parametrize("factored", [False, True, "two_launches_per_cycle"])
+def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored, monkeypatch):
     """The walking controller of examples/lipm_walking_controller.py:307-335 (LTV constraint
     vector rewritten every cycle by the phase machine, goal update, 300 cycles), 256 instances
     on the device against the CPU loop (numpy phase machine + oracle): states of every cycle,
@@ -640,6 +642,8 @@ def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored):
     from qpmpc_b200 import factor_model, lipm_walking_closed_loop
     from qpmpc_b200.workloads import lipm_advance, lipm_phase_vectors, lipm_walking_batch, to_batched
 
+    if factored == "two_launches_per_cycle":  # (True: the whole loop inside ONE launch of the shared-model kernel)
+        monkeypatch.setenv("QPMPC_B200_LOOP_FUSED", "0")
     B, cycles = 256, 300
     w = lipm_walking_batch(B, seed=4)
     x, foot = w["x0"].copy(), w["support_foot"].copy()

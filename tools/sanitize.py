@@ -64,6 +64,15 @@ for w in (pendulum_batch(37, seed=15), humanoid_batch(21, seed=16), triple_integ
     plan = solve_mpc_batch(prob, factored=factor_model(prob), return_multipliers=True)
     torch.cuda.synchronize()
     print("factored", w["name"], "unsolved", int((plan.status != 0).sum()), flush=True)
+w = pendulum_batch(21, seed=20)   # fused loop (one launch), lane groups of the last CTA without an instance
+prob = to_batched(w)
+from qpmpc_b200.workloads import pendulum_targets
+tg, goal = pendulum_targets(w["x0"], w["v_target"], w["N"], w["T"])
+prob.update_goal_state(goal)
+prob.update_target_states(tg)
+plan, traj, unsolved, stats = pendulum_closed_loop(prob, w["v_target"], 7, record=True, stats=True, factored=factor_model(prob))
+torch.cuda.synchronize()
+print("fused pendulum loop ok, unsolved", int(unsolved.item()))
 w = lipm_walking_batch(24)
 prob = to_batched(w)
 plan, traj, unsolved, _ = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
