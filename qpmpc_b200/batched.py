@@ -236,11 +236,25 @@ class BatchedMPCProblem:
 
     # -- C ABI views ----------------------------------------------------------
 
+    def __setattr__(self, name, value):
+        # the C-ABI views below are cached (a small batch is bound by this call path, not by the
+        # kernel); rebinding any attribute -- an operand, a weight, a state -- drops them.  Writing
+        # INTO a tensor changes neither its address nor the descriptor.
+        object.__setattr__(self, name, value)
+        if name[:3] != "_c_":
+            object.__setattr__(self, "_c_ops", None)
+            object.__setattr__(self, "_c_desc", {})
+
     def desc(self, method: int = _capi.ACTIVE_SET, max_iter: int = 0, tol: float = 0.0,
              polish: bool = True) -> _capi.Desc:
+        """The descriptor of the C ABI (cached: treat it as read-only)."""
+        key = (method, max_iter, tol, polish)
+        d = self._c_desc.get(key)
+        if d is not None:
+            return d
         if self.x0 is None:
             raise ProblemDefinitionError("initial state is undefined")  # mpc_qp.py:49-51
-        d = _capi.Desc()
+        d = self._c_desc[key] = _capi.Desc()
         d.batch, d.N = self.batch_size, self.nb_timesteps
         d.nx, d.nu, d.nc = self.state_dim, self.input_dim, self.ineq_dim
         d.dtype = _DTYPE_CODE[self.dtype]
@@ -258,10 +272,15 @@ class BatchedMPCProblem:
         return d
 
     def operands(self) -> _capi.Operands:
-        return _capi.Operands(
-            _ptr(self.A), _ptr(self.B), _ptr(self.C), _ptr(self.D), _ptr(self.e),
-            _ptr(self.x0), _ptr(self.goal), _ptr(self.targets),
-        )
+        """The operand pointers of the C ABI (cached: treat them as read-only)."""
+        ops = self._c_ops
+        if ops is None:
+            ops = _capi.Operands(
+                _ptr(self.A), _ptr(self.B), _ptr(self.C), _ptr(self.D), _ptr(self.e),
+                _ptr(self.x0), _ptr(self.goal), _ptr(self.targets),
+            )
+            object.__setattr__(self, "_c_ops", ops)
+        return ops
 
     # -- construction from host-side problems ---------------------------------
 

@@ -91,7 +91,9 @@ int launch_solve_pre(SolveParams p, cudaStream_t stream) {
     p.inst_stride = (L::fixed + 3) / 4 * 4;
     p.gt_off = p.g_off = p.scr_off = 0;
     const FactorLay F = factor_layout(NP, p.nx, p.N, p.q_wx != 0);
-    int wpc = env_int("QPMPC_B200_WPC", 8);
+    // (a fused loop copies the record once per CTA for all its cycles: smaller CTAs cost nothing and
+    // even out the last wave -- measured 382 -> 399 M solves/s on config 3)
+    int wpc = env_int("QPMPC_B200_WPC", p.loop.kind != 0 ? 4 : 8);
     wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
     size_t smem = 0;
     for (;; --wpc) {
