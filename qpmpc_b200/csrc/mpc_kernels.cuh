@@ -38,9 +38,11 @@
 #ifndef QPMPC_MINB
 #define QPMPC_MINB 4
 #endif
-// single precision needs half the registers for the same arrays: 3 CTAs of 8 warps per SM
+// single precision needs half the registers for the same arrays: 4 CTAs of 8 warps per SM
+// (64 registers, 136 B of spills; config 4's 8 192 instances then fit in ONE wave of the
+// machine: measured 219 (3 CTAs, 80 registers) -> 250 M solves/s; 2 CTAs at 125 registers: 233)
 #ifndef QPMPC_MINB_F32
-#define QPMPC_MINB_F32 3
+#define QPMPC_MINB_F32 4
 #endif
 // paired-row variants (one stored row per lane): resident CTAs of 8 warps per SM, double precision
 #ifndef QPMPC_MINB_PAIRED

@@ -29,6 +29,7 @@ cases = [
     triple_integrator_batch(3, N=64, seed=4),
     triple_integrator_batch(5, N=48, seed=7),
     triple_integrator_batch(7, N=24, seed=8),
+    triple_integrator_batch(3, N=96, seed=9),   # CTA kernel out of its global-memory workspace
     humanoid_batch(19),
     pendulum_batch(23),
     pendulum_batch(11, ltv_model=True),
