@@ -746,6 +746,8 @@ int qpmpc_b200_solve_host(const qpmpc_b200_desc *d, const qpmpc_b200_operands *i
             for (int o = 0; o < OP_COUNT; ++o) {
                 const OperandView &v = p.op[o];
                 if (!v.ptr || v.per_instance) continue;
+                // (letting every CTA read small shared operands from host memory instead was measured:
+                // config 4 end to end 102 -> 74 M solves/s -- the copy call is cheaper)
                 bool moved = false;
                 if ((e = ensure(&c.buf[o], &c.cap[o], (size_t)v.sz * es, &moved)) != cudaSuccess) return (int)e;
                 if (moved) c.drop_graphs();  // (graphs of the staged path hold the old address)
