@@ -24,7 +24,7 @@ namespace qpmpc {
 // consecutive addresses: X[t * NP + l].
 struct FactorLay {
     int NP, LDL, LDG;
-    int oL, oDv, oLinv, oM, oRowc, oG, oFx, oFg, oHx, oFt, total;
+    int oL, oDv, oLinv, oM, oRowc, oG, oFx, oFg, oHx, oFt, oLinvT, oMT, LDM, total;
 };
 __host__ __device__ inline int up4(int v) { return (v + 3) / 4 * 4; }
 __host__ __device__ inline FactorLay factor_layout(int NP, int nx, int N, bool has_ft) {
@@ -43,6 +43,11 @@ __host__ __device__ inline FactorLay factor_layout(int NP, int nx, int N, bool h
     F.oFg = o, o += nx * NP;
     F.oHx = o, o += nx * NP;             // Hx of the stored (+) rows: Hx[t * NP + srow]
     F.oFt = o, o += has_ft ? N * nx * NP : 0;
+    // for the recovery of x = -L^-T (t + M_A' lambda) by two short products instead of two
+    // substitutions: L^-1 by ROWS (LinvT[k * NP + l] = (L^-1)_kl) and the stored rows of M by rows
+    F.LDM = NP + 1;
+    F.oLinvT = o, o += NP * NP;
+    F.oMT = o, o += up4(NP * F.LDM);     // MT[srow * LDM + c] = M[srow][c]
     F.total = up4(o);
     return F;
 }
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(128) mpc_factor_kernel(const FactorParams p) {
         if (c <= r) {
             R[F.oL + c * F.LDL + r] = Ls[r * 33 + c];
             R[F.oLinv + c * NP + r] = Li[r * 33 + c];
+            R[F.oLinvT + r * NP + c] = Li[r * 33 + c];
         }
     }
     for (int c = tid; c < NP; c += nt) R[F.oDv + c] = bad ? Num<T>::nan() : T(1) / Ls[c * 33 + c];
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(128) mpc_factor_kernel(const FactorParams p) {
             T s = T(0);  // M[srow][c] = sum_k G[srow][k] Linv[c][k]
             for (int kk = 0; kk <= c && kk < n; ++kk) s += g[kk] * Li[c * 33 + kk];
             R[F.oM + c * NP + srow] = s;
+            R[F.oMT + srow * F.LDM + c] = s;
             m2 += s * s;
         }
         R[F.oRowc + srow] = sqrt_(g2);

@@ -1353,6 +1353,7 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
         __syncwarp();
     }
 
+    const int araw = aidx;  // (paired: stored row | sign bit)
     if (PAIRED && aidx >= 0) {
         // stored row | sign -> index of the row in G / h
         const int sr = aidx & 0x7fff, sk = sr / half;
@@ -1363,7 +1364,29 @@ __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8)
     // one-shot) recovery code together so that they share instruction fetches.
     if (!HASJ && QPMPC_SYNC_TAIL && !looping) __syncthreads();  // (a fused loop would pay the wait every cycle)
     // ---- x from the multipliers (J not kept): x = -P^-1 (q + G_A' lambda)  // @phase D x from multipliers
-    if (!HASJ) {
+    if constexpr (PRE) {
+        // shared model: L^-1 (q + G_A' lambda) = t + M_A' lambda with t (still in xs) and the rows of
+        // M = G+ L^-T from the record, then x = -L^-T y with L^-1 by rows: two short products,
+        // no substitution (the substitutions are 2 NP dependent shuffles)
+        T y = xs[l];
+        const int namax = __reduce_max_sync(FULL_MASK, st == 0 ? na : 0);
+        for (int i = 0; i < namax; ++i) {
+            const T li = __shfl_sync(FULL_MASK, lam, i, NP);
+            const int ai = __shfl_sync(FULL_MASK, araw, i, NP);
+            if (i < na && st == 0) y += ((ai & 0x8000) ? -li : li) * rec[F.oMT + (ai & 0x7fff) * F.LDM + l];
+        }
+        __syncwarp();
+        xs[l] = y;
+        __syncwarp();
+        T xa = T(0), xb = T(0);
+#pragma unroll
+        for (int k = 0; k < NP; k += 2) {
+            const T2 v = *reinterpret_cast<const T2 *>(xs + k);
+            xa += rec[F.oLinvT + k * NP + l] * v.x;
+            xb += rec[F.oLinvT + (k + 1) * NP + l] * v.y;
+        }
+        x = -(xa + xb);
+    } else if (!HASJ) {
         // w_l = q_l + sum_i lambda_i G[a_i, l]
         T w = qs[l];
         {
