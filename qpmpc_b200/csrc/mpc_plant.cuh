@@ -26,12 +26,13 @@ template <typename T>
 __device__ __forceinline__ void pendulum_integrate(T &r, T &th, T &rd, T &thd, T u, int substeps, T dt, T w2, T g) {
     T sn, cs;
     sincos_(th, &sn, &cs);
+    const T rdd = u;
+    const T ug = rdd / g, hu = rdd / T(2);  // (the input is constant over the cycle: one division)
     for (int s = 0; s < substeps; ++s) {
-        const T rdd = u;
-        const T thdd = w2 * (sn - (rdd / g) * cs);
-        r = r + dt * (rd + dt * (rdd / T(2)));
+        const T thdd = w2 * (sn - ug * cs);
+        r = r + dt * (rd + dt * hu);
         rd = rd + dt * rdd;
-        const T dth = dt * (thd + dt * (thdd / T(2)));
+        const T dth = dt * (thd + dt * (thdd * T(0.5)));
         th = th + dth;
         thd = thd + dt * thdd;
         if (s + 1 < substeps) {
@@ -59,9 +60,10 @@ __device__ __forceinline__ void pendulum_target(T *tg, T r, T v, int k, T Ts) {
 // constant-jerk integration (examples/lipm_walking_controller.py:219-225)
 template <typename T>
 __device__ __forceinline__ void lipm_integrate(T &pos, T &vel, T &acc, T jerk, int substeps, T dt) {
+    const T j6 = dt * jerk / T(6), j2 = jerk / T(2);  // (constant over the cycle: one division)
     for (int s = 0; s < substeps; ++s) {
-        const T p1 = pos + dt * (vel + dt * (acc / T(2) + dt * jerk / T(6)));
-        const T v1 = vel + dt * (acc + dt * (jerk / T(2)));
+        const T p1 = pos + dt * (vel + dt * (acc * T(0.5) + j6));
+        const T v1 = vel + dt * (acc + dt * j2);
         acc = acc + dt * jerk;
         pos = p1;
         vel = v1;
