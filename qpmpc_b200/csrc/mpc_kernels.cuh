@@ -642,17 +642,24 @@ __device__ __forceinline__ void fsolve(const T *Lc, const T *dv, T (&a)[NP], T (
     }
 }
 
-// Minimum / maximum of non-negative values over the NP lanes of an instance.
+// Minimum / maximum of non-negative values over the NP lanes of an instance.  NP = 32: REDUX.
+// Narrower groups (several instances per warp, each with its own member mask): shuffle
+// butterflies.  REDUX with one member mask per group (QPMPC_SEG_REDUX=1) gives the same results
+// but the groups of a warp are then served one after the other: measured 147 -> 136 M solves/s
+// on config 2, 522 -> 431 at N = 8.
+#ifndef QPMPC_SEG_REDUX
+#define QPMPC_SEG_REDUX 0
+#endif
 template <typename T, int NP>
 __device__ __forceinline__ T group_min_pos(T v, unsigned segmask) {
-    if (NP == 32) return seg_min_pos(v, segmask);
+    if (NP == 32 || QPMPC_SEG_REDUX) return seg_min_pos(v, segmask);
 #pragma unroll
     for (int off = NP / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
     return v;
 }
 template <typename T, int NP>
 __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
-    if (NP == 32) return seg_max_pos(v, segmask);
+    if (NP == 32 || QPMPC_SEG_REDUX) return seg_max_pos(v, segmask);
 #pragma unroll
     for (int off = NP / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, off, NP));
     return v;
