@@ -496,6 +496,14 @@ static int emu_solve_factored_impl(const qpmpc_b200_desc *d, const qpmpc_b200_op
     p.status = out->status;
     p.iters = out->iters;
     p.Z = out->Z;
+    {   // (qpmpc_b200.cu: solve_factored_impl -- long terminal-cost horizons take the structure-exploiting kernel)
+        const int lr = env_int("QPMPC_B200_LR", -1);
+        const bool paired = d->paired != 0 && d->nc > 0 && (d->nc & 1) == 0 && env_int("QPMPC_B200_NO_PAIRED", 0) == 0;
+        if (!loop && d->method == QPMPC_B200_ACTIVE_SET && lr != 0 && env_int("QPMPC_B200_FORCE_CTA", 0) == 0 &&
+            lr_applicable(p, paired) && (p.n > 16 || (p.n > 8 && env_int("QPMPC_B200_LR16", LR16_DEFAULT) != 0)) &&
+            env_int("QPMPC_B200_FACTORED_LR", 1) != 0)
+            return emu_solve(d, in, out, wpc);
+    }
     p.record = record;
     if (loop) p.loop = *loop;
     if (np == 8) return solve_pre<double, 8>(p, wpc);
