@@ -353,6 +353,54 @@ def test_fp32_humanoid_within_stated_tolerance():
     assert err.max() <= 1e-4, err.max()
 
 
+def test_fp32_shared_model_path_and_walking_loop():
+    """Single precision through the shared-model path: the humanoid pattern (BASELINE config 4)
+    with the model factored once holds the fp32 bar against the fp64 oracle, and the walking
+    loop of the same model (the closed-loop form of config 4), all 300 cycles in one fp32 launch,
+    stays within 2e-3 of the fp64 CPU loop with every cycle solved."""
+    import torch
+
+    from qpmpc_b200 import factor_model, lipm_walking_closed_loop, solve_mpc_batch
+    from qpmpc_b200.workloads import (humanoid_batch, lipm_advance, lipm_phase_vectors, lipm_walking_batch,
+                                      to_batched)
+
+    w = humanoid_batch(1024)
+    ref = _oracle(w)
+    prob = to_batched(w, dtype=torch.float32)
+    plan = solve_mpc_batch(prob, factored=factor_model(prob))
+    U = plan.inputs.reshape(1024, -1).double().cpu().numpy()
+    ok = (plan.status.cpu().numpy() == 0) & (ref["status"] == 0)
+    assert ok.mean() > 0.99
+    scale = np.maximum(1.0, np.abs(ref["U"][ok]).max(axis=1))
+    err = (np.abs(U[ok] - ref["U"][ok]).max(axis=1) / scale).max()
+    assert err <= 1e-4, err
+
+    import oracle
+    from qpmpc_b200.workloads import oracle_ops
+
+    B, cycles = 64, 300
+    w = lipm_walking_batch(B, seed=4)
+    x, foot = w["x0"].copy(), w["support_foot"].copy()
+    pidx, sidx = w["phase_index"].copy(), w["stride_index"].copy()
+    traj = [x.copy()]
+    for _ in range(cycles):
+        e, goal = lipm_phase_vectors(w, foot, pidx, sidx)
+        wc = dict(w, e=e, goal=goal, x0=x)
+        r = oracle.solve_batch(B, w["N"], w["nx"], w["nu"], w["nc"], oracle_ops(wc), w["w_t"], w["w_x"], w["w_u"])
+        assert (r["status"] == 0).all()
+        x, foot, pidx, sidx = lipm_advance(w, x, r["U"][:, 0], foot, pidx, sidx)
+        traj.append(x.copy())
+    ref_traj = np.stack(traj)
+    prob = to_batched(w, dtype=torch.float32)
+    plan, got, unsolved, phase = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
+                                                          w["stride_index"], cycles, record=True,
+                                                          factored=factor_model(prob))
+    torch.cuda.synchronize()
+    assert int(unsolved.item()) == 0
+    assert np.abs(got.double().cpu().numpy() - ref_traj).max() <= 2e-3
+    assert np.array_equal(phase["phase_index"].cpu().numpy(), pidx)
+
+
 def _cpu_closed_loop(w, cycles, substeps=15, return_iters=False):
     """The loop of examples/wheeled_inverted_pendulum.py:99-118 on the CPU: the
     oracle solves, the host mirror of the plant integrates."""
