@@ -182,7 +182,9 @@ __device__ __forceinline__ T pdip_solve_inv(const T *Li, T *xs, T w, int l) {
 }
 
 // Row l of H = P + G' diag(wv) G into Hrow and, in the same pass over the
-// rows, g = sum_row G[row, l] tv[row].
+// rows, g = sum_row G[row, l] tv[row].  (Skipping the structurally zero columns of the block
+// lower triangular G, four at a time behind a warp-uniform branch, was measured: 14.4 -> 12.7
+// M solves/s on config 2 -- the straight unrolled stream of FMAs wins.)
 template <typename T, int NP, int LDG, int LDL>
 __device__ __forceinline__ T pdip_build(T (&Hrow)[NP], const T *Pc, const T *Gc, const T *wv, const T *tv, int m,
                                         int l) {
