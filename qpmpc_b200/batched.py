@@ -588,7 +588,9 @@ def pendulum_closed_loop(
     place; goal / targets are (re)allocated per instance.
 
     ``factored``: the model's :func:`factor_model` record (goal and targets must be present in
-    the problem it was made from); every cycle then only rebuilds q and h.
+    the problem it was made from); every cycle then only rebuilds q and h, and the whole loop
+    runs inside ONE kernel launch (each lane group solves, moves its plant and rewrites its
+    targets in shared memory; ``QPMPC_B200_LOOP_FUSED=0``: a solve and a plant launch per cycle).
 
     Returns ``(plan_of_last_cycle, trajectory or None, unsolved_count_tensor)``;
     trajectory is [cycles + 1, B, 4].  With ``stats`` a fourth value: dict(upright = device

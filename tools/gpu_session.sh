@@ -29,6 +29,8 @@ if [ "$WHAT" = all ] || [ "$WHAT" = bench ]; then
     timeout 300 python bench.py --config 5 --horizon $n --batch 262144 --cpu-seconds 2 > $OUT/${TAG}_bench_c5_N$n.json 2>> $OUT/${TAG}_bench.err
     echo "rc=$?"; cat $OUT/${TAG}_bench_c5_N$n.json
   done
+  echo "== config 2's shape with one shared model: full path against the factored one"
+  timeout 200 python tools/shared_model_bench.py > $OUT/${TAG}_shared_model.txt 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_shared_model.txt
   tail -5 $OUT/${TAG}_bench.err
 fi
 if [ "$WHAT" = all ] || [ "$WHAT" = prof ]; then
