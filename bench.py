@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5, 6])
+    ap.add_argument("--f32", action="store_true",
+                    help="config 6 only: run the walking loop in single precision (the precision BASELINE configs[3] names)")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--horizon", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -99,8 +101,12 @@ def make_workload(args, seed):
     return triple_integrator_batch(args.batch, N=args.horizon, seed=(0 if args.config == 2 else 3) + seed)
 
 
+def is_f32(args):
+    return args.config == 4 or (args.config == 6 and getattr(args, "f32", False))
+
+
 def dtype_of(args):
-    return "f32" if args.config == 4 else "f64"
+    return "f32" if is_f32(args) else "f64"
 
 
 def solves_per_step(args):
@@ -116,7 +122,7 @@ def config_dict(args, world, rotate=None):
            "(targets -> condense+solve -> 15 plant substeps per cycle), shared model (BASELINE configs[2])",
         4: f"humanoid/LIPM fp32 nx=3 nu=1 nc=2 N={N} batch={B}/GPU per-instance per-step e_k (BASELINE configs[3])",
         5: f"triple_integrator T=1/N fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU (BASELINE configs[4], one sweep point)",
-        6: f"lipm_walking_controller fp64 nx=3 nu=1 nc=2 N={N} batch={B}/GPU, {WALK_CYCLES}-cycle walking loop: per "
+        6: f"lipm_walking_controller {'fp32' if is_f32(args) else 'fp64'} nx=3 nu=1 nc=2 N={N} batch={B}/GPU, {WALK_CYCLES}-cycle walking loop: per "
            "cycle the phase machine rewrites the per-step ZMP bounds e_k and the goal, condense+solve, 15 "
            "integration substeps (the closed-loop form of BASELINE configs[3]'s LIPM LTV constraints; "
            "examples/lipm_walking_controller.py)",
@@ -391,7 +397,7 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------
 def kernel_name(args):
     n = args.horizon  # nu = 1 in every config
-    t = "float" if args.config == 4 else "double"
+    t = "float" if is_f32(args) else "double"
     if args.method == "pdip":
         return f"mpc_pdip_kernel<{t},NP={8 if n <= 8 else 16 if n <= 16 else 32}>"
     terminal_only = args.config != 3  # config 3 has a stage cost
@@ -557,8 +563,8 @@ def run_b200(args, rank, local_rank, world):
 
     B, N = args.batch, args.horizon
     n = N  # nu = 1
-    tdtype = torch.float32 if args.config == 4 else torch.float64
-    es = 4 if args.config == 4 else 8
+    tdtype = torch.float32 if is_f32(args) else torch.float64
+    es = 4 if is_f32(args) else 8
     w0 = make_workload(args, 1000 * rank)
     bytes_per_solve = algorithmic_bytes_per_solve(w0, es)
     in_bytes = (bytes_per_solve - es * n - 4) * B
@@ -692,12 +698,20 @@ def run_b200(args, rank, local_rank, world):
         kev[1].record()
         torch.cuda.synchronize()
         kernel_ms = kev[0].elapsed_time(kev[1]) / 50
+    # units one launch of the dominant kernel processes: the batch -- or, when the whole closed
+    # loop runs inside ONE launch of the shared-model kernel, the batch times the cycles (the
+    # launch IS the step then)
+    units_per_launch = B
+    fused_loop = loop_cfg and model is not None and os.environ.get("QPMPC_B200_LOOP_FUSED", "1") != "0"
+    if fused_loop:
+        units_per_launch = solves_per_step(args)
+        kernel_ms = total_ms / args.steps
 
     # ---- e2e: host buffers through the C ABI ----------------------------------------------
     lib = _capi.load()
     e2e = None
     if not loop_cfg:
-        np_dtype = np.float32 if args.config == 4 else np.float64
+        np_dtype = np.float32 if is_f32(args) else np.float64
         names = [k for k in ("A", "B", "C", "D", "e", "x0", "goal", "targets") if sets[0][k] is not None]
         host_sets = []
         for w in sets[:min(4, rotate)]:
@@ -834,11 +848,11 @@ def run_b200(args, rank, local_rank, world):
                 hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    achieved_gbs = bytes_per_solve * B / (kernel_ms * 1e-3) / 1e9
+    achieved_gbs = bytes_per_solve * units_per_launch / (kernel_ms * 1e-3) / 1e9
     tf = ctypes.c_double(0.0)
     lib.qpmpc_b200_fp64_peak(local_rank, ctypes.byref(tf))
     f_survey, f_exec = flop_models(args, iters_mean)
-    tfl = lambda f: f * B / (kernel_ms * 1e-3) / 1e12  # noqa: E731
+    tfl = lambda f: f * units_per_launch / (kernel_ms * 1e-3) / 1e12  # noqa: E731
 
     if rank != 0:
         if world > 1:
@@ -861,14 +875,16 @@ def run_b200(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "kernel": kernel_name(args), "kernel_ms": kernel_ms,
-                     "bytes_per_solve": bytes_per_solve,
-                     "note": "latency/FP64-issue bound by design (SURVEY 8d): HBM fraction is "
-                             "necessarily tiny; see fp64"},
+                     "bytes_per_solve": bytes_per_solve, "units_per_launch": units_per_launch,
+                     "note": ("latency/FP64-issue bound by design (SURVEY 8d): HBM fraction is necessarily tiny; see fp64"
+                              + ("; the launch is the whole closed loop: `achieved` counts the algorithmic bytes of every "
+                                 "cycle, `traffic` is what the launch really moved -- the state never leaves the SM "
+                                 "between cycles" if fused_loop else ""))},
         "iters_mean": iters_mean, "gather": gather_kind, "numa_node": numa_node,
         "step_ms_min_max": [min(per_step_ms), max(per_step_ms)],
         "clocks": clocks,
     }
-    if args.config != 4:
+    if not is_f32(args):
         line["fp64"] = {
             "peak_tflops": tf.value,
             "peak_source": "qpmpc_b200_fp64_peak: 16 independent DFMA chains per thread, 8 CTAs of 256 threads "
