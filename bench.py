@@ -861,8 +861,8 @@ def run_b200(args, rank, local_rank, world):
     value = world * solves_per_step(args) * args.steps / (total_ms * 1e-3)
     prof = measured_profile(args)
     traffic, traffic_src = prof["traffic"], prof["source"]
-    if traffic is not None and prof.get("profile_batch") not in (None, B):
-        traffic = traffic * B / prof["profile_batch"]  # the summary's launch had another batch
+    if traffic is not None and prof.get("profile_batch") not in (None, units_per_launch):
+        traffic = traffic * units_per_launch / prof["profile_batch"]  # the summary's launch had another batch
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
