@@ -426,8 +426,8 @@ def measured_profile(args):
             text = open(path).read()
         except OSError:
             continue
-        m = re.search(r"== kernel: void (?:qpmpc::)?(\w+)<", text)
-        if not m or m.group(1) != want:
+        m = re.search(r"== kernel: void (?:qpmpc::)?(\w+)<(\w+),", text)
+        if not m or m.group(1) != want or m.group(2) != ("float" if is_f32(args) else "double"):
             continue
         vals = {}
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
