@@ -605,7 +605,7 @@ def run_b200(args, rank, local_rank, world):
         prob.x0.copy_(x0_src, non_blocking=True)
         return lipm_walking_closed_loop(prob, phase_src["support_foot"].clone(), phase_src["strides"],
                                         phase_src["phase_index"].clone(), phase_src["stride_index"].clone(),
-                                        WALK_CYCLES, factored=model)
+                                        WALK_CYCLES, factored=model if model is not None else False)
 
     def step(i):
         if args.config == 6:
@@ -614,7 +614,7 @@ def run_b200(args, rank, local_rank, world):
             return plan
         if args.config == 3:
             problems[0].x0.copy_(x0_init)
-            plan, _, unsolved, stats = pendulum_closed_loop(problems[0], v_dev, CYCLES, factored=model, stats=True)
+            plan, _, unsolved, stats = pendulum_closed_loop(problems[0], v_dev, CYCLES, factored=model if model is not None else False, stats=True)
             loop_info["unsolved"], loop_info["stats"] = unsolved, stats
             return plan
         if gather is not None:
@@ -824,7 +824,7 @@ def run_b200(args, rank, local_rank, world):
         for _ in range(e2e_steps):
             problems[0].x0.copy_(x0_host, non_blocking=True)
             vd.copy_(v_host, non_blocking=True)
-            pendulum_closed_loop(problems[0], vd, CYCLES, factored=model)
+            pendulum_closed_loop(problems[0], vd, CYCLES, factored=model if model is not None else False)
             xf_host.copy_(problems[0].x0, non_blocking=True)
             torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0

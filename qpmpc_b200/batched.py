@@ -467,6 +467,22 @@ def _model_signature(problem: "BatchedMPCProblem"):
             *(None if t is None else t.data_ptr() for t in (problem.A, problem.B, problem.C, problem.D)))
 
 
+def _resolve_factored(problem: "BatchedMPCProblem", factored):
+    """``factored`` of the closed loops: a :class:`FactoredModel`, ``False`` (never: condense and
+    factor every instance every cycle) or ``None`` (factor the model here when it is shared by
+    the batch -- inside one loop call it cannot change -- else fall back to the full path)."""
+    if factored is False:
+        return None
+    if factored is not None:
+        if factored.signature != _model_signature(problem):
+            raise ProblemDefinitionError("the factored model belongs to another problem")
+        return factored
+    desc = problem.desc()
+    if int(_capi.load().qpmpc_b200_factor_bytes(ctypes.byref(desc))) == 0:
+        return None
+    return factor_model(problem)
+
+
 def factor_model(problem: BatchedMPCProblem) -> FactoredModel:
     """Condense and factor the model of ``problem`` once (``qpmpc_b200_factor``).  Needs A, B, C,
     D shared by the batch and paired constraint rows; raises ``BackendError`` otherwise."""
@@ -577,7 +593,7 @@ def pendulum_closed_loop(
     gravity: float = 9.81,
     sampling_period: float = 0.1,
     record: bool = False,
-    factored: Optional[FactoredModel] = None,
+    factored=None,
     stats: bool = False,
 ):
     """Receding-horizon closed loop of the wheeled inverted pendulum on the
@@ -588,7 +604,9 @@ def pendulum_closed_loop(
     place; goal / targets are (re)allocated per instance.
 
     ``factored``: the model's :func:`factor_model` record (goal and targets must be present in
-    the problem it was made from); every cycle then only rebuilds q and h, and the whole loop
+    the problem it was made from), ``None`` (default: the loop factors the model itself when it is
+    shared by the batch) or ``False`` (condense and factor every instance every cycle).  With a
+    factored model every cycle only rebuilds q and h, and the whole loop
     runs inside ONE kernel launch (each lane group solves, moves its plant and rewrites its
     targets in shared memory; ``QPMPC_B200_LOOP_FUSED=0``: a solve and a plant launch per cycle).
 
@@ -623,8 +641,7 @@ def pendulum_closed_loop(
         unsolved = torch.zeros(1, dtype=torch.int32, device=dev)
         upright = torch.zeros(1, dtype=torch.int32, device=dev) if stats else None
         iter_hist = torch.zeros(max(cycles, 1), dtype=torch.int64, device=dev) if stats else None
-        if factored is not None and factored.signature != _model_signature(problem):
-            raise ProblemDefinitionError("the factored model belongs to another problem")
+        factored = _resolve_factored(problem, factored)
         desc = problem.desc()
         ops = problem.operands()
         outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), None)
@@ -656,7 +673,7 @@ def lipm_walking_closed_loop(
     foot_size: float = 0.065,
     max_zmp_dist: float = 100.0,
     record: bool = False,
-    factored: Optional[FactoredModel] = None,
+    factored=None,
 ):
     """Walking loop of ``examples/lipm_walking_controller.py:307-335`` on the device, batched:
     per cycle the phase machine writes the ZMP bounds ``e_k`` of the horizon and the goal, the
@@ -667,6 +684,9 @@ def lipm_walking_closed_loop(
     ``problem.goal`` [B, 3] are (re)allocated and rewritten every cycle.  ``support_foot`` [B],
     ``phase_index`` [B] and ``stride_index`` [B] are the phase machine's state (updated in place
     when given as device tensors), ``strides`` [B, 2] the alternating strides.
+
+    ``factored`` as in :func:`pendulum_closed_loop` (default: the loop factors the shared model
+    itself and runs all its cycles inside one kernel launch; ``False``: the full path per cycle).
 
     Returns ``(plan_of_last_cycle, trajectory or None, unsolved_count_tensor, phase_state)``
     with ``phase_state = dict(support_foot, phase_index, stride_index)``.  Asynchronous.
@@ -703,8 +723,7 @@ def lipm_walking_closed_loop(
         iters = torch.zeros(B, dtype=torch.int32, device=dev)
         traj = torch.empty((cycles + 1, B, 3), dtype=dt_, device=dev) if record else None
         unsolved = torch.zeros(1, dtype=torch.int32, device=dev)
-        if factored is not None and factored.signature != _model_signature(problem):
-            raise ProblemDefinitionError("the factored model belongs to another problem")
+        factored = _resolve_factored(problem, factored)
         desc = problem.desc()
         ops = problem.operands()
         outs = _capi.Outputs(_ptr(U), _ptr(status), _ptr(iters), None)

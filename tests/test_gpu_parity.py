@@ -451,7 +451,7 @@ def test_pendulum_closed_loop_matches_cpu_loop():
     w = pendulum_batch(48, seed=1)
     ref = _cpu_closed_loop(w, 40)
     prob = to_batched(w)
-    plan, traj, unsolved = pendulum_closed_loop(prob, w["v_target"], 40, record=True)
+    plan, traj, unsolved = pendulum_closed_loop(prob, w["v_target"], 40, record=True, factored=False)
     torch.cuda.synchronize()
     assert int(unsolved.item()) == 0
     got = traj.cpu().numpy()
@@ -638,7 +638,7 @@ def test_pendulum_closed_loop_1024_instances_200_cycles_against_the_cpu_loop(fac
         prob.update_target_states(tg)
         model = factor_model(prob)
     plan, traj, unsolved, stats = pendulum_closed_loop(prob, w["v_target"], cycles, record=True, stats=True,
-                                                      factored=model)
+                                                      factored=model if model is not None else False)
     torch.cuda.synchronize()
     assert int(unsolved.item()) == 0
     got = traj.cpu().numpy()
@@ -709,7 +709,8 @@ def test_lipm_walking_closed_loop_300_cycles_against_the_cpu_loop(factored, monk
     prob = to_batched(w)
     model = factor_model(prob) if factored else None
     plan, traj, unsolved, phase = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
-                                                           w["stride_index"], cycles, record=True, factored=model)
+                                                           w["stride_index"], cycles, record=True,
+                                                           factored=model if model is not None else False)
     torch.cuda.synchronize()
     assert int(unsolved.item()) == 0
     assert np.abs(traj.cpu().numpy() - ref).max() <= 1e-6

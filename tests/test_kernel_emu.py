@@ -603,7 +603,8 @@ def test_lipm_walking_closed_loop_matches_the_cpu_loop(factored, emulated_engine
     prob = to_batched(w)
     model = factor_model(prob) if factored else None
     plan, traj, unsolved, phase = lipm_walking_closed_loop(prob, w["support_foot"], w["strides"], w["phase_index"],
-                                                           w["stride_index"], 40, record=True, factored=model)
+                                                           w["stride_index"], 40, record=True,
+                                                           factored=model if model is not None else False)
     assert int(unsolved.item()) == 0
     assert np.abs(traj.numpy() - ref).max() <= 1e-6
     assert np.abs(phase["support_foot"].numpy() - foot).max() <= 1e-12
@@ -624,19 +625,23 @@ def test_pendulum_closed_loop_in_one_launch_matches_two_launches_per_cycle(emula
     from qpmpc_b200 import factor_model, pendulum_closed_loop
     from qpmpc_b200.workloads import pendulum_targets, to_batched
 
-    def run(fused):
+    def run(fused, explicit=True):
         monkeypatch.setenv("QPMPC_B200_LOOP_FUSED", fused)
         w = pendulum_batch(19, seed=7)
         prob = to_batched(w)
-        tg, goal = pendulum_targets(w["x0"], w["v_target"], w["N"], w["T"])
-        prob.update_goal_state(goal)
-        prob.update_target_states(tg)
-        model = factor_model(prob)
+        model = None  # (None: the loop factors the shared model itself)
+        if explicit:
+            tg, goal = pendulum_targets(w["x0"], w["v_target"], w["N"], w["T"])
+            prob.update_goal_state(goal)
+            prob.update_target_states(tg)
+            model = factor_model(prob)
         plan, traj, unsolved, stats = pendulum_closed_loop(prob, w["v_target"], 25, record=True, stats=True, factored=model)
         return plan, traj, unsolved, stats, prob
 
     a = run("1")
     b = run("0")
+    c = run("1", explicit=False)
+    assert torch.equal(a[1], c[1]) and torch.equal(a[0].inputs, c[0].inputs) and torch.equal(a[3]["iterations"], c[3]["iterations"])
     assert int(a[2].item()) == int(b[2].item()) == 0
     assert np.abs(a[1].numpy() - b[1].numpy()).max() <= 1e-12
     assert np.abs(a[0].inputs.numpy() - b[0].inputs.numpy()).max() <= 1e-10

@@ -45,7 +45,7 @@ for w in cases:
     bad += int((plan.status != 0).sum())
     print(w["name"], w["batch"], "unsolved", int((plan.status != 0).sum()), flush=True)
 w = pendulum_batch(16, seed=1)
-plan, traj, unsolved = pendulum_closed_loop(to_batched(w), w["v_target"], 5, record=True)
+plan, traj, unsolved = pendulum_closed_loop(to_batched(w), w["v_target"], 5, record=True, factored=False)
 torch.cuda.synchronize()
 print("closed loop ok, unsolved", int(unsolved.item()))
 
