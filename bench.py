@@ -505,7 +505,7 @@ def bind_to_gpu_numa_node(local_rank):
             return None
         os.sched_setaffinity(0, cpus)
         return node
-    except (OSError, ValueError, AttributeError):
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):  # no sysfs entry, no driver ...
         return None
 
 
