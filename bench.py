@@ -631,15 +631,16 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler comes up first (nvidia-smi takes a moment), so that nothing idles the GPU
+    # between the W warm-up steps and the K timed ones
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
     for i in range(args.warmup):
         plan = step(i)
     barrier()
     if not loop_cfg:
         assert int((plan.status != 0).sum().item()) == 0, "warm-up batch has unsolved instances"
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
     launches0 = _capi.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
