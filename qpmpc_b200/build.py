@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-Xcompiler", "-fPIC",
 ]
 # tuning experiments: QPMPC_MINB=<resident CTAs/SM> overrides the kernels' default
-for _macro in ("QPMPC_MINB", "QPMPC_MINB_F32", "QPMPC_MINB_PAIRED", "QPMPC_THREADS_PAIRED", "QPMPC_SYNC_TAIL", "QPMPC_LR_MINB", "QPMPC_LR_MINB32", "QPMPC_LR_MINB16", "QPMPC_SEG_REDUX"):
+for _macro in ("QPMPC_MINB", "QPMPC_MINB_F32", "QPMPC_MINB_PAIRED", "QPMPC_THREADS_PAIRED", "QPMPC_SYNC_TAIL", "QPMPC_LR_MINB", "QPMPC_LR_MINB32", "QPMPC_LR_MINB16", "QPMPC_SEG_REDUX", "QPMPC_MINB_PRE"):
     if os.environ.get(_macro):
         NVCC_FLAGS.append(f"-D{_macro}=" + os.environ[_macro])
 

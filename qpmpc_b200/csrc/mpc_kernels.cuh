@@ -48,6 +48,11 @@
 #ifndef QPMPC_MINB_PAIRED
 #define QPMPC_MINB_PAIRED 2
 #endif
+// shared-model variant (PRE), double precision: resident CTAs of 8 warps per SM (3, i.e. 80
+// registers and 224 B of spills, was measured on the fused loops: 501 -> 390, 458 -> 215 M solves/s)
+#ifndef QPMPC_MINB_PRE
+#define QPMPC_MINB_PRE 2
+#endif
 // ... and the largest CTA they are launched with (threads)
 #ifndef QPMPC_THREADS_PAIRED
 #define QPMPC_THREADS_PAIRED 256
@@ -678,7 +683,8 @@ __device__ __forceinline__ T group_max_pos(T v, unsigned segmask) {
 template <typename T, int NP, int MR, bool MREG, bool RS, bool PAIRED = false, bool PRE = false>  // @phase kernel prologue
 __global__ void __launch_bounds__((PAIRED && !PRE && NP <= 16 && sizeof(T) == 8) ? QPMPC_THREADS_PAIRED : 256,
                                   (NP <= 16 && MREG)
-                                      ? (sizeof(T) == 4 ? QPMPC_MINB_F32 : (PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
+                                      ? (sizeof(T) == 4 ? QPMPC_MINB_F32
+                                                        : (PRE ? QPMPC_MINB_PRE : PAIRED ? QPMPC_MINB_PAIRED : QPMPC_MINB / 2))
                                       : 1)
     mpc_solve_kernel(const SolveParams p) {
     using L = Lay<T, NP, MR, MREG, RS, PAIRED, PRE>;
